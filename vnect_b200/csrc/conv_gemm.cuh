@@ -1,0 +1,357 @@
+// Implicit-GEMM convolution for sm_100a: TMA (tiled, 5-D, zero OOB fill = SAME padding) -> 128B/64B-swizzled smem
+// -> tcgen05.mma (fp16 operands, fp32 accumulators in TMEM) -> fused epilogue (bias / folded BN / residual / ReLU).
+//
+// GEMM view: D[M = pixels, N = Cout] = A[M, K] * B[N, K]^T with K = taps * Cin. Activations are NHWC fp16, so A is
+// K-major straight out of HBM; weights are pre-packed [Cout][tap][Cin] (K-major). One K block = one filter tap x
+// BLOCK_K channels = ONE TMA box whose W/H origin is shifted by the tap offset; out-of-image rows/cols are zero
+// filled by the TMA unit, which is exactly TF 'SAME' padding for stride-1 convs.
+//
+// Every conv of src/vnect_model.py:27-214 (reference) maps onto this one kernel:
+//   1x1 convs           flat rows (M = n*H*W), 1 tap
+//   3x3 convs           spatial tiles tw x th (<=128 px) of one image, 9 taps
+//   4x4/2 transposed    4 output phases, each a 2x2-tap conv, epilogue scatters to (2y+py, 2x+px)
+//   conv1 7x7/2, Cin=3  7 row taps; a K block is an 8-pixel x 4-channel window of the padded, parity-split input
+//
+// Warp roles (256 threads, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane quarter = warp % 4). TMEM accumulators are double
+// buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+#pragma once
+#include "ptx.cuh"
+
+namespace vnect {
+
+constexpr int kBlockM = 128;
+constexpr int kGemmThreads = 256;
+
+enum EpiKind : int {
+  EPI_NHWC_F16 = 0,    // fp16 NHWC, bias (+residual) (+ReLU)
+  EPI_PLANAR_F32 = 1,  // fp32 channel-planar [n][c][OH][OW] (heat-map / location-map output, read by the post-process)
+  EPI_DECONV_HEAD = 2  // fused res5c head: BN(folded)+ReLU on cols 0-127, deltas on 128-190, bone lengths -> 191-211
+};
+
+struct ConvGemmParams {
+  // ---- tiling of the GEMM rows
+  int mode;  // 0 = flat rows, 1 = spatial tiles
+  int M;     // valid rows (flat)
+  int NB, H, W;
+  int tw, th, tiles_x, tiles_y;
+  int num_m_tiles, num_n_tiles;
+  int phases;            // 1, or 4 for the transposed conv
+  int taps, cblocks;     // K loop = taps * cblocks blocks of BLOCK_K
+  int b_rows_per_phase;  // padded Cout
+  signed char tap_dx[16], tap_dy[16], tap_dp[16];  // [phase * taps + tap]
+  uint32_t stage_tx_bytes;
+  // ---- epilogue
+  int n_valid;    // valid output columns
+  int relu_cols;  // ReLU on columns < relu_cols (multiple of 32)
+  const float* bias;
+  const __half* residual;
+  int ldr;
+  void* out;
+  int ldc;
+  int OH, OW;    // output grid
+  int oys, oxs;  // output pixel = (y*oys + py, x*oxs + px)
+  int decimate;  // 1: only rows with even (y, x) are stored, at (y/2, x/2) -- feeds the stride-2 1x1 convs
+};
+
+template <int BLOCK_N, int SWZ>
+struct GemmCfg {
+  static constexpr int BLOCK_K = SWZ / 2;  // fp16 elements per smem row
+  static constexpr int A_BYTES = kBlockM * SWZ;
+  static constexpr int B_BYTES = BLOCK_N * SWZ;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
+                                        : (2 * BLOCK_N <= 64)  ? 64
+                                        : (2 * BLOCK_N <= 128) ? 128
+                                        : (2 * BLOCK_N <= 256) ? 256
+                                                               : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "epilogue walks 32-column chunks");
+};
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int BLOCK_N, int SWZ, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ ConvGemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, SWZ>;
+  constexpr int BLOCK_K = Cfg::BLOCK_K;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr uint32_t IDESC = make_idesc_f16(kBlockM, BLOCK_N, false);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.phases * p.num_m_tiles * p.num_n_tiles;
+  const int k_iters = p.taps * p.cblocks;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.num_n_tiles;
+        const int rest = tile / p.num_n_tiles;
+        const int m_tile = rest % p.num_m_tiles;
+        const int ph = rest / p.num_m_tiles;
+        int cx, cy, cn;
+        if (p.mode == 0) {
+          cx = m_tile * kBlockM;
+          cy = 0;
+          cn = 0;
+        } else {
+          const int per_img = p.tiles_x * p.tiles_y;
+          cn = m_tile / per_img;
+          const int t2 = m_tile - cn * per_img;
+          cy = (t2 / p.tiles_x) * p.th;
+          cx = (t2 % p.tiles_x) * p.tw;
+        }
+        const int b_row = ph * p.b_rows_per_phase + n_tile * BLOCK_N;
+        for (int t = 0; t < p.taps; ++t) {
+          const int ti = ph * p.taps + t;
+          const int ax = cx + p.tap_dx[ti], ay = cy + p.tap_dy[ti], ap = p.tap_dp[ti];
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            tma_load_5d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
+            tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (single thread)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < k_iters; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            umma_f16(d_tmem, make_kmajor_desc<SWZ>(a_addr + k * 32), make_kmajor_desc<SWZ>(b_addr + k * 32), IDESC,
+                     (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================ epilogue (4 warps = 128 TMEM lanes = 128 rows)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row of the tile owned by this thread
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      const int rest = tile / p.num_n_tiles;
+      const int m_tile = rest % p.num_m_tiles;
+      const int ph = rest / p.num_m_tiles;
+      bool valid;
+      int n, y, x;
+      if (p.mode == 0) {
+        const int m = m_tile * kBlockM + r;
+        valid = m < p.M;
+        const int hw = p.H * p.W;
+        n = m / hw;
+        const int rem = m - n * hw;
+        y = rem / p.W;
+        x = rem - y * p.W;
+      } else {
+        const int per_img = p.tiles_x * p.tiles_y;
+        n = m_tile / per_img;
+        const int t2 = m_tile - n * per_img;
+        const int ly = r / p.tw, lx = r - ly * p.tw;
+        y = (t2 / p.tiles_x) * p.th + ly;
+        x = (t2 % p.tiles_x) * p.tw + lx;
+        valid = (ly < p.th) && (y < p.H) && (x < p.W);
+      }
+      int oy, ox;
+      if (p.decimate) {
+        valid = valid && !((y | x) & 1);
+        oy = y >> 1;
+        ox = x >> 1;
+      } else {
+        oy = y * p.oys + (ph >> 1);
+        ox = x * p.oxs + (ph & 1);
+      }
+      const size_t pix = (static_cast<size_t>(n) * p.OH + oy) * p.OW + ox;
+      const size_t rpix = (static_cast<size_t>(n) * p.H + y) * p.W + x;  // residual lives on the GEMM-row grid
+      const int col_base = n_tile * BLOCK_N;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+
+      float bone[21];
+      if constexpr (EPI == EPI_DECONV_HEAD) {
+#pragma unroll
+        for (int j = 0; j < 21; ++j) bone[j] = 0.f;
+      }
+
+#pragma unroll
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + c0, v);
+        tmem_ld_wait();
+        const int col0 = col_base + c0;
+        float f[32];
+        if (p.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(bp + j);
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        }
+        if constexpr (EPI == EPI_PLANAR_F32) {
+          if (valid) {
+            float* o = reinterpret_cast<float*>(p.out);
+            const size_t plane = static_cast<size_t>(p.OH) * p.OW;
+            const size_t base = static_cast<size_t>(n) * p.n_valid * plane + static_cast<size_t>(oy) * p.OW + ox;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < p.n_valid) o[base + static_cast<size_t>(col0 + j) * plane] = f[j];
+            }
+          }
+        } else {
+          if (valid) {
+            if (p.residual != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + rpix * p.ldr + col0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 rv = __ldg(rp + j);
+                const __half2* h = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __half22float2(h[e]);
+                  f[8 * j + 2 * e] += t.x;
+                  f[8 * j + 2 * e + 1] += t.y;
+                }
+              }
+            }
+            if (col0 < p.relu_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if constexpr (EPI == EPI_DECONV_HEAD) {
+              // columns 128..190 are the 63 (dx, dy, dz) deltas; bone_j = sqrt(dx_j^2 + dy_j^2 + dz_j^2)
+              // (reference: src/vnect_model.py:198-205)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;  // compile-time after unrolling (single N tile)
+                if (c >= 128 && c < 191) bone[(c - 128) % 21] += f[j] * f[j];
+              }
+            }
+            uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + pix * p.ldc + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_half2(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_half2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_half2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_half2(f[8 * j + 6], f[8 * j + 7]);
+              op[j] = o;
+            }
+          }
+        }
+      }
+      if constexpr (EPI == EPI_DECONV_HEAD) {
+        if (valid) {
+          __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldc;
+          float b[26];
+#pragma unroll
+          for (int j = 0; j < 21; ++j) b[j] = sqrtf(bone[j]);
+          b[21] = b[22] = b[23] = b[24] = b[25] = 0.f;
+          o[191] = __float2half_rn(b[0]);  // overwrites the zero pad column written by the generic store above
+          uint4* op = reinterpret_cast<uint4*>(o + 192);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            uint4 w;
+            w.x = pack_half2(b[1 + 8 * j + 0], b[1 + 8 * j + 1]);
+            w.y = pack_half2(b[1 + 8 * j + 2], b[1 + 8 * j + 3]);
+            w.z = pack_half2(b[1 + 8 * j + 4], b[1 + 8 * j + 5]);
+            w.w = (j < 2) ? pack_half2(b[1 + 8 * j + 6], b[1 + 8 * j + 7]) : 0u;
+            op[j] = w;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace vnect

@@ -1,0 +1,263 @@
+// Host side of the implicit-GEMM convolution: tensor-map construction, tile-shape choice and launch.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "conv_gemm.cuh"
+
+namespace vnect {
+
+// ---------------------------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is fetched through the runtime so the library has no link-time dependency on libcuda
+// (it must dlopen on a CPU-only box for the symbol-export test).
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+inline bool encode_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                        const uint32_t* box, int swz_bytes, std::string* err) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    if (err) *err = "cuTensorMapEncodeTiled entry point unavailable";
+    return false;
+  }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUtensorMapSwizzle sw = swz_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swz_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                            : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) {
+      char buf[256];
+      snprintf(buf, sizeof buf,
+               "cuTensorMapEncodeTiled failed (%d): rank %d dims[%llu %llu %llu ...] box[%u %u %u ...] stride0 %llu",
+               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+               (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+               (unsigned long long)strides_bytes[0]);
+      *err = buf;
+    }
+    return false;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+enum ConvKind : int { CONV_1x1 = 0, CONV_3x3 = 1, CONV_DECONV4 = 2, CONV_STEM7 = 3 };
+
+struct ConvSpec {
+  int kind = CONV_1x1;
+  // GEMM-row grid (= conv output grid before the phase scatter); for CONV_STEM7 this is the 184x184 output grid
+  int NB = 1, H = 1, W = 1;
+  const __half* in = nullptr;  // NHWC fp16 activation [NB,H,W,cin_pad]; CONV_STEM7: parity-split padded input
+  int cin_pad = 64;            // channels per pixel of `in` (multiple of 64); CONV_STEM7: ignored
+  // CONV_STEM7 input geometry: [NB][2 parities][rows_per_parity][row_pitch_elems]
+  int stem_rows_per_parity = 0, stem_row_pitch = 0;
+  const __half* w = nullptr;  // packed [phases * n_pad][taps * cin_pad] fp16, K-major
+  int n_pad = 64;             // padded Cout (multiple of block_n)
+  int n_valid = 64;
+  int block_n = 64;
+  const float* bias = nullptr;  // [n_pad] fp32 or null
+  int relu_cols = 0;
+  const __half* residual = nullptr;
+  int ldr = 0;
+  void* out = nullptr;
+  int ldc = 0;
+  int epi = EPI_NHWC_F16;
+  int decimate = 0;
+};
+
+struct ConvLaunch {
+  CUtensorMap tmap_a, tmap_b;
+  ConvGemmParams p;
+  int block_n = 0, swz = 128, epi = 0, grid = 0;
+  size_t smem = 0;
+  double flops = 0;  // algorithmic: 2 * valid rows * n_valid * taps * real Cin is tracked by the caller; this is GEMM work
+};
+
+inline void choose_tile(int H, int W, int* tw_out, int* th_out) {
+  int best_tiles = 1 << 30, btw = 1, bth = 1;
+  for (int tw = 1; tw <= (W < 128 ? W : 128); ++tw) {
+    int th = 128 / tw;
+    if (th > H) th = H;
+    if (th < 1) continue;
+    int tiles = ((W + tw - 1) / tw) * ((H + th - 1) / th);
+    if (tiles < best_tiles || (tiles == best_tiles && tw > btw)) {
+      best_tiles = tiles;
+      btw = tw;
+      bth = th;
+    }
+  }
+  *tw_out = btw;
+  *th_out = bth;
+}
+
+inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::string* err) {
+  memset(L, 0, sizeof(*L));
+  ConvGemmParams& p = L->p;
+  const int swz = (s.kind == CONV_STEM7) ? 64 : 128;
+  const int block_k = swz / 2;
+  L->swz = swz;
+  L->block_n = s.block_n;
+  L->epi = s.epi;
+  if (s.n_pad % s.block_n != 0) {
+    if (err) *err = "n_pad must be a multiple of block_n";
+    return false;
+  }
+  p.NB = s.NB;
+  p.H = s.H;
+  p.W = s.W;
+  p.M = s.NB * s.H * s.W;
+  p.phases = 1;
+  p.b_rows_per_phase = s.n_pad;
+  p.num_n_tiles = s.n_pad / s.block_n;
+  p.n_valid = s.n_valid;
+  p.relu_cols = s.relu_cols;
+  p.bias = s.bias;
+  p.residual = s.residual;
+  p.ldr = s.ldr;
+  p.out = s.out;
+  p.ldc = s.ldc;
+  p.decimate = s.decimate;
+  p.OH = s.decimate ? s.H / 2 : s.H;
+  p.OW = s.decimate ? s.W / 2 : s.W;
+  p.oys = p.oxs = 1;
+
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  int k_total;
+  if (s.kind == CONV_1x1) {
+    p.mode = 0;
+    p.taps = 1;
+    p.cblocks = s.cin_pad / block_k;
+    p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
+    p.tw = kBlockM;
+    p.th = 1;
+    p.tiles_x = p.tiles_y = 1;
+    dims[0] = s.cin_pad; dims[1] = p.M; dims[2] = 1; dims[3] = 1; dims[4] = 1;
+    strides[0] = (uint64_t)s.cin_pad * 2;
+    strides[1] = strides[2] = strides[3] = (uint64_t)s.cin_pad * 2 * p.M;
+    box[0] = block_k; box[1] = kBlockM; box[2] = 1; box[3] = 1; box[4] = 1;
+    k_total = s.cin_pad;
+  } else if (s.kind == CONV_3x3 || s.kind == CONV_DECONV4) {
+    p.mode = 1;
+    choose_tile(s.H, s.W, &p.tw, &p.th);
+    p.tiles_x = (s.W + p.tw - 1) / p.tw;
+    p.tiles_y = (s.H + p.th - 1) / p.th;
+    p.num_m_tiles = s.NB * p.tiles_x * p.tiles_y;
+    p.cblocks = s.cin_pad / block_k;
+    if (s.kind == CONV_3x3) {
+      p.taps = 9;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          p.tap_dy[ky * 3 + kx] = (signed char)(ky - 1);
+          p.tap_dx[ky * 3 + kx] = (signed char)(kx - 1);
+          p.tap_dp[ky * 3 + kx] = 0;
+        }
+    } else {
+      // 4x4 stride-2 'SAME' transposed conv: output (2j+py, 2i+px); per axis, phase 0 uses kernel taps {1,3} at
+      // input offsets {0,-1}, phase 1 uses taps {0,2} at offsets {+1,0}. Tap order here must
+      // match pack_deconv_weights(): tap = a*2 + b with a the row choice, b the column choice.
+      p.taps = 4;
+      p.phases = 4;
+      p.oys = p.oxs = 2;
+      p.OH = 2 * s.H;
+      p.OW = 2 * s.W;
+      for (int ph = 0; ph < 4; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            const int dy = py == 0 ? (a == 0 ? 0 : -1) : (a == 0 ? 1 : 0);
+            const int dx = px == 0 ? (b == 0 ? 0 : -1) : (b == 0 ? 1 : 0);
+            p.tap_dy[ph * 4 + a * 2 + b] = (signed char)dy;
+            p.tap_dx[ph * 4 + a * 2 + b] = (signed char)dx;
+            p.tap_dp[ph * 4 + a * 2 + b] = 0;
+          }
+      }
+    }
+    dims[0] = s.cin_pad; dims[1] = s.W; dims[2] = s.H; dims[3] = 1; dims[4] = s.NB;
+    strides[0] = (uint64_t)s.cin_pad * 2;
+    strides[1] = strides[0] * s.W;
+    strides[2] = strides[1] * s.H;
+    strides[3] = strides[2];
+    box[0] = block_k; box[1] = p.tw; box[2] = p.th; box[3] = 1; box[4] = 1;
+    k_total = p.taps * s.cin_pad;
+  } else {  // CONV_STEM7
+    p.mode = 1;
+    choose_tile(s.H, s.W, &p.tw, &p.th);
+    p.tiles_x = (s.W + p.tw - 1) / p.tw;
+    p.tiles_y = (s.H + p.th - 1) / p.th;
+    p.num_m_tiles = s.NB * p.tiles_x * p.tiles_y;
+    p.cblocks = 1;
+    p.taps = 7;
+    for (int ky = 0; ky < 7; ++ky) {
+      p.tap_dy[ky] = (signed char)(ky >> 1);
+      p.tap_dx[ky] = 0;
+      p.tap_dp[ky] = (signed char)(ky & 1);
+    }
+    // window of 8 px x 4 ch (32 elements) per output column, consecutive output columns 2 px = 16 B apart
+    dims[0] = 32; dims[1] = s.W; dims[2] = s.stem_rows_per_parity; dims[3] = 2; dims[4] = s.NB;
+    strides[0] = 16;
+    strides[1] = (uint64_t)s.stem_row_pitch * 2;
+    strides[2] = strides[1] * s.stem_rows_per_parity;
+    strides[3] = strides[2] * 2;
+    box[0] = 32; box[1] = p.tw; box[2] = p.th; box[3] = 1; box[4] = 1;
+    k_total = 7 * 32;
+  }
+  p.stage_tx_bytes = (uint32_t)(box[0] * box[1] * box[2] * 2 + (uint32_t)s.block_n * block_k * 2);
+  if (!encode_tmap(&L->tmap_a, s.in, 5, dims, strides, box, swz, err)) return false;
+  uint64_t bd[2] = {(uint64_t)k_total, (uint64_t)p.phases * s.n_pad};
+  uint64_t bs[1] = {(uint64_t)k_total * 2};
+  uint32_t bb[2] = {(uint32_t)block_k, (uint32_t)s.block_n};
+  if (!encode_tmap(&L->tmap_b, s.w, 2, bd, bs, bb, swz, err)) return false;
+  const int total = p.phases * p.num_m_tiles * p.num_n_tiles;
+  L->grid = total < num_sms ? total : num_sms;
+  L->flops = 2.0 * p.phases * (double)p.M * s.n_pad * k_total;
+  return true;
+}
+
+template <int BLOCK_N, int SWZ, int EPI>
+inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
+  using Cfg = GemmCfg<BLOCK_N, SWZ>;
+  static bool attr_set = false;
+  auto kern = conv_gemm_kernel<BLOCK_N, SWZ, EPI>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  kern<<<L.grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(L.tmap_a, L.tmap_b, L.p);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
+  if (L.swz == 64 && L.block_n == 64 && L.epi == EPI_NHWC_F16) return launch_one<64, 64, EPI_NHWC_F16>(L, st);
+  if (L.swz == 128 && L.epi == EPI_NHWC_F16) {
+    if (L.block_n == 64) return launch_one<64, 128, EPI_NHWC_F16>(L, st);
+    if (L.block_n == 128) return launch_one<128, 128, EPI_NHWC_F16>(L, st);
+    if (L.block_n == 256) return launch_one<256, 128, EPI_NHWC_F16>(L, st);
+  }
+  if (L.swz == 128 && L.epi == EPI_PLANAR_F32 && L.block_n == 96) return launch_one<96, 128, EPI_PLANAR_F32>(L, st);
+  if (L.swz == 128 && L.epi == EPI_DECONV_HEAD && L.block_n == 192)
+    return launch_one<192, 128, EPI_DECONV_HEAD>(L, st);
+  return cudaErrorInvalidConfiguration;
+}
+
+}  // namespace vnect

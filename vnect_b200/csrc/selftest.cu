@@ -1,0 +1,277 @@
+// GPU self-test of the tcgen05 implicit-GEMM convolution kernel against a naive direct convolution written with
+// plain CUDA loops (test infrastructure only; never linked into libvnect_b200.so).
+//   build: make -C vnect_b200/csrc selftest      run (on a B200): build/selftest
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "conv_plan.cuh"
+
+using namespace vnect;
+
+#define CK(x)                                                                              \
+  do {                                                                                     \
+    cudaError_t e_ = (x);                                                                  \
+    if (e_ != cudaSuccess) {                                                               \
+      printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      exit(2);                                                                             \
+    }                                                                                      \
+  } while (0)
+
+struct NaiveGeom {
+  int kind, NB, H, W, cin_pad, n_pad, taps, phases, k_total;
+  int stem_rpp, stem_pitch;
+  signed char dx[16], dy[16], dp[16];
+};
+
+// raw fp32 accumulators acc[ph][m][col]
+__global__ void naive_acc_kernel(const __half* __restrict__ in, const __half* __restrict__ w, float* __restrict__ acc,
+                                 NaiveGeom g) {
+  const long long total = (long long)g.phases * g.NB * g.H * g.W * g.n_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % g.n_pad);
+    long long r = i / g.n_pad;
+    const int x = (int)(r % g.W);
+    r /= g.W;
+    const int y = (int)(r % g.H);
+    r /= g.H;
+    const int n = (int)(r % g.NB);
+    const int ph = (int)(r / g.NB);
+    const __half* wrow = w + ((size_t)ph * g.n_pad + col) * g.k_total;
+    float s = 0.f;
+    for (int t = 0; t < g.taps; ++t) {
+      const int ti = ph * g.taps + t;
+      if (g.kind == CONV_STEM7) {
+        const int row = y + g.dy[ti];
+        if (row < 0 || row >= g.stem_rpp) continue;
+        const __half* a = in + (((size_t)n * 2 + g.dp[ti]) * g.stem_rpp + row) * g.stem_pitch + (size_t)x * 8;
+        for (int c = 0; c < 32; ++c) s += __half2float(a[c]) * __half2float(wrow[t * 32 + c]);
+      } else {
+        const int yy = y + g.dy[ti], xx = x + g.dx[ti];
+        if (yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) continue;
+        const __half* a = in + (((size_t)n * g.H + yy) * g.W + xx) * g.cin_pad;
+        for (int c = 0; c < g.cin_pad; ++c) s += __half2float(a[c]) * __half2float(wrow[(size_t)t * g.cin_pad + c]);
+      }
+    }
+    acc[i] = s;
+  }
+}
+
+static uint32_t rng_state = 12345u;
+static float frand() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return ((rng_state >> 8) & 0xFFFF) / 32768.0f - 1.0f;
+}
+
+struct Case {
+  const char* name;
+  int kind, NB, H, W, cin_pad, n_pad, n_valid, block_n, epi;
+  bool bias, residual;
+  int relu_cols, decimate;
+};
+
+static int run_case(const Case& c, int num_sms, bool timing) {
+  ConvSpec s;
+  s.kind = c.kind;
+  s.NB = c.NB;
+  s.H = c.H;
+  s.W = c.W;
+  s.cin_pad = c.cin_pad;
+  s.n_pad = c.n_pad;
+  s.n_valid = c.n_valid;
+  s.block_n = c.block_n;
+  s.epi = c.epi;
+  s.relu_cols = c.relu_cols;
+  s.decimate = c.decimate;
+  const int phases = c.kind == CONV_DECONV4 ? 4 : 1;
+  const int taps = c.kind == CONV_1x1 ? 1 : c.kind == CONV_3x3 ? 9 : c.kind == CONV_DECONV4 ? 4 : 7;
+  const int k_total = c.kind == CONV_STEM7 ? 7 * 32 : taps * c.cin_pad;
+  size_t in_elems;
+  int rpp = 0, pitch = 0;
+  if (c.kind == CONV_STEM7) {
+    rpp = c.H + 3;
+    pitch = (2 * c.W + 6) * 4;
+    in_elems = (size_t)c.NB * 2 * rpp * pitch;
+    s.stem_rows_per_parity = rpp;
+    s.stem_row_pitch = pitch;
+  } else {
+    in_elems = (size_t)c.NB * c.H * c.W * c.cin_pad;
+  }
+  std::vector<__half> h_in(in_elems), h_w((size_t)phases * c.n_pad * k_total);
+  for (auto& v : h_in) v = __float2half(frand());
+  const float wscale = 1.0f / sqrtf((float)k_total);
+  for (auto& v : h_w) v = __float2half(frand() * wscale * 2.f);
+  std::vector<float> h_bias(c.n_pad);
+  for (auto& v : h_bias) v = frand() * 0.5f;
+
+  int OH = c.H, OW = c.W;
+  if (c.kind == CONV_DECONV4) { OH = 2 * c.H; OW = 2 * c.W; }
+  if (c.decimate) { OH = c.H / 2; OW = c.W / 2; }
+  const int ldc = c.epi == EPI_DECONV_HEAD ? 256 : c.n_pad;
+  const size_t out_elems = c.epi == EPI_PLANAR_F32 ? (size_t)c.NB * c.n_valid * OH * OW : (size_t)c.NB * OH * OW * ldc;
+  const size_t out_bytes = out_elems * (c.epi == EPI_PLANAR_F32 ? 4 : 2);
+  const int ldr = c.n_pad;
+  std::vector<__half> h_res;
+  if (c.residual) {
+    h_res.resize((size_t)c.NB * c.H * c.W * ldr);
+    for (auto& v : h_res) v = __float2half(frand());
+  }
+
+  __half *d_in, *d_w, *d_res = nullptr;
+  float *d_bias, *d_acc;
+  void* d_out;
+  CK(cudaMalloc(&d_in, in_elems * 2));
+  CK(cudaMalloc(&d_w, h_w.size() * 2));
+  CK(cudaMalloc(&d_bias, c.n_pad * 4));
+  CK(cudaMalloc(&d_out, out_bytes));
+  CK(cudaMemset(d_out, 0, out_bytes));
+  const size_t acc_elems = (size_t)phases * c.NB * c.H * c.W * c.n_pad;
+  CK(cudaMalloc(&d_acc, acc_elems * 4));
+  CK(cudaMemcpy(d_in, h_in.data(), in_elems * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_w, h_w.data(), h_w.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_bias, h_bias.data(), c.n_pad * 4, cudaMemcpyHostToDevice));
+  if (c.residual) {
+    CK(cudaMalloc(&d_res, h_res.size() * 2));
+    CK(cudaMemcpy(d_res, h_res.data(), h_res.size() * 2, cudaMemcpyHostToDevice));
+  }
+  s.in = d_in;
+  s.w = d_w;
+  s.bias = c.bias ? d_bias : nullptr;
+  s.residual = d_res;
+  s.ldr = ldr;
+  s.out = d_out;
+  s.ldc = ldc;
+
+  ConvLaunch L;
+  std::string err;
+  if (!build_conv(s, num_sms, &L, &err)) {
+    printf("[%s] build_conv FAILED: %s\n", c.name, err.c_str());
+    return 1;
+  }
+  CK(launch_conv(L, 0));
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) {
+    printf("[%s] kernel FAILED: %s\n", c.name, cudaGetErrorString(se));
+    exit(3);  // context is gone
+  }
+
+  NaiveGeom g;
+  g.kind = c.kind; g.NB = c.NB; g.H = c.H; g.W = c.W; g.cin_pad = c.cin_pad; g.n_pad = c.n_pad;
+  g.taps = taps; g.phases = phases; g.k_total = k_total; g.stem_rpp = rpp; g.stem_pitch = pitch;
+  memcpy(g.dx, L.p.tap_dx, 16); memcpy(g.dy, L.p.tap_dy, 16); memcpy(g.dp, L.p.tap_dp, 16);
+  naive_acc_kernel<<<1184, 256>>>(d_in, d_w, d_acc, g);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> h_acc(acc_elems);
+  CK(cudaMemcpy(h_acc.data(), d_acc, acc_elems * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint8_t> h_out(out_bytes);
+  CK(cudaMemcpy(h_out.data(), d_out, out_bytes, cudaMemcpyDeviceToHost));
+  const __half* o16 = reinterpret_cast<const __half*>(h_out.data());
+  const float* o32 = reinterpret_cast<const float*>(h_out.data());
+
+  double max_err = 0;
+  long long bad = 0, checked = 0;
+  auto check = [&](float got, float exp) {
+    const float tol = 3e-3f * fabsf(exp) + 3e-3f;
+    const float e = fabsf(got - exp);
+    if (!(e <= tol)) {
+      if (bad < 5) printf("   mismatch got %f exp %f\n", got, exp);
+      ++bad;
+    }
+    if (e > max_err) max_err = e;
+    ++checked;
+  };
+  for (int ph = 0; ph < phases; ++ph)
+    for (int n = 0; n < c.NB; ++n)
+      for (int y = 0; y < c.H; ++y)
+        for (int x = 0; x < c.W; ++x) {
+          const size_t m = ((size_t)n * c.H + y) * c.W + x;
+          const float* a = &h_acc[((size_t)ph * c.NB * c.H * c.W + m) * c.n_pad];
+          int oy, ox;
+          if (c.decimate) {
+            if ((y | x) & 1) continue;
+            oy = y / 2; ox = x / 2;
+          } else if (c.kind == CONV_DECONV4) {
+            oy = 2 * y + (ph >> 1); ox = 2 * x + (ph & 1);
+          } else {
+            oy = y; ox = x;
+          }
+          const size_t pix = ((size_t)n * OH + oy) * OW + ox;
+          float bone[21] = {0};
+          for (int col = 0; col < c.n_pad; ++col) {
+            float v = a[col] + (c.bias ? h_bias[col] : 0.f);
+            if (c.residual) v += __half2float(h_res[m * ldr + col]);
+            if (col < c.relu_cols) v = fmaxf(v, 0.f);
+            if (c.epi == EPI_PLANAR_F32) {
+              if (col < c.n_valid) check(o32[((size_t)n * c.n_valid + col) * OH * OW + (size_t)oy * OW + ox], v);
+            } else if (c.epi == EPI_DECONV_HEAD) {
+              if (col < 191) check(__half2float(o16[pix * ldc + col]), v);
+              if (col >= 128 && col < 191) bone[(col - 128) % 21] += v * v;
+            } else {
+              check(__half2float(o16[pix * ldc + col]), v);
+            }
+          }
+          if (c.epi == EPI_DECONV_HEAD) {
+            for (int j = 0; j < 21; ++j) check(__half2float(o16[pix * ldc + 191 + j]), sqrtf(bone[j]));
+            for (int j = 212; j < 216; ++j) check(__half2float(o16[pix * ldc + j]), 0.f);
+          }
+        }
+  printf("[%s] tiles=%d grid=%d tile=%dx%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n", c.name,
+         L.p.phases * L.p.num_m_tiles * L.p.num_n_tiles, L.grid, L.p.tw, L.p.th, checked, bad, max_err,
+         bad == 0 ? "PASS" : "FAIL");
+
+  if (timing && bad == 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CK(launch_conv(L, 0));
+    CK(cudaEventRecord(e0));
+    const int reps = 20;
+    for (int i = 0; i < reps; ++i) CK(launch_conv(L, 0));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double us = ms * 1000.0 / reps;
+    printf("   timing: %.2f us/launch, %.1f TFLOP/s (GEMM flops incl. padding)\n", us, L.flops / us * 1e-6);
+  }
+  cudaFree(d_in); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_out); cudaFree(d_acc);
+  if (d_res) cudaFree(d_res);
+  return bad == 0 ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  printf("device: %s, SMs %d, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
+  const int sms = prop.multiProcessorCount;
+  const bool big = argc > 1 && atoi(argv[1]) > 0;
+  std::vector<Case> cases = {
+      {"1x1 64->64 relu 92x92", CONV_1x1, 2, 92, 92, 64, 64, 64, 64, EPI_NHWC_F16, true, false, 64, 0},
+      {"1x1 256->512 +res relu 46x46", CONV_1x1, 4, 46, 46, 256, 512, 512, 256, EPI_NHWC_F16, true, true, 512, 0},
+      {"1x1 1024->256 relu 23x23 bn128", CONV_1x1, 8, 23, 23, 1024, 256, 256, 128, EPI_NHWC_F16, true, false, 256, 0},
+      {"1x1 64->256 +res relu decimate", CONV_1x1, 2, 92, 92, 64, 256, 256, 256, EPI_NHWC_F16, true, true, 256, 1},
+      {"3x3 64->64 relu 92x92", CONV_3x3, 2, 92, 92, 64, 64, 64, 64, EPI_NHWC_F16, true, false, 64, 0},
+      {"3x3 256->256 relu 23x23", CONV_3x3, 3, 23, 23, 256, 256, 256, 128, EPI_NHWC_F16, true, false, 256, 0},
+      {"3x3 128->128 relu 46x46", CONV_3x3, 1, 46, 46, 128, 128, 128, 128, EPI_NHWC_F16, true, false, 128, 0},
+      {"deconv4x4s2 256->192 head 23x23", CONV_DECONV4, 2, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false,
+       128, 0},
+      {"1x1 128->84 planar f32 46x46", CONV_1x1, 2, 46, 46, 128, 96, 84, 96, EPI_PLANAR_F32, false, false, 0, 0},
+      {"stem 7x7s2 3->64 relu 184x184", CONV_STEM7, 2, 184, 184, 0, 64, 64, 64, EPI_NHWC_F16, true, false, 64, 0},
+  };
+  int fails = 0;
+  for (const auto& c : cases) fails += run_case(c, sms, true);
+  if (big) {
+    std::vector<Case> bigc = {
+        {"BIG 1x1 1024->1024 23x23 nb128", CONV_1x1, 128, 23, 23, 1024, 1024, 1024, 256, EPI_NHWC_F16, true, false,
+         1024, 0},
+        {"BIG 3x3 512->512 23x23 nb64", CONV_3x3, 64, 23, 23, 512, 512, 512, 256, EPI_NHWC_F16, true, false, 512, 0},
+        {"BIG 3x3 64->64 92x92 nb32", CONV_3x3, 32, 92, 92, 64, 64, 64, 64, EPI_NHWC_F16, true, false, 64, 0},
+        {"BIG 1x1 256->64 92x92 nb32", CONV_1x1, 32, 92, 92, 256, 64, 64, 64, EPI_NHWC_F16, true, false, 64, 0},
+    };
+    for (const auto& c : bigc) fails += run_case(c, sms, true);
+  }
+  printf("SELFTEST %s (%d failing cases)\n", fails == 0 ? "PASSED" : "FAILED", fails);
+  return fails == 0 ? 0 : 1;
+}
