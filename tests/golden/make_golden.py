@@ -1,0 +1,140 @@
+#!/usr/bin/env python3
+"""Mint the golden fixtures of tests/golden/ by running the reference's OWN code (dev container only).
+
+    python tests/golden/make_golden.py
+
+Needs /root/reference (read-only).  The reference's ``src/utils.py``, ``src/OneEuroFilter.py`` and ``src/estimator.py``
+are imported unchanged through ``oracle.ref_shim``; TensorFlow is replaced by a stub whose ``Session.run`` returns
+either seeded synthetic maps (post-processing fixtures, machine independent) or ``oracle.forward.OracleNet`` output
+(end-to-end fixtures).  Library versions are recorded in every file.
+
+Fixtures (all small):
+  pre.npz     gen_input_batch (estimator.py:70-81): sha256 of the float32 batch + scaler/offsets per case
+  post.npz    multi-frame VNectEstimator.__call__ on synthetic maps: joints_2d / joints_3d per frame
+  filter.npz  OneEuroFilter on a seeded noisy signal (float64), irregular timestamps
+  e2e.npz     VNectEstimator.__call__ with the CNN restatement (W0) on test_pic + synthetic frames
+  test_pic.npz  decoded pixels of pic/test_pic.jpg (C1 input; the GPU box has no reference tree)
+"""
+import hashlib
+import os
+import sys
+
+import cv2
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim, synth  # noqa: E402
+from oracle.forward import OracleNet  # noqa: E402
+from oracle.weights import make_weights  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+VERSIONS = dict(cv2=cv2.__version__, numpy=np.__version__)
+
+PRE_CASES = [  # (name, H, W, seed, scales)
+    ("square368", 368, 368, 11, [1.0, 0.7]),
+    ("square368_3s", 368, 368, 12, [1, 0.85, 0.7]),
+    ("wide960x540", 540, 960, 13, [1.0, 0.7]),
+    ("tall300x200", 300, 200, 14, [1, 0.85, 0.7]),
+    ("small100x180", 100, 180, 15, [1.0, 0.7]),
+    ("half736", 736, 736, 16, [1.0]),
+    ("odd367x251", 367, 251, 17, [1.0, 0.7]),
+]
+POST_CASES = [  # (name, seed, scales, n_frames, dt pattern)
+    ("s2_border", 101, [1.0, 0.7], 6, "regular30"),
+    ("s3_default", 102, [1, 0.85, 0.7], 5, "irregular"),
+    ("s1_single", 103, [1.0], 4, "regular25"),
+    ("s2_interior", 104, [1.0, 0.7], 5, "irregular"),
+]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def timestamps(pattern, n, seed):
+    if pattern == "regular30":
+        t = 1000 + np.arange(n) / 30.0
+    elif pattern == "regular25":
+        t = 1000 + np.arange(n) / 25.0
+    else:
+        t = 1000 + np.cumsum(np.random.default_rng(seed).uniform(0.01, 0.09, n))
+    return t, t + 0.004  # 2D-group and 3D-group clock readings
+
+
+def post_frame_maps(seed, k, scales):
+    """Frame k of a synthetic map stream: blob centres drift with k so the filters see motion."""
+    return synth.synthetic_maps(seed * 100 + k, len(scales), border_joints=(k % 2 == 0))
+
+
+def main():
+    assert ref_shim.reference_available(), "run in the dev container (needs /root/reference)"
+    utils, oef, est_mod = ref_shim.load_reference_modules()
+
+    # ---- pre.npz
+    pre = dict(versions=str(VERSIONS))
+    for name, h, w, seed, scales in PRE_CASES:
+        img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        batch, scaler, (ox, oy) = est_mod.VNectEstimator.gen_input_batch(img, 368, scales)
+        pre[name + "/sha"] = sha(batch)
+        pre[name + "/meta"] = np.array([scaler, ox, oy], np.float64)
+        pre[name + "/sample"] = batch[:, ::37, ::41, :].copy()
+    np.savez_compressed(os.path.join(OUT, "pre.npz"), **pre)
+
+    # ---- filter.npz
+    rng = np.random.default_rng(5)
+    n = 200
+    t = 10.0 + np.cumsum(rng.uniform(0.005, 0.08, n))
+    sig = np.sin(t * 3.0) * 50 + rng.standard_normal(n) * 2
+    f2 = oef.OneEuroFilter(freq=30, mincutoff=1.7, beta=0.3, dcutoff=0.4)
+    f3 = oef.OneEuroFilter(freq=30, mincutoff=0.8, beta=0.4, dcutoff=0.4)
+    np.savez_compressed(os.path.join(OUT, "filter.npz"), t=t, x=sig,
+                        y2=np.array([f2(float(x), float(tt)) for x, tt in zip(sig, t)]),
+                        y3=np.array([f3(float(x), float(tt)) for x, tt in zip(sig, t)]), versions=str(VERSIONS))
+
+    # ---- post.npz
+    post = dict(versions=str(VERSIONS))
+    for name, seed, scales, nf, pat in POST_CASES:
+        state = {}
+        est, em = ref_shim.make_reference_estimator(lambda batch: state["maps"], scales)
+        t2, t3 = timestamps(pat, nf, seed)
+        img = np.zeros((368, 368, 3), np.uint8)
+        j2s, j3s = [], []
+        for k in range(nf):
+            state["maps"] = post_frame_maps(seed, k, scales)
+            j2, j3 = ref_shim.run_reference(est, em, img, float(t2[k]), float(t3[k]))
+            j2s.append(j2.copy())
+            j3s.append(j3.copy())
+        post[name + "/j2"] = np.array(j2s)
+        post[name + "/j3"] = np.array(j3s)
+        post[name + "/t2"] = t2
+        post[name + "/t3"] = t3
+    np.savez_compressed(os.path.join(OUT, "post.npz"), **post)
+
+    # ---- test_pic.npz + e2e.npz
+    pic = cv2.imread(os.path.join(ref_shim.REFERENCE_ROOT, "pic", "test_pic.jpg"))
+    np.savez_compressed(os.path.join(OUT, "test_pic.npz"), img=pic)
+    net = OracleNet(make_weights("W0"))
+    e2e = dict(versions=str(VERSIONS))
+    est, em = ref_shim.make_reference_estimator(net, [1.0])  # C1: run_pic-like, single scale
+    j2, j3 = ref_shim.run_reference(est, em, pic, 1000.0, 1000.004)
+    e2e["c1/j2"], e2e["c1/j3"] = j2, j3
+    est, em = ref_shim.make_reference_estimator(net, [1.0, 0.7])  # C2-like: independent frames, fresh filters each
+    for i in range(3):
+        est, em = ref_shim.make_reference_estimator(net, [1.0, 0.7])
+        j2, j3 = ref_shim.run_reference(est, em, synth.frame_c2(i), 1000.0, 1000.004)
+        e2e[f"c2_{i}/j2"], e2e[f"c2_{i}/j3"] = j2, j3
+    est, em = ref_shim.make_reference_estimator(net, [1.0, 0.7])  # C4-like: one stream, 4 frames, filters live
+    j2s, j3s = [], []
+    for k in range(4):
+        j2, j3 = ref_shim.run_reference(est, em, synth.stream_frame(0, k), 1000 + k / 30, 1000 + k / 30 + 0.004)
+        j2s.append(j2.copy())
+        j3s.append(j3.copy())
+    e2e["c4/j2"], e2e["c4/j3"] = np.array(j2s), np.array(j3s)
+    np.savez_compressed(os.path.join(OUT, "e2e.npz"), **e2e)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
