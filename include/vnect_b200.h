@@ -1,0 +1,118 @@
+/* vnect_b200 -- C ABI of the B200-native VNect per-frame hot path.
+ *
+ * The reference (XinArkh/VNect) has no FFI of its own: its seam is the Python class `VNectEstimator`
+ * (src/estimator.py:16-142) on top of a TensorFlow session looked up by tensor name (src/estimator.py:62-66).
+ * Each entry point below names the reference interface it replaces.  Plain pointers and sizes only; every buffer
+ * passed in or out is owned by the caller, the handle owns device weights, workspaces and per-stream filter state.
+ * All functions return 0 on success or a negative VNECT_E_* code; vnect_last_error() gives the message.
+ * One handle = one device + one CUDA stream; a handle is not thread-safe (neither is the reference object).
+ */
+#ifndef VNECT_B200_H
+#define VNECT_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VNECT_OK 0
+#define VNECT_E_INVALID (-1)      /* bad argument / wrong call order */
+#define VNECT_E_CUDA (-2)         /* CUDA runtime or driver error, incl. no usable sm_100 device */
+#define VNECT_E_WEIGHT (-3)       /* unknown variable name, wrong shape, or missing variable at finalize */
+#define VNECT_E_ZERO_DT (-4)      /* repeated timestamp for a stream: the reference raises ZeroDivisionError
+                                     (src/OneEuroFilter.py:66) */
+#define VNECT_E_UNSUPPORTED (-5)
+
+#define VNECT_JOINTS 21
+#define VNECT_MAX_SCALES 4
+
+typedef struct vnect_handle vnect_t;
+
+typedef struct vnect_config {
+  int32_t device;       /* CUDA device ordinal */
+  int32_t box_size;     /* CNN input side, 368 in the reference (src/estimator.py:19); multiple of 16 */
+  int32_t n_scales;     /* 1..VNECT_MAX_SCALES */
+  double scales[VNECT_MAX_SCALES]; /* pyramid scales, each in (0, 1]; reference default {1, 0.85, 0.7}
+                                      (src/estimator.py:32) */
+  int32_t max_frames;   /* largest n_frames of one vnect_estimate call (forward batch = max_frames * n_scales) */
+  int32_t max_streams;  /* number of independent temporal-filter slots (video streams) */
+  int32_t max_input_h;  /* largest raw frame accepted by vnect_estimate; 0 = box_size */
+  int32_t max_input_w;
+  int32_t filters;      /* 1 = OneEuroFilter smoothing on (reference behaviour), 0 = raw joints */
+} vnect_config;
+
+/* replaces VNectEstimator.__init__ (src/estimator.py:27-68): allocates the device context; weights come next */
+int vnect_create(vnect_t** out, const vnect_config* cfg);
+
+/* replaces VNect.load_weights / assign_weights_from_dict (src/vnect_model.py:219-236): one call per TF variable, names
+ * and layouts of src/caffe2pkl.py:57-76 ("<scope>/weights" HWIO, "<scope>/biases", "<scope>/kernel",
+ * "bn5c_branch2a/{gamma,beta,moving_mean,moving_variance}").  Host pointer, copied.  res2c_branch2a/* is accepted
+ * and ignored (dead in the reference graph, src/vnect_model.py:54-56). */
+int vnect_set_weight(vnect_t* h, const char* tf_name, const float* data, const int64_t* shape, int32_t rank);
+
+/* folds batch norm, converts to fp16, packs for the tensor cores, builds the launch plan (what saver.restore +
+ * graph import do in src/estimator.py:54-60) */
+int vnect_finalize(vnect_t* h);
+
+/* replaces sess.run([split_2:0..3], {Placeholder:0: batch}) (src/estimator.py:100-104):
+ * nhwc float32 [n, S, S, 3] -> four float32 [n, S/8, S/8, 21] maps (heat-map, x, y, z).  Host pointers. */
+int vnect_forward(vnect_t* h, const float* nhwc, int32_t n, float* hm, float* xm, float* ym, float* zm);
+
+/* replaces VNectEstimator.__call__ (src/estimator.py:97-142) for n_frames independent frames of identical size:
+ * bgr uint8 [n_frames][H][W][3] with row pitch `pitch` and frame stride `frame_stride` (bytes);
+ * stream_ids[n_frames] select the filter slot of each frame (distinct within one call);
+ * t2d / t3d [n_frames] are the two clock readings the reference takes per frame (src/estimator.py:84);
+ * joints2d float64 [n_frames][21][2] = (row, col) in input-image pixels, joints3d float32 [n_frames][21][3] in mm,
+ * root-relative.  All pointers are HOST pointers; copies are part of the call. */
+int vnect_estimate(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
+                   int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d,
+                   double* joints2d, float* joints3d);
+
+/* same computation with the frames and the results resident in device memory (dev_bgr, dev_joints2d, dev_joints3d are
+ * DEVICE pointers; stream_ids / t2d / t3d stay host arrays).  Asynchronous on the handle's stream. */
+int vnect_estimate_device(vnect_t* h, const uint8_t* dev_bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
+                          int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d,
+                          double* dev_joints2d, float* dev_joints3d);
+
+/* replaces VNectEstimator.gen_input_batch (src/estimator.py:70-81): out float32 [n_frames*n_scales][S][S][3]
+ * (fp16-rounded values of the network input), scaler_offsets float64 [3] = {scaler, offset_x, offset_y} */
+int vnect_preprocess(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
+                     int64_t frame_stride, float* out_nhwc, double* scaler_offsets);
+
+/* replaces src/estimator.py:105-142 fed with given maps (host float32 NHWC [n_frames*n_scales][S/8][S/8][21] each);
+ * scaler / offset_x / offset_y as returned by gen_input_batch.  raw_argmax (optional, may be NULL): int32
+ * [n_frames][21][2] unfiltered (row, col) in box pixels. */
+int vnect_postprocess(vnect_t* h, const float* hm, const float* xm, const float* ym, const float* zm, int32_t n_frames,
+                      const int32_t* stream_ids, const double* t2d, const double* t3d, double scaler, int32_t offset_x,
+                      int32_t offset_y, double* joints2d, float* joints3d, int32_t* raw_argmax);
+
+/* replaces VNectEstimator.joint_filter (src/estimator.py:83-95) on explicit values: one step of the 21*dim scalar
+ * filters of a stream at clock reading t.  values: host float64 [21*dim], filtered in place (dim 3 values are
+ * rounded to float32 like the reference's float32 array). */
+int vnect_filter(vnect_t* h, int32_t stream_id, int32_t dim, double t, double* values);
+
+/* forget the temporal-filter state of one stream (a new VNectEstimator() in the reference); -1 = all streams */
+int vnect_reset_stream(vnect_t* h, int32_t stream_id);
+
+/* run on a caller-provided cudaStream_t (e.g. torch's current stream) instead of the handle's own */
+int vnect_set_stream(vnect_t* h, void* cuda_stream);
+int vnect_synchronize(vnect_t* h);
+
+/* introspection for tests and benchmarks */
+int vnect_get_tap(vnect_t* h, const char* name, int32_t n, float* out_nhwc, int64_t capacity_elems,
+                  int32_t* dims4 /* n, H, W, C */);
+int64_t vnect_launch_count(vnect_t* h);      /* kernels launched by this handle so far */
+double vnect_info(vnect_t* h, const char* key); /* "flops_per_forward", "num_sms", "conv_launches_per_forward", ... */
+/* device time of `reps` back-to-back forwards of n images already in device memory (CUDA events on the handle's
+ * stream); per_layer_ms may be NULL or float[conv_launches_per_forward + 1] (pool is the last entry) */
+int vnect_time_forward(vnect_t* h, int32_t n, int32_t reps, float* total_ms, float* per_layer_ms);
+const char* vnect_step_name(vnect_t* h, int32_t i); /* name of launch i of one forward, NULL past the end */
+
+const char* vnect_last_error(vnect_t* h);
+const char* vnect_version(void);
+void vnect_destroy(vnect_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

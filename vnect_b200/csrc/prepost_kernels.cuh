@@ -1,0 +1,440 @@
+// Bandwidth-bound kernels around the CNN: bit-exact OpenCV-style preprocessing (K1), 3x3/2 max-pool (K3) and the
+// fused post-process (K8: multi-scale average -> x8 upsample argmax -> 1-euro filters -> location-map gather).
+//
+// Reference semantics being restated (XinArkh/VNect): src/estimator.py:70-81 and src/utils.py:13-21,82-150 (K1),
+// src/vnect_model.py:29 (pool), src/estimator.py:105-142 + src/utils.py:58-79,153-219 + src/OneEuroFilter.py:13-75
+// (K8).  Arithmetic that has to be bit-faithful uses explicit round-to-nearest intrinsics so that nvcc cannot
+// contract a*b+c into an FMA where OpenCV / CPython do not (and uses FMA where OpenCV+IPP does: the float64 x8
+// upsample; see oracle/prepost.py).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vnect {
+
+constexpr int kJoints = 21;
+constexpr int kRootJoint = 14;
+constexpr int kMaxScales = 4;
+constexpr int kMaxHm = 64;  // heat-map side limit (46 @368, 56 @448)
+
+// ---------------------------------------------------------------------------------------------------------------
+// OpenCV INTER_LINEAR coordinate rule: f = float((d + 0.5) * inv_scale - 0.5) in double, then
+// i = floor(f), f -= i in float.  reset=true (x axis): clamp i into [0, src-1] and zero f at the borders.
+__device__ __forceinline__ void cv_linear_coord(int d, double inv_scale, int src, bool reset, int* i_out,
+                                                float* f_out) {
+  const double fd = __dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), inv_scale), 0.5);
+  float f = __double2float_rn(fd);
+  int i = (int)floorf(f);
+  f = __fsub_rn(f, (float)i);
+  if (reset) {
+    if (i < 0) { i = 0; f = 0.f; }
+    if (i >= src - 1) { i = src - 1; f = 0.f; }
+  }
+  *i_out = i;
+  *f_out = f;
+}
+
+__device__ __forceinline__ int cv_coef(float f) { return __float2int_rn(__fmul_rn(f, 2048.f)); }
+
+// One output pixel (3 channels) of cv2.resize(u8, INTER_LINEAR): 11-bit fixed point, vertical pass
+// (((b0*(T0>>4))>>16) + ((b1*(T1>>4))>>16) + 2) >> 2.   src rows are `pitch` bytes apart, 3 bytes per pixel.
+__device__ __forceinline__ void cv_resize_u8_px(const uint8_t* __restrict__ src, int64_t pitch, int sh, int sw, int dy,
+                                                int dx, double inv_scale, int out[3]) {
+  int ix, iy;
+  float fx, fy;
+  cv_linear_coord(dx, inv_scale, sw, true, &ix, &fx);
+  cv_linear_coord(dy, inv_scale, sh, false, &iy, &fy);
+  const int a0 = cv_coef(__fsub_rn(1.f, fx)), a1 = cv_coef(fx);
+  const int b0 = cv_coef(__fsub_rn(1.f, fy)), b1 = cv_coef(fy);
+  const int ix1 = min(ix + 1, sw - 1);
+  const int y0 = min(max(iy, 0), sh - 1), y1 = min(max(iy + 1, 0), sh - 1);
+  const uint8_t* r0 = src + (int64_t)y0 * pitch;
+  const uint8_t* r1 = src + (int64_t)y1 * pitch;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int t0 = r0[ix * 3 + c] * a0 + r0[ix1 * 3 + c] * a1;
+    const int t1 = r1[ix * 3 + c] * a0 + r1[ix1 * 3 + c] * a1;
+    out[c] = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+  }
+}
+
+struct SquarifyParams {
+  int n_frames, H, W;       // raw frames
+  int64_t pitch, frame_stride;
+  int S;                    // box size
+  int dh, dw;               // scaled content size (cvRound(H*scaler), cvRound(W*scaler))
+  int off_x, off_y;         // placement inside the box (utils.py:82-104)
+  double inv_scale;         // 1 / scaler
+  int mode;                 // 0 = bilinear, 1 = exact 2x decimation (OpenCV switches INTER_LINEAR to INTER_AREA)
+};
+
+// utils.img_scale_squarify (utils.py:107-120): resize so the longer side is S, centre on black.  out: u8 [n,S,S,3].
+__global__ void squarify_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, SquarifyParams p) {
+  const int64_t total = (int64_t)p.n_frames * p.S * p.S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % p.S);
+    const int y = (int)((i / p.S) % p.S);
+    const int n = (int)(i / ((int64_t)p.S * p.S));
+    int v[3] = {0, 0, 0};
+    const int sy = y - p.off_y, sx = x - p.off_x;
+    if (sy >= 0 && sy < p.dh && sx >= 0 && sx < p.dw) {
+      const uint8_t* src = in + (int64_t)n * p.frame_stride;
+      if (p.mode == 0) {
+        cv_resize_u8_px(src, p.pitch, p.H, p.W, sy, sx, p.inv_scale, v);
+      } else {
+        const uint8_t* r0 = src + (int64_t)(2 * sy) * p.pitch + (int64_t)(2 * sx) * 3;
+        const uint8_t* r1 = r0 + p.pitch;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[c] = (r0[c] + r0[3 + c] + r1[c] + r1[3 + c] + 2) >> 2;
+      }
+    }
+    uint8_t* o = out + i * 3;
+    o[0] = (uint8_t)v[0];
+    o[1] = (uint8_t)v[1];
+    o[2] = (uint8_t)v[2];
+  }
+}
+
+struct PyramidParams {
+  int n_frames, S, n_scales;
+  int64_t sq_pitch, sq_frame_stride;  // square u8 input (may alias the raw frames when they are already S x S)
+  int R[kMaxScales];                  // resized side cvRound(S*s); == S for s >= 1 (identity)
+  int pad0[kMaxScales];               // (S - R) / 2
+  double inv_scale[kMaxScales];       // 1 / s
+  // stem layout: [forward][parity][rows_per_parity][row_pitch] halves, pixel (y, x) lives at padded (y+2, x+2)
+  int rows_per_parity, row_pitch;
+};
+
+// estimator.gen_input_batch (estimator.py:70-81): per scale shrink + zero pad (utils.py:123-150), then
+// float32(u8)/255 - 0.4, stored as fp16 in the parity-split padded NHWC4 layout the stem conv's TMA reads.
+__global__ void pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restrict__ x1, PyramidParams p) {
+  const int64_t per_fwd = (int64_t)p.S * p.S;
+  const int64_t total = (int64_t)p.n_frames * p.n_scales * per_fwd;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % p.S);
+    const int y = (int)((i / p.S) % p.S);
+    const int fwd = (int)(i / per_fwd);
+    const int frame = fwd / p.n_scales, si = fwd - frame * p.n_scales;
+    const uint8_t* src = sq + (int64_t)frame * p.sq_frame_stride;
+    int v[3] = {0, 0, 0};
+    if (p.R[si] == p.S) {
+      const uint8_t* q = src + (int64_t)y * p.sq_pitch + x * 3;
+      v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
+    } else {
+      const int ry = y - p.pad0[si], rx = x - p.pad0[si];
+      if (ry >= 0 && ry < p.R[si] && rx >= 0 && rx < p.R[si])
+        cv_resize_u8_px(src, p.sq_pitch, p.S, p.S, ry, rx, p.inv_scale[si], v);
+    }
+    __half h[4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) h[c] = __float2half_rn(__fsub_rn(__fdiv_rn((float)v[c], 255.f), 0.4f));
+    h[3] = __float2half_rn(0.f);
+    const int pr = y + 2, pc = x + 2;
+    __half* o = x1 + (((int64_t)fwd * 2 + (pr & 1)) * p.rows_per_parity + (pr >> 1)) * p.row_pitch + pc * 4;
+    *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(h);
+  }
+}
+
+// Operator-level entry (vnect_forward): float32 NHWC [n,S,S,3] -> stem layout (fp16).
+__global__ void f32_to_stem_kernel(const float* __restrict__ in, __half* __restrict__ x1, int n, int S,
+                                   int rows_per_parity, int row_pitch) {
+  const int64_t total = (int64_t)n * S * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % S);
+    const int y = (int)((i / S) % S);
+    const int fwd = (int)(i / ((int64_t)S * S));
+    __half h[4];
+    h[0] = __float2half_rn(in[i * 3 + 0]);
+    h[1] = __float2half_rn(in[i * 3 + 1]);
+    h[2] = __float2half_rn(in[i * 3 + 2]);
+    h[3] = __float2half_rn(0.f);
+    const int pr = y + 2, pc = x + 2;
+    __half* o = x1 + (((int64_t)fwd * 2 + (pr & 1)) * rows_per_parity + (pr >> 1)) * row_pitch + pc * 4;
+    *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(h);
+  }
+}
+
+// Inverse of the above for tests: stem layout -> float32 NHWC [n,S,S,3].
+__global__ void stem_to_f32_kernel(const __half* __restrict__ x1, float* __restrict__ out, int n, int S,
+                                   int rows_per_parity, int row_pitch) {
+  const int64_t total = (int64_t)n * S * S;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % S);
+    const int y = (int)((i / S) % S);
+    const int fwd = (int)(i / ((int64_t)S * S));
+    const int pr = y + 2, pc = x + 2;
+    const __half* o = x1 + (((int64_t)fwd * 2 + (pr & 1)) * rows_per_parity + (pr >> 1)) * row_pitch + pc * 4;
+    out[i * 3 + 0] = __half2float(o[0]);
+    out[i * 3 + 1] = __half2float(o[1]);
+    out[i * 3 + 2] = __half2float(o[2]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tc.layers.max_pool2d(kernel 3, stride 2, 'same') on NHWC fp16 (vnect_model.py:29): TF SAME pads (0,1) here and
+// ignores padded cells.  One thread = 8 channels (16 B) of one output pixel.
+__global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int NB, int H, int W,
+                                    int C, int OH, int OW) {
+  const int cv = C / 8;
+  const int64_t total = (int64_t)NB * OH * OW * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    int64_t r = i / cv;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int n = (int)(r / OH);
+    __half2 m[4];
+    bool first = true;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y = 2 * oy + ky;
+      if (y >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int x = 2 * ox + kx;
+        if (x >= W) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((int64_t)n * H + y) * W + x) * C) + c8);
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+        if (first) {
+          m[0] = h[0]; m[1] = h[1]; m[2] = h[2]; m[3] = h[3];
+          first = false;
+        } else {
+          m[0] = __hmax2(m[0], h[0]); m[1] = __hmax2(m[1], h[1]);
+          m[2] = __hmax2(m[2], h[2]); m[3] = __hmax2(m[3], h[3]);
+        }
+      }
+    }
+    *(reinterpret_cast<uint4*>(out + (((int64_t)n * OH + oy) * OW + ox) * C) + c8) = *reinterpret_cast<uint4*>(m);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K8: fused post-process.
+struct ScaleTable {  // per pyramid scale: where output cell c of the cropped, 1/s-resized map samples the raw map
+  short i0[kMaxHm], i1[kMaxHm];      // x axis (index clamp + f reset)
+  float a0[kMaxHm], a1[kMaxHm];
+  short j0[kMaxHm], j1[kMaxHm];      // y axis (rows clamped, f kept)
+  float b0[kMaxHm], b1[kMaxHm];
+  int identity;                       // s == 1: plain copy
+};
+
+struct FilterCfg { double freq, mincutoff, beta, dcutoff; };
+
+// One scalar 1-euro filter (OneEuroFilter.py:41-75).
+struct FilterState {
+  double prev;      // last raw value (LowPassFilter.__y of the x filter); float32-valued for 3D filters
+  double s_x, s_dx; // smoothed value / smoothed derivative
+  double lasttime, freq;
+  int has_prev, has_time;
+};
+
+__device__ __forceinline__ double oef_alpha(double freq, double cutoff) {
+  const double te = __ddiv_rn(1.0, freq);
+  const double tau = __ddiv_rn(1.0, __dmul_rn(6.283185307179586, cutoff));  // 2*math.pi is exact doubling
+  return __ddiv_rn(1.0, __dadd_rn(1.0, __ddiv_rn(tau, te)));
+}
+
+// x_is_f32: numpy-1.x ("legacy") promotion for the float32 3D joints -- the raw difference is float32.
+__device__ __forceinline__ double oef_step(FilterState& st, const FilterCfg& cfg, double x, double t, bool x_is_f32) {
+  if (st.has_time && st.lasttime != 0.0 && t != 0.0) st.freq = __ddiv_rn(1.0, __dsub_rn(t, st.lasttime));
+  st.lasttime = t;
+  st.has_time = 1;
+  double dx = 0.0;
+  if (st.has_prev) {
+    const double diff = x_is_f32 ? (double)__fsub_rn((float)x, (float)st.prev) : __dsub_rn(x, st.prev);
+    dx = __dmul_rn(diff, st.freq);
+  }
+  const double a_d = oef_alpha(st.freq, cfg.dcutoff);
+  const double edx = st.has_prev ? __dadd_rn(__dmul_rn(a_d, dx), __dmul_rn(__dsub_rn(1.0, a_d), st.s_dx)) : dx;
+  const double cutoff = __dadd_rn(cfg.mincutoff, __dmul_rn(cfg.beta, fabs(edx)));
+  const double a = oef_alpha(st.freq, cutoff);
+  const double s = st.has_prev ? __dadd_rn(__dmul_rn(a, x), __dmul_rn(__dsub_rn(1.0, a), st.s_x)) : x;
+  st.prev = x;
+  st.s_x = s;
+  st.s_dx = edx;
+  st.has_prev = 1;
+  return s;
+}
+
+struct PostParams {
+  int n_frames, n_scales, hs, S;  // hs = S / 8
+  const float* maps;              // planar [n_frames*n_scales][84][hs][hs]
+  const ScaleTable* tables;       // [n_scales]
+  const int* stream_ids;          // [n_frames]
+  const double* t2d;              // [n_frames]
+  const double* t3d;
+  FilterState* st2d;              // [max_streams][21][2]
+  FilterState* st3d;              // [max_streams][21][3]
+  FilterCfg cfg2d, cfg3d;
+  int filters_on;
+  double scaler;                  // box px per input px (S / max(H, W))
+  int off_x, off_y;
+  double* j2_box;                 // [n_frames][21][2] scratch: filtered 2D joints in box pixels (also an output tap)
+  float* j3_raw;                  // [n_frames][21][3] scratch: x100 location-map samples before root subtraction
+  int* raw_argmax;                // [n_frames][21][2] unfiltered argmax (row, col), a tap for parity tests
+  unsigned int* frame_counter;    // [n_frames], zeroed before launch
+  double* out2d;                  // [n_frames][21][2]
+  float* out3d;                   // [n_frames][21][3]
+};
+
+constexpr int kPostThreads = 128;
+
+// 1/s-resized (float32, cv2 arithmetic: separate mul/add) + cropped value of raw planar map `m` at cell (y, x).
+__device__ __forceinline__ float scaled_cell(const float* __restrict__ m, int hs, const ScaleTable& T, int y, int x) {
+  if (T.identity) return __ldg(m + y * hs + x);
+  const float* r0 = m + T.j0[y] * hs;
+  const float* r1 = m + T.j1[y] * hs;
+  const int x0 = T.i0[x], x1 = T.i1[x];
+  const float a0 = T.a0[x], a1 = T.a1[x];
+  const float t0 = __fadd_rn(__fmul_rn(__ldg(r0 + x0), a0), __fmul_rn(__ldg(r0 + x1), a1));
+  const float t1 = __fadd_rn(__fmul_rn(__ldg(r1 + x0), a0), __fmul_rn(__ldg(r1 + x1), a1));
+  return __fadd_rn(__fmul_rn(t0, T.b0[y]), __fmul_rn(t1, T.b1[y]));
+}
+
+// float64 mean over scales, accumulated in scale order (estimator.py:105-129)
+__device__ __forceinline__ double averaged_cell(const PostParams& p, int frame, int channel, int y, int x) {
+  double acc = 0.0;
+  const size_t plane = (size_t)p.hs * p.hs;
+  for (int s = 0; s < p.n_scales; ++s) {
+    const float* m = p.maps + ((size_t)(frame * p.n_scales + s) * 84 + channel) * plane;
+    acc = __dadd_rn(acc, (double)scaled_cell(m, p.hs, p.tables[s], y, x));
+  }
+  return __ddiv_rn(acc, (double)p.n_scales);
+}
+
+// utils.hm_pt_interp_bilinear (utils.py:58-79) on the averaged map of `channel`, point (row py, col px), float64.
+__device__ __forceinline__ double point_sample(const PostParams& p, int frame, int channel, double py, double px) {
+  const double sx = __dsub_rn(__ddiv_rn(__dadd_rn(px, 0.5), 8.0), 0.5);
+  const double sy = __dsub_rn(__ddiv_rn(__dadd_rn(py, 0.5), 8.0), 0.5);
+  int x0 = (int)sx, y0 = (int)sy;  // truncation toward zero, like int()
+  x0 = min(max(x0, 0), p.hs - 1);  // memory safety only: filtered joints stay inside the box
+  y0 = min(max(y0, 0), p.hs - 1);
+  const int x1 = min(x0 + 1, p.hs - 1), y1 = min(y0 + 1, p.hs - 1);
+  const double wx1 = __dsub_rn((double)x1, sx), wx0 = __dsub_rn(sx, (double)x0);
+  const double wy1 = __dsub_rn((double)y1, sy), wy0 = __dsub_rn(sy, (double)y0);
+  const double v00 = averaged_cell(p, frame, channel, y0, x0), v01 = averaged_cell(p, frame, channel, y0, x1);
+  const double v10 = averaged_cell(p, frame, channel, y1, x0), v11 = averaged_cell(p, frame, channel, y1, x1);
+  const double value0 = __dadd_rn(__dmul_rn(wx1, v00), __dmul_rn(wx0, v01));
+  const double value1 = __dadd_rn(__dmul_rn(wx1, v10), __dmul_rn(wx0, v11));
+  return __dadd_rn(__dmul_rn(wy1, value0), __dmul_rn(wy0, value1));
+}
+
+// Candidate k (0 .. 2*hs-1) of the x8 upsample along one axis: destination index d, source cell i, fraction f.
+// Between two source cell centres the upsample is monotonic, so its maximum over the 8 samples of a segment sits at
+// the first (f = 1/16) or last (f = 15/16) one; d = 0 stands for the exactly-tied samples 0..3 and d = 8*(hs-1)+4 for
+// the last four, where the first index wins like np.argmax.
+__device__ __forceinline__ void upsample_candidate(int k, int hs, int* d, int* i, double* f) {
+  if (k == 0) { *d = 0; *i = 0; *f = 0.0; return; }
+  if (k == 2 * hs - 1) { *d = 8 * (hs - 1) + 4; *i = hs - 1; *f = 0.0; return; }
+  const int r = (k - 1) >> 1;
+  if ((k - 1) & 1) { *d = 8 * r + 11; *i = r; *f = 0.9375; }
+  else             { *d = 8 * r + 4;  *i = r; *f = 0.0625; }
+}
+
+// grid = n_frames * 21 blocks of 128 threads; block (frame, joint).  The last block of a frame to finish runs the
+// per-frame tail (root subtraction, 3D filters, 2D rescale).
+__global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p) {
+  extern __shared__ double s_avg[];  // [hs][hs] averaged heat-map of this joint
+  __shared__ double s_val[kPostThreads / 32];
+  __shared__ int s_idx[kPostThreads / 32];
+  __shared__ int s_is_last;
+  const int frame = blockIdx.x / kJoints;
+  const int joint = blockIdx.x - frame * kJoints;
+  const int hs = p.hs, S = p.S;
+  const int tid = threadIdx.x;
+
+  // ---- 1. multi-scale float64 average of the heat-map (estimator.py:105-129)
+  for (int c = tid; c < hs * hs; c += kPostThreads) s_avg[c] = averaged_cell(p, frame, joint, c / hs, c % hs);
+  __syncthreads();
+
+  // ---- 2. argmax of the x8 bilinear upsample (utils.py:153-175), OpenCV+IPP arithmetic: fma(S1-S0, f, S0) per axis
+  double best = -INFINITY;
+  int best_idx = 0x7fffffff;
+  const int nc = 2 * hs;
+  for (int c = tid; c < nc * nc; c += kPostThreads) {
+    const int ky = c / nc, kx = c - ky * nc;
+    int dy, iy, dx, ix;
+    double fy, fx;
+    upsample_candidate(ky, hs, &dy, &iy, &fy);
+    upsample_candidate(kx, hs, &dx, &ix, &fx);
+    const int iy1 = min(iy + 1, hs - 1), ix1 = min(ix + 1, hs - 1);
+    const double s00 = s_avg[iy * hs + ix], s01 = s_avg[iy * hs + ix1];
+    const double s10 = s_avg[iy1 * hs + ix], s11 = s_avg[iy1 * hs + ix1];
+    const double h0 = __fma_rn(__dsub_rn(s01, s00), fx, s00);
+    const double h1 = __fma_rn(__dsub_rn(s11, s10), fx, s10);
+    const double v = __fma_rn(__dsub_rn(h1, h0), fy, h0);
+    const int idx = dy * S + dx;
+    if (v > best || (v == best && idx < best_idx)) { best = v; best_idx = idx; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+    if (ov > best || (ov == best && oi < best_idx)) { best = ov; best_idx = oi; }
+  }
+  if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = best_idx; }
+  __syncthreads();
+
+  // ---- 3. 2D filters, then the location-map gather at the FILTERED point (estimator.py:132-134)
+  if (tid < 32) {
+    best = s_val[0]; best_idx = s_idx[0];
+#pragma unroll
+    for (int w = 1; w < kPostThreads / 32; ++w)
+      if (s_val[w] > best || (s_val[w] == best && s_idx[w] < best_idx)) { best = s_val[w]; best_idx = s_idx[w]; }
+    const int row = best_idx / S, col = best_idx - row * S;
+    double coord = (tid == 0) ? (double)row : (double)col;
+    if (tid < 2) {
+      p.raw_argmax[(frame * kJoints + joint) * 2 + tid] = (tid == 0) ? row : col;
+      if (p.filters_on) {
+        FilterState st = p.st2d[((size_t)p.stream_ids[frame] * kJoints + joint) * 2 + tid];
+        coord = oef_step(st, p.cfg2d, coord, p.t2d[frame], false);
+        p.st2d[((size_t)p.stream_ids[frame] * kJoints + joint) * 2 + tid] = st;
+      }
+      p.j2_box[(frame * kJoints + joint) * 2 + tid] = coord;
+    }
+    const double py = __shfl_sync(0xffffffffu, coord, 0), px = __shfl_sync(0xffffffffu, coord, 1);
+    if (tid < 3) {
+      const double v = point_sample(p, frame, kJoints * (1 + tid) + joint, py, px);
+      p.j3_raw[(frame * kJoints + joint) * 3 + tid] = __double2float_rn(__dmul_rn(v, 100.0));  // mm, float32 store
+    }
+  }
+
+  // ---- 4. per-frame tail in the last block to arrive
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_is_last = (atomicAdd(&p.frame_counter[frame], 1u) == kJoints - 1);
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  if (tid < kJoints * 3) {
+    const int j = tid / 3, c = tid - j * 3;
+    const volatile float* raw = p.j3_raw + frame * kJoints * 3;
+    float v = __fsub_rn(raw[j * 3 + c], raw[kRootJoint * 3 + c]);  // joints_3d -= joints_3d[14] (utils.py:218)
+    if (p.filters_on) {
+      FilterState st = p.st3d[((size_t)p.stream_ids[frame] * kJoints + j) * 3 + c];
+      v = __double2float_rn(oef_step(st, p.cfg3d, (double)v, p.t3d[frame], true));
+      p.st3d[((size_t)p.stream_ids[frame] * kJoints + j) * 3 + c] = st;
+    }
+    p.out3d[(frame * kJoints + j) * 3 + c] = v;
+  }
+  if (tid < kJoints * 2) {
+    const int j = tid >> 1, c = tid & 1;
+    const volatile double* jb = p.j2_box + frame * kJoints * 2;
+    const double off = (c == 0) ? (double)p.off_y : (double)p.off_x;  // estimator.py:138-139
+    p.out2d[(frame * kJoints + j) * 2 + c] = __ddiv_rn(__dsub_rn(jb[j * 2 + c], off), p.scaler);
+  }
+}
+
+// VNectEstimator.joint_filter (estimator.py:83-95) on explicit values: 21*dim scalar filters of one stream.
+__global__ void joint_filter_kernel(FilterState* st, FilterCfg cfg, double* values, double t, int dim) {
+  const int i = threadIdx.x;
+  if (i >= kJoints * dim) return;
+  FilterState s = st[i];
+  const double v = oef_step(s, cfg, values[i], t, dim == 3);
+  values[i] = dim == 3 ? (double)__double2float_rn(v) : v;
+  st[i] = s;
+}
+
+}  // namespace vnect

@@ -1,0 +1,985 @@
+// C ABI of the B200-native VNect hot path (see include/vnect_b200.h): handle, weight ingest, plan, entry points.
+#include "vnect_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "conv_plan.cuh"
+#include "prepost_kernels.cuh"
+
+using namespace vnect;
+
+namespace {
+
+struct Act {
+  __half* p = nullptr;
+  int H = 0, W = 0, C = 0;
+};
+
+struct Step {
+  int kind = 0;  // 0 = conv, 1 = maxpool
+  std::string name;
+  ConvLaunch launch;
+  int tiles_per_image = 0;  // spatial
+  // pool
+  const __half* pin = nullptr;
+  __half* pout = nullptr;
+  int H = 0, W = 0, C = 0, OH = 0, OW = 0;
+};
+
+struct HostVar {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+}  // namespace
+
+struct vnect_handle {
+  vnect_config cfg{};
+  int S = 368, hs = 46, n_scales = 1, cap_fw = 1, num_sms = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool finalized = false;
+  std::string err;
+  long long launches = 0;
+  std::map<std::string, HostVar> vars;
+  std::vector<void*> allocs;
+  std::map<std::string, Act> acts;
+  std::vector<Step> steps;
+  int conv_steps = 0;
+  // stem input
+  __half* x1 = nullptr;
+  int stem_rpp = 0, stem_pitch = 0;
+  // output maps, planar fp32 [cap_fw][84][hs][hs]
+  float* maps = nullptr;
+  // pre/post buffers
+  uint8_t* d_frames = nullptr;
+  size_t d_frames_bytes = 0;
+  uint8_t* d_sq = nullptr;
+  float* d_f32_in = nullptr;  // vnect_forward staging [cap_fw][S][S][3]
+  ScaleTable* d_tables = nullptr;
+  int* d_stream_ids = nullptr;
+  double *d_t2d = nullptr, *d_t3d = nullptr;
+  FilterState *d_st2d = nullptr, *d_st3d = nullptr;
+  double* d_j2_box = nullptr;
+  float* d_j3_raw = nullptr;
+  int* d_raw_argmax = nullptr;
+  unsigned int* d_counter = nullptr;
+  double* d_out2d = nullptr;
+  float* d_out3d = nullptr;
+  double* d_filter_scratch = nullptr;
+  // pinned host staging for the small per-call arrays
+  int* h_stream_ids = nullptr;
+  double *h_t2d = nullptr, *h_t3d = nullptr;
+  std::vector<double> last_t2d, last_t3d;  // host mirror of the filters' last timestamps (NaN = none yet)
+  PyramidParams pyr{};
+};
+
+static int fail(vnect_t* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CU(h, call)                                                                                       \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(h, VNECT_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+static int dev_alloc(vnect_t* h, T** p, size_t count, bool zero = true) {
+  void* q = nullptr;
+  CU(h, cudaMalloc(&q, count * sizeof(T) + 256));
+  if (zero) CU(h, cudaMemset(q, 0, count * sizeof(T) + 256));
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return VNECT_OK;
+}
+
+static inline int grid_for(int64_t total, int threads, int sms) {
+  int64_t b = (total + threads - 1) / threads;
+  int64_t cap = (int64_t)sms * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+static const char* kBnVars[4] = {"gamma", "beta", "moving_mean", "moving_variance"};
+
+struct ConvDef {
+  const char* scope;
+  int k, cin, cout;
+};
+
+static std::vector<ConvDef> conv_defs() {
+  std::vector<ConvDef> d;
+  static std::vector<std::string> names;  // keeps c_str() alive
+  names.clear();
+  names.reserve(128);
+  auto add = [&](const std::string& s, int k, int ci, int co) {
+    names.push_back(s);
+    d.push_back({names.back().c_str(), k, ci, co});
+  };
+  auto block = [&](const std::string& pre, int cin, int mid, int cout, bool proj, const std::string& suf) {
+    if (proj) add(pre + "_branch1" + suf, 1, cin, cout);
+    add(pre + "_branch2a" + suf, 1, cin, mid);
+    add(pre + "_branch2b" + suf, 3, mid, mid);
+    add(pre + "_branch2c" + suf, 1, mid, cout);
+  };
+  add("conv1", 7, 3, 64);
+  block("res2a", 64, 64, 256, true, "");
+  block("res2b", 256, 64, 256, false, "");
+  block("res2c", 256, 64, 256, false, "");
+  block("res3a", 256, 128, 512, true, "");
+  for (const char* b : {"res3b", "res3c", "res3d"}) block(b, 512, 128, 512, false, "");
+  block("res4a", 512, 256, 1024, true, "");
+  for (const char* b : {"res4b", "res4c", "res4d", "res4e", "res4f"}) block(b, 1024, 256, 1024, false, "");
+  block("res5a", 1024, 512, 1024, true, "_new");
+  add("res5b_branch2a_new", 1, 1024, 256);
+  add("res5b_branch2b_new", 3, 256, 128);
+  add("res5b_branch2c_new", 1, 128, 256);
+  add("res5c_branch2b", 3, 212, 128);
+  return d;
+}
+
+static bool expected_shape(const std::string& name, std::vector<int64_t>* shape) {
+  const size_t slash = name.find('/');
+  if (slash == std::string::npos) return false;
+  const std::string scope = name.substr(0, slash), leaf = name.substr(slash + 1);
+  if (scope == "bn5c_branch2a") {
+    for (const char* v : kBnVars)
+      if (leaf == v) {
+        *shape = {128};
+        return true;
+      }
+    return false;
+  }
+  if (leaf == "kernel") {
+    if (scope == "res5c_branch1a") { *shape = {4, 4, 63, 256}; return true; }
+    if (scope == "res5c_branch2a") { *shape = {4, 4, 128, 256}; return true; }
+    if (scope == "res5c_branch2c") { *shape = {1, 1, 128, 84}; return true; }
+    return false;
+  }
+  for (const ConvDef& c : conv_defs())
+    if (scope == c.scope) {
+      if (leaf == "weights") { *shape = {c.k, c.k, c.cin, c.cout}; return true; }
+      if (leaf == "biases") { *shape = {c.cout}; return true; }
+    }
+  return false;
+}
+
+static std::vector<__half> to_half(const std::vector<float>& v) {
+  std::vector<__half> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = __float2half_rn(v[i]);
+  return o;
+}
+
+// HWIO [k,k,cin,cout] -> [n_pad][k*k*cin_pad], K-major per output channel, zero padded
+static std::vector<float> pack_conv(const HostVar& w, int k, int cin, int cout, int cin_pad, int n_pad) {
+  std::vector<float> b((size_t)n_pad * k * k * cin_pad, 0.f);
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co)
+          b[(size_t)co * k * k * cin_pad + (size_t)(ky * k + kx) * cin_pad + ci] =
+              w.data[(((size_t)ky * k + kx) * cin + ci) * cout + co];
+  return b;
+}
+
+// stem: [64][7 rows][8 px][4 ch] (px 7 and ch 3 are zero)
+static std::vector<float> pack_stem(const HostVar& w) {
+  std::vector<float> b((size_t)64 * 224, 0.f);
+  for (int ky = 0; ky < 7; ++ky)
+    for (int kx = 0; kx < 7; ++kx)
+      for (int c = 0; c < 3; ++c)
+        for (int co = 0; co < 64; ++co) b[(size_t)co * 224 + ky * 32 + kx * 4 + c] = w.data[((ky * 7 + kx) * 3 + c) * 64 + co];
+  return b;
+}
+
+// Both transposed convs + folded batch norm as 4 phase GEMMs: [4 phases][192 cols][4 taps][256 ch].
+// cols 0-127 = res5c_branch2a * bn scale, 128-190 = res5c_branch1a, 191 = 0.  TF kernel layout [kh,kw,out,in].
+static std::vector<float> pack_deconv(const HostVar& w2a, const HostVar& w1a, const std::vector<float>& bn_scale) {
+  std::vector<float> b((size_t)4 * 192 * 1024, 0.f);
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    for (int a = 0; a < 2; ++a)
+      for (int bb = 0; bb < 2; ++bb) {
+        const int ky = py == 0 ? (a == 0 ? 1 : 3) : (a == 0 ? 0 : 2);
+        const int kx = px == 0 ? (bb == 0 ? 1 : 3) : (bb == 0 ? 0 : 2);
+        for (int col = 0; col < 191; ++col)
+          for (int ci = 0; ci < 256; ++ci) {
+            float v;
+            if (col < 128)
+              v = w2a.data[(((size_t)ky * 4 + kx) * 128 + col) * 256 + ci] * bn_scale[col];
+            else
+              v = w1a.data[(((size_t)ky * 4 + kx) * 63 + (col - 128)) * 256 + ci];
+            b[((size_t)ph * 192 + col) * 1024 + (size_t)(a * 2 + bb) * 256 + ci] = v;
+          }
+      }
+  }
+  return b;
+}
+
+template <typename T>
+static int upload(vnect_t* h, const std::vector<T>& v, T** out) {
+  int rc = dev_alloc(h, out, v.size(), false);
+  if (rc) return rc;
+  CU(h, cudaMemcpy(*out, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return VNECT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+static int new_act(vnect_t* h, const std::string& name, int H, int W, int C) {
+  Act a;
+  a.H = H; a.W = W; a.C = C;
+  int rc = dev_alloc(h, &a.p, (size_t)h->cap_fw * H * W * C, true);
+  if (rc) return rc;
+  h->acts[name] = a;
+  return VNECT_OK;
+}
+
+struct ConvOpts {
+  bool relu = true;
+  std::string residual;  // act name or empty
+  bool decimate = false;
+};
+
+static int pick_block_n(int n) { return n >= 256 ? 256 : n >= 128 ? 128 : 64; }
+
+static int add_conv(vnect_t* h, const std::string& scope, int k, const std::string& in, const std::string& out,
+                    int cin, int cout, const ConvOpts& o) {
+  const Act& ai = h->acts.at(in);
+  const HostVar& w = h->vars.at(scope + "/weights");
+  const HostVar& b = h->vars.at(scope + "/biases");
+  const int cin_pad = ai.C;
+  __half* dw = nullptr;
+  float* db = nullptr;
+  int rc = upload(h, to_half(pack_conv(w, k, cin, cout, cin_pad, cout)), &dw);
+  if (rc) return rc;
+  rc = upload(h, b.data, &db);
+  if (rc) return rc;
+  const int OH = o.decimate ? ai.H / 2 : ai.H, OW = o.decimate ? ai.W / 2 : ai.W;
+  rc = new_act(h, out, OH, OW, cout);
+  if (rc) return rc;
+  ConvSpec s;
+  s.kind = k == 1 ? CONV_1x1 : CONV_3x3;
+  s.NB = h->cap_fw; s.H = ai.H; s.W = ai.W;
+  s.in = ai.p; s.cin_pad = cin_pad;
+  s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout);
+  s.bias = db; s.relu_cols = o.relu ? cout : 0;
+  if (!o.residual.empty()) {
+    const Act& r = h->acts.at(o.residual);
+    if (r.H != ai.H || r.W != ai.W || r.C != cout) return fail(h, VNECT_E_INVALID, "residual shape mismatch at %s", scope.c_str());
+    s.residual = r.p; s.ldr = r.C;
+  }
+  s.out = h->acts.at(out).p; s.ldc = cout; s.epi = EPI_NHWC_F16; s.decimate = o.decimate ? 1 : 0;
+  Step st;
+  st.kind = 0; st.name = scope;
+  std::string err;
+  if (!build_conv(s, h->num_sms, &st.launch, &err)) return fail(h, VNECT_E_CUDA, "%s: %s", scope.c_str(), err.c_str());
+  h->steps.push_back(st);
+  return VNECT_OK;
+}
+
+// bottleneck block (reference: src/vnect_model.py:31-177); `a_in` overrides the 3x3's input (the res2c wiring, :56)
+static int add_block(vnect_t* h, const std::string& pre, const std::string& in, int cin, int mid, int cout, bool proj,
+                     const std::string& suf, bool decimate_out, const std::string& a_override = "") {
+  int rc;
+  ConvOpts lin; lin.relu = false;
+  ConvOpts relu;
+  std::string shortcut = in;
+  if (proj) {
+    rc = add_conv(h, pre + "_branch1" + suf, 1, in, pre + "_branch1" + suf, cin, cout, lin);
+    if (rc) return rc;
+    shortcut = pre + "_branch1" + suf;
+  }
+  std::string a = a_override;
+  if (a.empty()) {
+    a = pre + "_branch2a" + suf;
+    rc = add_conv(h, a, 1, in, a, cin, mid, relu);
+    if (rc) return rc;
+  }
+  rc = add_conv(h, pre + "_branch2b" + suf, 3, a, pre + "_branch2b" + suf, mid, mid, relu);
+  if (rc) return rc;
+  ConvOpts last; last.relu = true; last.residual = shortcut; last.decimate = decimate_out;
+  return add_conv(h, pre + "_branch2c" + suf, 1, pre + "_branch2b" + suf, pre, mid, cout, last);
+}
+
+static void set_batch(ConvLaunch& L, int nb, int sms) {
+  ConvGemmParams& p = L.p;
+  p.NB = nb;
+  p.M = nb * p.H * p.W;
+  p.num_m_tiles = p.mode == 0 ? (p.M + kBlockM - 1) / kBlockM : nb * p.tiles_x * p.tiles_y;
+  const int total = p.phases * p.num_m_tiles * p.num_n_tiles;
+  L.grid = total < sms ? total : sms;
+}
+
+// cv2 INTER_LINEAR coordinate rule on the host, identical arithmetic to cv_linear_coord (double -> float)
+static void host_linear_coord(int d, double inv_scale, int src, bool reset, int* i_out, float* f_out) {
+  const double fd = ((double)d + 0.5) * inv_scale - 0.5;
+  float f = (float)fd;
+  int i = (int)std::floor(f);
+  f = f - (float)i;
+  if (reset) {
+    if (i < 0) { i = 0; f = 0.f; }
+    if (i >= src - 1) { i = src - 1; f = 0.f; }
+  }
+  *i_out = i;
+  *f_out = f;
+}
+
+static inline int cv_round_host(double v) { return (int)std::nearbyint(v); }
+
+static int build_tables(vnect_t* h) {
+  std::vector<ScaleTable> t(h->n_scales);
+  const int hs = h->hs;
+  for (int s = 0; s < h->n_scales; ++s) {
+    ScaleTable& T = t[s];
+    memset(&T, 0, sizeof T);
+    const double sc = h->cfg.scales[s];
+    if (sc == 1.0) {
+      T.identity = 1;
+      continue;
+    }
+    // estimator.py:112-120: rescale = 1.0 / s; cv2.resize(fx = fy = rescale); centre crop of hs cells
+    const double rescale = 1.0 / sc;
+    const int R = cv_round_host(hs * rescale);
+    const double inv = 1.0 / rescale;
+    const int crop0 = R / 2 - hs / 2;
+    for (int c = 0; c < hs; ++c) {
+      int i;
+      float f;
+      host_linear_coord(c + crop0, inv, hs, true, &i, &f);
+      T.i0[c] = (short)i;
+      T.i1[c] = (short)std::min(i + 1, hs - 1);
+      T.a0[c] = 1.f - f;
+      T.a1[c] = f;
+      host_linear_coord(c + crop0, inv, hs, false, &i, &f);
+      T.j0[c] = (short)std::min(std::max(i, 0), hs - 1);
+      T.j1[c] = (short)std::min(std::max(i + 1, 0), hs - 1);
+      T.b0[c] = 1.f - f;
+      T.b1[c] = f;
+    }
+  }
+  return upload(h, t, &h->d_tables);
+}
+
+static int alloc_prepost(vnect_t* h) {
+  const int S = h->S, nb = h->cap_fw;
+  int rc;
+  // stem input: parity-split, zero-padded NHWC4 (zeros are written once here and never touched again)
+  h->stem_rpp = S / 2 + 3;
+  h->stem_pitch = (S + 6) * 4;
+  if ((rc = dev_alloc(h, &h->x1, (size_t)nb * 2 * h->stem_rpp * h->stem_pitch, true))) return rc;
+  if ((rc = dev_alloc(h, &h->maps, (size_t)nb * 84 * h->hs * h->hs, true))) return rc;
+  const int mf = h->cfg.max_frames, ms = h->cfg.max_streams;
+  h->d_frames_bytes = (size_t)mf * h->cfg.max_input_h * h->cfg.max_input_w * 3;
+  if ((rc = dev_alloc(h, &h->d_frames, h->d_frames_bytes))) return rc;
+  if ((rc = dev_alloc(h, &h->d_sq, (size_t)mf * S * S * 3))) return rc;
+  if ((rc = dev_alloc(h, &h->d_f32_in, (size_t)nb * S * S * 3))) return rc;
+  if ((rc = build_tables(h))) return rc;
+  if ((rc = dev_alloc(h, &h->d_stream_ids, mf))) return rc;
+  if ((rc = dev_alloc(h, &h->d_t2d, mf))) return rc;
+  if ((rc = dev_alloc(h, &h->d_t3d, mf))) return rc;
+  if ((rc = dev_alloc(h, &h->d_st2d, (size_t)ms * kJoints * 2))) return rc;
+  if ((rc = dev_alloc(h, &h->d_st3d, (size_t)ms * kJoints * 3))) return rc;
+  if ((rc = dev_alloc(h, &h->d_j2_box, (size_t)mf * kJoints * 2))) return rc;
+  if ((rc = dev_alloc(h, &h->d_j3_raw, (size_t)mf * kJoints * 3))) return rc;
+  if ((rc = dev_alloc(h, &h->d_raw_argmax, (size_t)mf * kJoints * 2))) return rc;
+  if ((rc = dev_alloc(h, &h->d_counter, mf))) return rc;
+  if ((rc = dev_alloc(h, &h->d_out2d, (size_t)mf * kJoints * 2))) return rc;
+  if ((rc = dev_alloc(h, &h->d_out3d, (size_t)mf * kJoints * 3))) return rc;
+  if ((rc = dev_alloc(h, &h->d_filter_scratch, 64))) return rc;
+  CU(h, cudaMallocHost(&h->h_stream_ids, mf * sizeof(int)));
+  CU(h, cudaMallocHost(&h->h_t2d, mf * sizeof(double)));
+  CU(h, cudaMallocHost(&h->h_t3d, mf * sizeof(double)));
+  h->last_t2d.assign(ms, NAN);
+  h->last_t3d.assign(ms, NAN);
+  PyramidParams& py = h->pyr;
+  py.S = S; py.n_scales = h->n_scales;
+  py.rows_per_parity = h->stem_rpp; py.row_pitch = h->stem_pitch;
+  for (int i = 0; i < h->n_scales; ++i) {
+    const double sc = h->cfg.scales[i];
+    py.R[i] = sc < 1.0 ? cv_round_host(S * sc) : S;  // estimator.py:77: only scales < 1 are resized
+    py.pad0[i] = (S - py.R[i]) / 2;
+    py.inv_scale[i] = 1.0 / sc;
+  }
+  return VNECT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+const char* vnect_version(void) { return "vnect_b200 0.1 (sm_100a; fp16 operands, fp32 accumulate)"; }
+
+const char* vnect_last_error(vnect_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+int vnect_create(vnect_t** out, const vnect_config* cfg) {
+  if (!out || !cfg) return VNECT_E_INVALID;
+  *out = nullptr;
+  vnect_t* h = new vnect_handle();
+  *out = h;  // returned even on failure so the caller can read the error, then destroy
+  h->cfg = *cfg;
+  if (cfg->box_size < 64 || cfg->box_size % 16 != 0 || cfg->box_size / 8 > kMaxHm)
+    return fail(h, VNECT_E_INVALID, "box_size %d must be a multiple of 16 in [64, %d]", cfg->box_size, kMaxHm * 8);
+  if (cfg->n_scales < 1 || cfg->n_scales > kMaxScales) return fail(h, VNECT_E_INVALID, "n_scales out of range");
+  for (int i = 0; i < cfg->n_scales; ++i)
+    if (!(cfg->scales[i] > 0.0 && cfg->scales[i] <= 1.0))
+      return fail(h, VNECT_E_INVALID, "scale %g not in (0, 1]", cfg->scales[i]);
+  if (cfg->max_frames < 1 || cfg->max_streams < 1) return fail(h, VNECT_E_INVALID, "max_frames/max_streams must be >= 1");
+  h->S = cfg->box_size;
+  h->hs = h->S / 8;
+  h->n_scales = cfg->n_scales;
+  h->cap_fw = cfg->max_frames * cfg->n_scales;
+  if (h->cfg.max_input_h <= 0) h->cfg.max_input_h = h->S;
+  if (h->cfg.max_input_w <= 0) h->cfg.max_input_w = h->S;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, VNECT_E_CUDA, "no CUDA device: this library has no CPU path");
+  CU(h, cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CU(h, cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(h, VNECT_E_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+  h->num_sms = prop.multiProcessorCount;
+  CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->own_stream = true;
+  int rc = alloc_prepost(h);
+  if (rc) return rc;
+  return vnect_reset_stream(h, -1);
+}
+
+int vnect_set_weight(vnect_t* h, const char* tf_name, const float* data, const int64_t* shape, int32_t rank) {
+  if (!h || !tf_name || !data || !shape) return fail(h, VNECT_E_INVALID, "null argument");
+  if (h->finalized) return fail(h, VNECT_E_INVALID, "weights are frozen after vnect_finalize");
+  std::vector<int64_t> want;
+  if (!expected_shape(tf_name, &want)) return fail(h, VNECT_E_WEIGHT, "unknown variable '%s'", tf_name);
+  if ((int)want.size() != rank) return fail(h, VNECT_E_WEIGHT, "'%s': rank %d, expected %zu", tf_name, rank, want.size());
+  size_t n = 1;
+  for (int i = 0; i < rank; ++i) {
+    if (shape[i] != want[i]) return fail(h, VNECT_E_WEIGHT, "'%s': dim %d is %lld, expected %lld", tf_name, i, (long long)shape[i], (long long)want[i]);
+    n *= (size_t)shape[i];
+  }
+  HostVar& v = h->vars[tf_name];
+  v.data.assign(data, data + n);
+  v.shape = want;
+  return VNECT_OK;
+}
+
+int vnect_finalize(vnect_t* h) {
+  if (!h) return VNECT_E_INVALID;
+  if (h->finalized) return fail(h, VNECT_E_INVALID, "already finalized");
+  // every variable of the graph must be present (the reference restores all 109 from the checkpoint)
+  for (const ConvDef& c : conv_defs())
+    for (const char* leaf : {"/weights", "/biases"})
+      if (!h->vars.count(std::string(c.scope) + leaf)) return fail(h, VNECT_E_WEIGHT, "missing variable %s%s", c.scope, leaf);
+  for (const char* k : {"res5c_branch1a/kernel", "res5c_branch2a/kernel", "res5c_branch2c/kernel"})
+    if (!h->vars.count(k)) return fail(h, VNECT_E_WEIGHT, "missing variable %s", k);
+  for (const char* v : kBnVars)
+    if (!h->vars.count(std::string("bn5c_branch2a/") + v)) return fail(h, VNECT_E_WEIGHT, "missing variable bn5c_branch2a/%s", v);
+
+  const int S = h->S, nb = h->cap_fw;
+  int rc;
+  {
+    __half* dw = nullptr;
+    float* db = nullptr;
+    rc = upload(h, to_half(pack_stem(h->vars.at("conv1/weights"))), &dw);
+    if (rc) return rc;
+    rc = upload(h, h->vars.at("conv1/biases").data, &db);
+    if (rc) return rc;
+    rc = new_act(h, "conv1", S / 2, S / 2, 64);
+    if (rc) return rc;
+    ConvSpec s;
+    s.kind = CONV_STEM7;
+    s.NB = nb; s.H = S / 2; s.W = S / 2;
+    s.in = h->x1; s.stem_rows_per_parity = h->stem_rpp; s.stem_row_pitch = h->stem_pitch;
+    s.w = dw; s.n_pad = 64; s.n_valid = 64; s.block_n = 64; s.bias = db; s.relu_cols = 64;
+    s.out = h->acts.at("conv1").p; s.ldc = 64; s.epi = EPI_NHWC_F16;
+    Step st;
+    st.kind = 0; st.name = "conv1";
+    std::string err;
+    if (!build_conv(s, h->num_sms, &st.launch, &err)) return fail(h, VNECT_E_CUDA, "conv1: %s", err.c_str());
+    h->steps.push_back(st);
+  }
+  {  // pool1 (vnect_model.py:29)
+    rc = new_act(h, "pool1", S / 4, S / 4, 64);
+    if (rc) return rc;
+    Step st;
+    st.kind = 1; st.name = "pool1";
+    st.pin = h->acts.at("conv1").p; st.pout = h->acts.at("pool1").p;
+    st.H = S / 2; st.W = S / 2; st.C = 64; st.OH = S / 4; st.OW = S / 4;
+    h->steps.push_back(st);
+  }
+  if ((rc = add_block(h, "res2a", "pool1", 64, 64, 256, true, "", false))) return rc;
+  if ((rc = add_block(h, "res2b", "res2a", 256, 64, 256, false, "", false))) return rc;
+  // res2c: the 3x3 reads res2b_branch2a (vnect_model.py:56); its output only feeds stride-2 1x1 convs -> decimated
+  if ((rc = add_block(h, "res2c", "res2b", 256, 64, 256, false, "", true, "res2b_branch2a"))) return rc;
+  if ((rc = add_block(h, "res3a", "res2c", 256, 128, 512, true, "", false))) return rc;
+  if ((rc = add_block(h, "res3b", "res3a", 512, 128, 512, false, "", false))) return rc;
+  if ((rc = add_block(h, "res3c", "res3b", 512, 128, 512, false, "", false))) return rc;
+  if ((rc = add_block(h, "res3d", "res3c", 512, 128, 512, false, "", true))) return rc;
+  if ((rc = add_block(h, "res4a", "res3d", 512, 256, 1024, true, "", false))) return rc;
+  {
+    std::string prev = "res4a";
+    for (const char* b : {"res4b", "res4c", "res4d", "res4e", "res4f"}) {
+      if ((rc = add_block(h, b, prev, 1024, 256, 1024, false, "", false))) return rc;
+      prev = b;
+    }
+  }
+  if ((rc = add_block(h, "res5a", "res4f", 1024, 512, 1024, true, "_new", false))) return rc;
+  ConvOpts relu;
+  if ((rc = add_conv(h, "res5b_branch2a_new", 1, "res5a", "res5b_branch2a_new", 1024, 256, relu))) return rc;
+  if ((rc = add_conv(h, "res5b_branch2b_new", 3, "res5b_branch2a_new", "res5b_branch2b_new", 256, 128, relu))) return rc;
+  if ((rc = add_conv(h, "res5b_branch2c_new", 1, "res5b_branch2b_new", "res5b_branch2c_new", 128, 256, relu))) return rc;
+  {  // res5c head: two transposed convs + BN + ReLU + bone lengths + concat (vnect_model.py:188-209), one kernel
+    const HostVar& g = h->vars.at("bn5c_branch2a/gamma");
+    const HostVar& be = h->vars.at("bn5c_branch2a/beta");
+    const HostVar& mu = h->vars.at("bn5c_branch2a/moving_mean");
+    const HostVar& var = h->vars.at("bn5c_branch2a/moving_variance");
+    std::vector<float> scale(128), bias(192, 0.f);
+    for (int c = 0; c < 128; ++c) {
+      scale[c] = g.data[c] / std::sqrt(var.data[c] + 0.001f);  // tc.layers.batch_norm epsilon default
+      bias[c] = be.data[c] - mu.data[c] * scale[c];
+    }
+    __half* dw = nullptr;
+    float* db = nullptr;
+    rc = upload(h, to_half(pack_deconv(h->vars.at("res5c_branch2a/kernel"), h->vars.at("res5c_branch1a/kernel"), scale)), &dw);
+    if (rc) return rc;
+    if ((rc = upload(h, bias, &db))) return rc;
+    if ((rc = new_act(h, "res5c_branch2a_feat", S / 8, S / 8, 256))) return rc;
+    const Act& ai = h->acts.at("res5b_branch2c_new");
+    ConvSpec s;
+    s.kind = CONV_DECONV4;
+    s.NB = nb; s.H = ai.H; s.W = ai.W; s.in = ai.p; s.cin_pad = 256;
+    s.w = dw; s.n_pad = 192; s.n_valid = 191; s.block_n = 192; s.bias = db; s.relu_cols = 128;
+    s.out = h->acts.at("res5c_branch2a_feat").p; s.ldc = 256; s.epi = EPI_DECONV_HEAD;
+    Step st;
+    st.kind = 0; st.name = "res5c_deconv_head";
+    std::string err;
+    if (!build_conv(s, h->num_sms, &st.launch, &err)) return fail(h, VNECT_E_CUDA, "deconv head: %s", err.c_str());
+    h->steps.push_back(st);
+  }
+  if ((rc = add_conv(h, "res5c_branch2b", 3, "res5c_branch2a_feat", "res5c_branch2b", 212, 128, relu))) return rc;
+  {  // res5c_branch2c: 1x1 128 -> 84, no bias, linear (vnect_model.py:213); channel-planar fp32 for the post-process
+    const HostVar& w = h->vars.at("res5c_branch2c/kernel");
+    __half* dw = nullptr;
+    rc = upload(h, to_half(pack_conv(w, 1, 128, 84, 128, 96)), &dw);
+    if (rc) return rc;
+    const Act& ai = h->acts.at("res5c_branch2b");
+    ConvSpec s;
+    s.kind = CONV_1x1;
+    s.NB = nb; s.H = ai.H; s.W = ai.W; s.in = ai.p; s.cin_pad = 128;
+    s.w = dw; s.n_pad = 96; s.n_valid = 84; s.block_n = 96; s.bias = nullptr; s.relu_cols = 0;
+    s.out = h->maps; s.ldc = 0; s.epi = EPI_PLANAR_F32;
+    Step st;
+    st.kind = 0; st.name = "res5c_branch2c";
+    std::string err;
+    if (!build_conv(s, h->num_sms, &st.launch, &err)) return fail(h, VNECT_E_CUDA, "res5c_branch2c: %s", err.c_str());
+    h->steps.push_back(st);
+  }
+  h->conv_steps = 0;
+  for (const Step& st : h->steps) h->conv_steps += st.kind == 0;
+
+  h->vars.clear();  // host copies no longer needed
+  h->finalized = true;
+  CU(h, cudaDeviceSynchronize());
+  return VNECT_OK;
+}
+
+}  // extern "C"
+
+// run the CNN on the first n forwards of x1 (already filled), on the handle's stream
+static int run_forward(vnect_t* h, int n, cudaEvent_t* layer_events = nullptr) {
+  int ei = 0;
+  for (Step& st : h->steps) {
+    if (layer_events) CU(h, cudaEventRecord(layer_events[ei++], h->stream));
+    if (st.kind == 0) {
+      set_batch(st.launch, n, h->num_sms);
+      CU(h, launch_conv(st.launch, h->stream));
+    } else {
+      const int64_t total = (int64_t)n * st.OH * st.OW * (st.C / 8);
+      maxpool3x3s2_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(st.pin, st.pout, n, st.H, st.W, st.C, st.OH, st.OW);
+      CU(h, cudaGetLastError());
+    }
+    ++h->launches;
+  }
+  if (layer_events) CU(h, cudaEventRecord(layer_events[ei++], h->stream));
+  return VNECT_OK;
+}
+
+struct Geometry {
+  double scaler;
+  int dh, dw, off_x, off_y, mode;
+  bool alias;  // frames already are S x S: the pyramid reads them directly
+};
+
+// utils.img_scale_squarify geometry (utils.py:82-120)
+static Geometry squarify_geometry(int S, int H, int W) {
+  Geometry g;
+  g.scaler = (double)S / (double)std::max(H, W);
+  g.dw = cv_round_host(W * g.scaler);
+  g.dh = cv_round_host(H * g.scaler);
+  g.off_x = g.off_y = 0;
+  if (g.dh > g.dw) g.off_x = S / 2 - g.dw / 2;
+  else g.off_y = S / 2 - g.dh / 2;
+  g.mode = (1.0 / g.scaler == 2.0) ? 1 : 0;  // OpenCV turns exact 2x INTER_LINEAR decimation into INTER_AREA
+  g.alias = (H == S && W == S);
+  return g;
+}
+
+// device frames -> x1 (stem layout) for n_frames * n_scales forwards
+static int run_preprocess(vnect_t* h, const uint8_t* dev_bgr, int n_frames, int H, int W, int64_t pitch,
+                          int64_t frame_stride, const Geometry& g) {
+  const int S = h->S;
+  const uint8_t* sq = dev_bgr;
+  int64_t sq_pitch = pitch, sq_stride = frame_stride;
+  if (!g.alias) {
+    SquarifyParams sp;
+    sp.n_frames = n_frames; sp.H = H; sp.W = W; sp.pitch = pitch; sp.frame_stride = frame_stride; sp.S = S;
+    sp.dh = g.dh; sp.dw = g.dw; sp.off_x = g.off_x; sp.off_y = g.off_y; sp.inv_scale = 1.0 / g.scaler; sp.mode = g.mode;
+    const int64_t total = (int64_t)n_frames * S * S;
+    squarify_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(dev_bgr, h->d_sq, sp);
+    CU(h, cudaGetLastError());
+    ++h->launches;
+    sq = h->d_sq; sq_pitch = (int64_t)S * 3; sq_stride = (int64_t)S * S * 3;
+  }
+  PyramidParams py = h->pyr;
+  py.n_frames = n_frames; py.sq_pitch = sq_pitch; py.sq_frame_stride = sq_stride;
+  const int64_t total = (int64_t)n_frames * h->n_scales * S * S;
+  pyramid_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(sq, h->x1, py);
+  CU(h, cudaGetLastError());
+  ++h->launches;
+  return VNECT_OK;
+}
+
+// validates ids / timestamps on the host exactly where the reference would raise, then stages them to the device
+static int stage_frame_meta(vnect_t* h, int n_frames, const int32_t* stream_ids, const double* t2d, const double* t3d) {
+  if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames %d not in [1, %d]", n_frames, h->cfg.max_frames);
+  std::set<int> seen;
+  for (int i = 0; i < n_frames; ++i) {
+    const int sid = stream_ids ? stream_ids[i] : i;
+    if (sid < 0 || sid >= h->cfg.max_streams) return fail(h, VNECT_E_INVALID, "stream id %d not in [0, %d)", sid, h->cfg.max_streams);
+    if (!seen.insert(sid).second) return fail(h, VNECT_E_INVALID, "stream id %d appears twice in one call (frames of a stream are sequential)", sid);
+    if (h->cfg.filters) {
+      if (!t2d || !t3d) return fail(h, VNECT_E_INVALID, "timestamps required when filters are on");
+      // OneEuroFilter.py:65-66: freq = 1.0 / (timestamp - lasttime) when both are truthy
+      if (h->last_t2d[sid] == h->last_t2d[sid] && h->last_t2d[sid] != 0.0 && t2d[i] != 0.0 && t2d[i] == h->last_t2d[sid])
+        return fail(h, VNECT_E_ZERO_DT, "float division by zero (stream %d: repeated 2D timestamp %.17g)", sid, t2d[i]);
+      if (h->last_t3d[sid] == h->last_t3d[sid] && h->last_t3d[sid] != 0.0 && t3d[i] != 0.0 && t3d[i] == h->last_t3d[sid])
+        return fail(h, VNECT_E_ZERO_DT, "float division by zero (stream %d: repeated 3D timestamp %.17g)", sid, t3d[i]);
+    }
+  }
+  // the previous call's async H2D of these pinned arrays must be done before they are overwritten
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n_frames; ++i) {
+    const int sid = stream_ids ? stream_ids[i] : i;
+    h->h_stream_ids[i] = sid;
+    h->h_t2d[i] = t2d ? t2d[i] : 0.0;
+    h->h_t3d[i] = t3d ? t3d[i] : 0.0;
+    if (h->cfg.filters) {
+      h->last_t2d[sid] = t2d[i];
+      h->last_t3d[sid] = t3d[i];
+    }
+  }
+  CU(h, cudaMemcpyAsync(h->d_stream_ids, h->h_stream_ids, n_frames * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_t2d, h->h_t2d, n_frames * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_t3d, h->h_t3d, n_frames * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return VNECT_OK;
+}
+
+static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, int off_y, double* dev_out2d,
+                           float* dev_out3d) {
+  PostParams p;
+  p.n_frames = n_frames; p.n_scales = h->n_scales; p.hs = h->hs; p.S = h->S;
+  p.maps = h->maps; p.tables = h->d_tables;
+  p.stream_ids = h->d_stream_ids; p.t2d = h->d_t2d; p.t3d = h->d_t3d;
+  p.st2d = h->d_st2d; p.st3d = h->d_st3d;
+  p.cfg2d = {30.0, 1.7, 0.3, 0.4};  // estimator.py:34-39
+  p.cfg3d = {30.0, 0.8, 0.4, 0.4};  // estimator.py:40-45
+  p.filters_on = h->cfg.filters;
+  p.scaler = scaler; p.off_x = off_x; p.off_y = off_y;
+  p.j2_box = h->d_j2_box; p.j3_raw = h->d_j3_raw; p.raw_argmax = h->d_raw_argmax;
+  p.frame_counter = h->d_counter;
+  p.out2d = dev_out2d; p.out3d = dev_out3d;
+  CU(h, cudaMemsetAsync(h->d_counter, 0, n_frames * sizeof(unsigned int), h->stream));
+  const size_t smem = (size_t)h->hs * h->hs * sizeof(double);
+  postprocess_kernel<<<n_frames * kJoints, kPostThreads, smem, h->stream>>>(p);
+  CU(h, cudaGetLastError());
+  ++h->launches;
+  return VNECT_OK;
+}
+
+extern "C" {
+
+int vnect_forward(vnect_t* h, const float* nhwc, int32_t n, float* hm, float* xm, float* ym, float* zm) {
+  if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  if (!nhwc || !hm || !xm || !ym || !zm) return fail(h, VNECT_E_INVALID, "null buffer");
+  if (n < 1 || n > h->cap_fw) return fail(h, VNECT_E_INVALID, "n %d not in [1, %d]", n, h->cap_fw);
+  const int S = h->S, hs = h->hs;
+  const size_t in_elems = (size_t)n * S * S * 3;
+  CU(h, cudaMemcpyAsync(h->d_f32_in, nhwc, in_elems * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  f32_to_stem_kernel<<<grid_for((int64_t)n * S * S, 256, h->num_sms), 256, 0, h->stream>>>(h->d_f32_in, h->x1, n, S, h->stem_rpp, h->stem_pitch);
+  CU(h, cudaGetLastError());
+  ++h->launches;
+  int rc = run_forward(h, n);
+  if (rc) return rc;
+  std::vector<float> planar((size_t)n * 84 * hs * hs);
+  CU(h, cudaMemcpyAsync(planar.data(), h->maps, planar.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  float* outs[4] = {hm, xm, ym, zm};
+  const size_t plane = (size_t)hs * hs;
+  for (int i = 0; i < n; ++i)
+    for (int m = 0; m < 4; ++m)
+      for (int j = 0; j < kJoints; ++j) {
+        const float* src = planar.data() + ((size_t)i * 84 + m * kJoints + j) * plane;
+        float* dst = outs[m] + (size_t)i * plane * kJoints + j;
+        for (size_t px = 0; px < plane; ++px) dst[px * kJoints] = src[px];
+      }
+  return VNECT_OK;
+}
+
+int vnect_estimate_device(vnect_t* h, const uint8_t* dev_bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
+                          int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d,
+                          double* dev_joints2d, float* dev_joints3d) {
+  if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  if (!dev_bgr || !dev_joints2d || !dev_joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
+  if (H < 2 || W < 2 || pitch < (int64_t)W * 3) return fail(h, VNECT_E_INVALID, "bad frame geometry %dx%d pitch %lld", H, W, (long long)pitch);
+  int rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d);
+  if (rc) return rc;
+  const Geometry g = squarify_geometry(h->S, H, W);
+  if ((rc = run_preprocess(h, dev_bgr, n_frames, H, W, pitch, frame_stride, g))) return rc;
+  if ((rc = run_forward(h, n_frames * h->n_scales))) return rc;
+  return run_postprocess(h, n_frames, g.scaler, g.off_x, g.off_y, dev_joints2d, dev_joints3d);
+}
+
+int vnect_estimate(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
+                   int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d,
+                   double* joints2d, float* joints3d) {
+  if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  if (!bgr || !joints2d || !joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
+  if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames %d not in [1, %d]", n_frames, h->cfg.max_frames);
+  if (H < 2 || W < 2 || H > h->cfg.max_input_h || W > h->cfg.max_input_w)
+    return fail(h, VNECT_E_INVALID, "frame %dx%d outside [2, max_input %dx%d]", H, W, h->cfg.max_input_h, h->cfg.max_input_w);
+  if (pitch < (int64_t)W * 3) return fail(h, VNECT_E_INVALID, "pitch smaller than a row");
+  // host -> device, tightly packed on the device
+  const int64_t dpitch = (int64_t)W * 3, dstride = dpitch * H;
+  if (pitch == dpitch && frame_stride == dstride) {
+    CU(h, cudaMemcpyAsync(h->d_frames, bgr, (size_t)dstride * n_frames, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    for (int i = 0; i < n_frames; ++i)
+      CU(h, cudaMemcpy2DAsync(h->d_frames + (size_t)i * dstride, dpitch, bgr + (size_t)i * frame_stride, pitch, dpitch, H, cudaMemcpyHostToDevice, h->stream));
+  }
+  int rc = vnect_estimate_device(h, h->d_frames, n_frames, H, W, dpitch, dstride, stream_ids, t2d, t3d, h->d_out2d, h->d_out3d);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(joints2d, h->d_out2d, (size_t)n_frames * kJoints * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(joints3d, h->d_out3d, (size_t)n_frames * kJoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return VNECT_OK;
+}
+
+int vnect_preprocess(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
+                     int64_t frame_stride, float* out_nhwc, double* scaler_offsets) {
+  if (!h || !h->x1) return fail(h, VNECT_E_INVALID, "handle not created");
+  if (!bgr || !out_nhwc) return fail(h, VNECT_E_INVALID, "null buffer");
+  if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames out of range");
+  if (H < 2 || W < 2 || H > h->cfg.max_input_h || W > h->cfg.max_input_w) return fail(h, VNECT_E_INVALID, "frame size outside max_input");
+  const int64_t dpitch = (int64_t)W * 3, dstride = dpitch * H;
+  for (int i = 0; i < n_frames; ++i)
+    CU(h, cudaMemcpy2DAsync(h->d_frames + (size_t)i * dstride, dpitch, bgr + (size_t)i * frame_stride, pitch, dpitch, H, cudaMemcpyHostToDevice, h->stream));
+  const Geometry g = squarify_geometry(h->S, H, W);
+  int rc = run_preprocess(h, h->d_frames, n_frames, H, W, dpitch, dstride, g);
+  if (rc) return rc;
+  const int n = n_frames * h->n_scales, S = h->S;
+  stem_to_f32_kernel<<<grid_for((int64_t)n * S * S, 256, h->num_sms), 256, 0, h->stream>>>(h->x1, h->d_f32_in, n, S, h->stem_rpp, h->stem_pitch);
+  CU(h, cudaGetLastError());
+  ++h->launches;
+  CU(h, cudaMemcpyAsync(out_nhwc, h->d_f32_in, (size_t)n * S * S * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (scaler_offsets) {
+    scaler_offsets[0] = g.scaler;
+    scaler_offsets[1] = g.off_x;
+    scaler_offsets[2] = g.off_y;
+  }
+  return VNECT_OK;
+}
+
+int vnect_postprocess(vnect_t* h, const float* hm, const float* xm, const float* ym, const float* zm, int32_t n_frames,
+                      const int32_t* stream_ids, const double* t2d, const double* t3d, double scaler, int32_t offset_x,
+                      int32_t offset_y, double* joints2d, float* joints3d, int32_t* raw_argmax) {
+  if (!h || !h->x1) return fail(h, VNECT_E_INVALID, "handle not created");
+  if (!hm || !xm || !ym || !zm || !joints2d || !joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
+  int rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d);
+  if (rc) return rc;
+  const int n = n_frames * h->n_scales, hs = h->hs;
+  const size_t plane = (size_t)hs * hs;
+  std::vector<float> planar((size_t)n * 84 * plane);
+  const float* ins[4] = {hm, xm, ym, zm};
+  for (int i = 0; i < n; ++i)
+    for (int m = 0; m < 4; ++m)
+      for (int j = 0; j < kJoints; ++j) {
+        float* dst = planar.data() + ((size_t)i * 84 + m * kJoints + j) * plane;
+        const float* src = ins[m] + (size_t)i * plane * kJoints + j;
+        for (size_t px = 0; px < plane; ++px) dst[px] = src[px * kJoints];
+      }
+  CU(h, cudaMemcpyAsync(h->maps, planar.data(), planar.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = run_postprocess(h, n_frames, scaler, offset_x, offset_y, h->d_out2d, h->d_out3d))) return rc;
+  CU(h, cudaMemcpyAsync(joints2d, h->d_out2d, (size_t)n_frames * kJoints * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(joints3d, h->d_out3d, (size_t)n_frames * kJoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (raw_argmax)
+    CU(h, cudaMemcpyAsync(raw_argmax, h->d_raw_argmax, (size_t)n_frames * kJoints * 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return VNECT_OK;
+}
+
+int vnect_reset_stream(vnect_t* h, int32_t stream_id) {
+  if (!h || !h->d_st2d) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  const int ms = h->cfg.max_streams;
+  if (stream_id < -1 || stream_id >= ms) return fail(h, VNECT_E_INVALID, "stream id out of range");
+  const int lo = stream_id < 0 ? 0 : stream_id, hi = stream_id < 0 ? ms : stream_id + 1;
+  std::vector<FilterState> s2((size_t)(hi - lo) * kJoints * 2), s3((size_t)(hi - lo) * kJoints * 3);
+  FilterState z;
+  memset(&z, 0, sizeof z);
+  z.freq = 30.0;  // estimator.py:35,41
+  for (auto& s : s2) s = z;
+  for (auto& s : s3) s = z;
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(h->d_st2d + (size_t)lo * kJoints * 2, s2.data(), s2.size() * sizeof(FilterState), cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(h->d_st3d + (size_t)lo * kJoints * 3, s3.data(), s3.size() * sizeof(FilterState), cudaMemcpyHostToDevice));
+  for (int i = lo; i < hi; ++i) h->last_t2d[i] = h->last_t3d[i] = NAN;
+  return VNECT_OK;
+}
+
+int vnect_filter(vnect_t* h, int32_t stream_id, int32_t dim, double t, double* values) {
+  if (!h || !h->x1 || !values) return fail(h, VNECT_E_INVALID, "handle not created / null buffer");
+  if (stream_id < 0 || stream_id >= h->cfg.max_streams || (dim != 2 && dim != 3)) return fail(h, VNECT_E_INVALID, "bad stream id or dim");
+  std::vector<double>& last = dim == 2 ? h->last_t2d : h->last_t3d;
+  if (last[stream_id] == last[stream_id] && last[stream_id] != 0.0 && t != 0.0 && t == last[stream_id])
+    return fail(h, VNECT_E_ZERO_DT, "float division by zero (stream %d: repeated timestamp %.17g)", stream_id, t);
+  last[stream_id] = t;
+  const int n = kJoints * dim;
+  CU(h, cudaMemcpyAsync(h->d_filter_scratch, values, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  FilterState* st = dim == 2 ? h->d_st2d + (size_t)stream_id * kJoints * 2 : h->d_st3d + (size_t)stream_id * kJoints * 3;
+  const FilterCfg cfg = dim == 2 ? FilterCfg{30.0, 1.7, 0.3, 0.4} : FilterCfg{30.0, 0.8, 0.4, 0.4};
+  joint_filter_kernel<<<1, 64, 0, h->stream>>>(st, cfg, h->d_filter_scratch, t, dim);
+  CU(h, cudaGetLastError());
+  ++h->launches;
+  CU(h, cudaMemcpyAsync(values, h->d_filter_scratch, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return VNECT_OK;
+}
+
+int vnect_set_stream(vnect_t* h, void* cuda_stream) {
+  if (!h) return VNECT_E_INVALID;
+  if (h->own_stream && h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  h->own_stream = false;
+  return VNECT_OK;
+}
+
+int vnect_synchronize(vnect_t* h) {
+  if (!h) return VNECT_E_INVALID;
+  CU(h, cudaStreamSynchronize(h->stream));
+  return VNECT_OK;
+}
+
+int vnect_get_tap(vnect_t* h, const char* name, int32_t n, float* out_nhwc, int64_t capacity_elems, int32_t* dims4) {
+  if (!h || !h->finalized || !name) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  auto it = h->acts.find(name);
+  if (it == h->acts.end()) return fail(h, VNECT_E_INVALID, "no activation named '%s'", name);
+  const Act& a = it->second;
+  if (n < 1 || n > h->cap_fw) return fail(h, VNECT_E_INVALID, "n out of range");
+  if (dims4) { dims4[0] = n; dims4[1] = a.H; dims4[2] = a.W; dims4[3] = a.C; }
+  const size_t elems = (size_t)n * a.H * a.W * a.C;
+  if (!out_nhwc) return VNECT_OK;
+  if ((int64_t)elems > capacity_elems) return fail(h, VNECT_E_INVALID, "buffer too small for tap '%s'", name);
+  std::vector<__half> tmp(elems);
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(tmp.data(), a.p, elems * sizeof(__half), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < elems; ++i) out_nhwc[i] = __half2float(tmp[i]);
+  return VNECT_OK;
+}
+
+int64_t vnect_launch_count(vnect_t* h) { return h ? h->launches : 0; }
+
+const char* vnect_step_name(vnect_t* h, int32_t i) {
+  if (!h || i < 0 || i >= (int)h->steps.size()) return nullptr;
+  return h->steps[i].name.c_str();
+}
+
+double vnect_info(vnect_t* h, const char* key) {
+  if (!h || !key) return NAN;
+  const std::string k = key;
+  if (k == "num_sms") return h->num_sms;
+  if (k == "conv_launches_per_forward") return h->conv_steps;
+  if (k == "launches_per_forward") return (double)h->steps.size();
+  if (k == "gemm_flops_per_forward") {  // executed GEMM work incl. channel / tile padding, per image
+    double f = 0;
+    for (const Step& st : h->steps)
+      if (st.kind == 0) f += st.launch.flops / h->cap_fw;
+    return f;
+  }
+  if (k == "hm_size") return h->hs;
+  if (k == "max_forwards") return h->cap_fw;
+  return NAN;
+}
+
+int vnect_time_forward(vnect_t* h, int32_t n, int32_t reps, float* total_ms, float* per_layer_ms) {
+  if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  if (n < 1 || n > h->cap_fw || reps < 1) return fail(h, VNECT_E_INVALID, "bad n/reps");
+  const int ns = (int)h->steps.size();
+  std::vector<cudaEvent_t> ev(ns + 1);
+  for (auto& e : ev) CU(h, cudaEventCreate(&e));
+  cudaEvent_t e0, e1;
+  CU(h, cudaEventCreate(&e0));
+  CU(h, cudaEventCreate(&e1));
+  int rc = run_forward(h, n);  // warm-up
+  if (rc) return rc;
+  CU(h, cudaEventRecord(e0, h->stream));
+  for (int r = 0; r < reps; ++r)
+    if ((rc = run_forward(h, n))) return rc;
+  CU(h, cudaEventRecord(e1, h->stream));
+  CU(h, cudaEventSynchronize(e1));
+  float ms = 0;
+  CU(h, cudaEventElapsedTime(&ms, e0, e1));
+  if (total_ms) *total_ms = ms / reps;
+  if (per_layer_ms) {
+    std::vector<double> acc(ns, 0.0);
+    for (int r = 0; r < reps; ++r) {
+      if ((rc = run_forward(h, n, ev.data()))) return rc;
+      CU(h, cudaStreamSynchronize(h->stream));
+      for (int i = 0; i < ns; ++i) {
+        float t = 0;
+        CU(h, cudaEventElapsedTime(&t, ev[i], ev[i + 1]));
+        acc[i] += t;
+      }
+    }
+    for (int i = 0; i < ns; ++i) per_layer_ms[i] = (float)(acc[i] / reps);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return VNECT_OK;
+}
+
+void vnect_destroy(vnect_t* h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_stream_ids) cudaFreeHost(h->h_stream_ids);
+  if (h->h_t2d) cudaFreeHost(h->h_t2d);
+  if (h->h_t3d) cudaFreeHost(h->h_t3d);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+}  // extern "C"
