@@ -1,0 +1,312 @@
+"""Parity of the CUDA hot path against the CPU oracle, through the C ABI (run on a B200: pytest -m gpu).
+
+Tolerances (BASELINE.json north_star): maps within 1e-2 relative (we assert rel-L2 and normwise-max < 3e-3: fp16
+operands, fp32 accumulate), argmax indices equal except documented near-ties, 3D joints within 1 mm.  Pre- and
+post-processing are integer / float64 work and must be bit-exact.
+"""
+import numpy as np
+import pytest
+
+from oracle import prepost, synth
+from oracle.forward import OracleNet
+from tests.golden.make_golden import POST_CASES, post_frame_maps, timestamps
+
+pytestmark = pytest.mark.gpu
+
+SCALES2 = [1.0, 0.7]
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b))
+
+
+@pytest.fixture(scope="module")
+def engine_w1(w1):
+    from vnect_b200 import VNectEngine
+    eng = VNectEngine(w1, SCALES2, max_frames=8, max_streams=8, max_input=(540, 960))
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def engine_w0(w0):
+    from vnect_b200 import VNectEngine
+    eng = VNectEngine(w0, SCALES2, max_frames=8, max_streams=8)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def oracle_net_w1(w1):
+    return OracleNet(w1)
+
+
+class Clock:
+    def __init__(self):
+        self.q = []
+
+    def __call__(self):
+        return self.q.pop(0)
+
+
+# ------------------------------------------------------------------------------------------------ K1 preprocessing
+@pytest.mark.parametrize("hw_seed", [(368, 368, 1), (540, 960, 2), (300, 200, 3), (368, 200, 5), (101, 97, 6),
+                                     (367, 251, 7)])
+def test_preprocess_bit_exact(engine_w1, hw_seed):
+    h, w, seed = hw_seed
+    img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    got, scaler, offs = engine_w1.preprocess(img)
+    ref, rscaler, roffs = prepost.gen_input_batch(img, 368, SCALES2)
+    assert scaler == rscaler and offs == roffs
+    assert np.array_equal(got, ref.astype(np.float16).astype(np.float32))  # device stores the fp16 network input
+
+
+def test_preprocess_exact_2x_decimation_and_three_scales():
+    from vnect_b200 import VNectEngine
+    scales = [1, 0.85, 0.7]
+    eng = VNectEngine(False, scales, max_frames=2, max_input=(736, 736))
+    try:
+        imgs = np.random.default_rng(9).integers(0, 256, (2, 736, 736, 3), dtype=np.uint8)
+        got, scaler, offs = eng.preprocess(imgs)
+        for i in range(2):
+            ref, rs, ro = prepost.gen_input_batch(imgs[i], 368, scales)
+            assert np.array_equal(got[3 * i:3 * i + 3], ref.astype(np.float16).astype(np.float32))
+            assert (scaler, offs) == (rs, ro)
+    finally:
+        eng.close()
+
+
+def test_preprocess_noncontiguous_crop(engine_w1):
+    frame = np.random.default_rng(10).integers(0, 256, (540, 960, 3), dtype=np.uint8)
+    crop = frame[40:460, 100:700, :]  # what run_estimator.py:100 passes
+    got, _, _ = engine_w1.preprocess(crop)
+    ref, _, _ = prepost.gen_input_batch(np.ascontiguousarray(crop), 368, SCALES2)
+    assert np.array_equal(got, ref.astype(np.float16).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------------ CNN forward
+LAYER_TAPS = ["conv1", "pool1", "res2a_branch2a", "res2a_branch2b", "res2a", "res2b", "res2c", "res3a", "res3d",
+              "res4a", "res4f", "res5a", "res5b_branch2c_new", "res5c_branch2a_feat", "res5c_branch2b"]
+
+
+def test_forward_layer_taps_and_maps_w1(engine_w1, oracle_net_w1):
+    x = np.stack([prepost.gen_input_batch(synth.frame_c2(i), 368, [1.0])[0][0] for i in range(2)])
+    outs = engine_w1.forward(x)
+    refs, taps = oracle_net_w1(x, want_taps=True)
+    for name in LAYER_TAPS:
+        got, ref = engine_w1.tap(name, 2), taps[name]
+        if name in ("res2c", "res3d"):
+            ref = ref[:, ::2, ::2, :]  # only the pixels the stride-2 consumers read are materialised
+        if name == "res5c_branch2a_feat":
+            assert np.all(got[..., 212:] == 0)
+            got = got[..., :212]
+        assert got.shape == ref.shape, name
+        assert rel_l2(got, ref) < 2e-3, name
+    for got, ref in zip(outs, refs):
+        assert got.shape == (2, 46, 46, 21) and got.dtype == np.float32
+        assert rel_l2(got, ref) < 3e-3
+        assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-3
+    agree = (outs[0].reshape(2, -1, 21).argmax(1) == refs[0].reshape(2, -1, 21).argmax(1)).mean()
+    assert agree >= 0.95
+
+
+def test_forward_w0_real_picture(engine_w0, oracle_net_w0, golden):
+    pic = golden("test_pic.npz")["img"]
+    batch, _, _ = prepost.gen_input_batch(pic, 368, SCALES2)
+    outs = engine_w0.forward(batch)
+    refs = oracle_net_w0(batch)
+    for got, ref in zip(outs, refs):
+        assert rel_l2(got, ref) < 3e-3
+
+
+def test_forward_is_batch_invariant(engine_w1):
+    x = np.stack([prepost.gen_input_batch(synth.frame_c2(i), 368, [1.0])[0][0] for i in range(5)])
+    all5 = engine_w1.forward(x)
+    one = engine_w1.forward(x[3:4])
+    for a, b in zip(all5, one):
+        assert np.array_equal(a[3:4], b)  # bit-identical regardless of batch composition
+
+
+# ------------------------------------------------------------------------------------------------ K8 post-processing
+@pytest.mark.parametrize("case", POST_CASES, ids=[c[0] for c in POST_CASES])
+def test_postprocess_against_reference_golden(case, golden):
+    """Committed outputs of the reference's own estimator/utils/OneEuroFilter (tests/golden/post.npz)."""
+    from vnect_b200 import VNectEngine
+    name, seed, scales, nf, pat = case
+    g = golden("post.npz")
+    eng = VNectEngine(False, scales, max_frames=1, max_streams=1)
+    try:
+        t2, t3 = timestamps(pat, nf, seed)
+        for k in range(nf):
+            maps = post_frame_maps(seed, k, scales)
+            j2, j3, raw = eng.postprocess(maps, 1.0, (0, 0), [0], [t2[k]], [t3[k]])
+            assert np.array_equal(j2[0], g[name + "/j2"][k]), (name, k)  # float64, bit-exact
+            # the fixture ran the 3D filter in float32 (numpy >= 2 promotion); the CUDA path is float64 ('legacy')
+            assert np.abs(j3[0].astype(np.float64) - g[name + "/j3"][k]).max() < 1e-2
+    finally:
+        eng.close()
+
+
+def test_postprocess_bit_exact_vs_oracle_legacy(engine_w1):
+    clock = Clock()
+    cur = {}
+    ref = prepost.OracleEstimator(lambda b: cur["m"], SCALES2, clock=clock, promotion="legacy")
+    engine_w1.reset()
+    for k in range(4):
+        cur["m"] = synth.synthetic_maps(700 + k, 2, border_joints=(k % 2 == 0))
+        t2, t3 = 10.0 + 0.05 * k, 10.003 + 0.05 * k
+        clock.q = [t2, t3]
+        r2, r3 = ref(np.zeros((368, 368, 3), np.uint8))
+        j2, j3, raw = engine_w1.postprocess(cur["m"], 1.0, (0, 0), [0], [t2], [t3])
+        assert np.array_equal(raw[0], ref.last["joints_2d_raw"].astype(np.int32))
+        assert np.array_equal(j2[0], r2)
+        assert np.array_equal(j3[0], r3)
+
+
+def test_postprocess_rescale_and_batch(engine_w1):
+    """8 independent streams in one call == 8 single calls; offsets / scaler applied like estimator.py:138-139."""
+    maps = [synth.synthetic_maps(800 + i, 2) for i in range(8)]
+    batch = tuple(np.concatenate([m[c] for m in maps]) for c in range(4))
+    engine_w1.reset()
+    j2, j3, _ = engine_w1.postprocess(batch, 0.684, (58, 0), np.arange(8), np.full(8, 3.0), np.full(8, 3.01))
+    for i in range(8):
+        clock = Clock()
+        clock.q = [3.0, 3.01]
+        ref = prepost.OracleEstimator(lambda b: maps[i], SCALES2, clock=clock)
+        ref(np.zeros((368, 368, 3), np.uint8))
+        r2 = ref.last["joints_2d_box"].copy()
+        r2[:, 0] = (r2[:, 0] - 0) / 0.684
+        r2[:, 1] = (r2[:, 1] - 58) / 0.684
+        assert np.array_equal(j2[i], r2)
+
+
+# ------------------------------------------------------------------------------------------------ end to end
+def _count_argmax_diffs(j2, r2):
+    return int((np.abs(j2 - r2).max(axis=1) > 1e-9).sum())
+
+
+def test_estimate_stream_vs_oracle(engine_w0, oracle_net_w0):
+    clock = Clock()
+    ref = prepost.OracleEstimator(oracle_net_w0, SCALES2, clock=clock)
+    engine_w0.reset()
+    diffs = 0
+    for k in range(4):
+        img = synth.stream_frame(0, k)
+        t2, t3 = 1000 + k / 30, 1000 + k / 30 + 0.004
+        clock.q = [t2, t3]
+        r2, r3 = ref(img)
+        j2, j3 = engine_w0.estimate(img, [0], [t2], [t3])
+        assert j2.dtype == np.float64 and j3.dtype == np.float32
+        d = _count_argmax_diffs(j2[0], r2)
+        diffs += d
+        if d == 0:
+            assert np.abs(j3[0] - r3).max() < 1.0  # mm
+    assert diffs <= 2  # documented near-ties only (fp16 CNN vs fp32 oracle)
+
+
+def test_estimate_matches_reference_golden(engine_w0, golden):
+    """tests/golden/e2e.npz: the reference's own estimator on the fp32 CNN restatement (C2-like frames)."""
+    g = golden("e2e.npz")
+    engine_w0.reset()
+    frames = np.stack([synth.frame_c2(i) for i in range(3)])
+    j2, j3 = engine_w0.estimate(frames, [0, 1, 2], np.full(3, 1000.0), np.full(3, 1000.004))
+    total = 0
+    for i in range(3):
+        d = _count_argmax_diffs(j2[i], g[f"c2_{i}/j2"])
+        total += d
+        if d == 0:
+            assert np.abs(j3[i] - g[f"c2_{i}/j3"]).max() < 1.0
+    assert total <= 2
+
+
+def test_estimate_non_square_input(w0, oracle_net_w0, golden):
+    """C1: the 538x368 test picture, single scale (run_pic.py path)."""
+    from vnect_b200 import VNectEngine
+    pic = golden("test_pic.npz")["img"]
+    eng = VNectEngine(w0, [1.0], max_frames=1, max_input=pic.shape[:2])
+    try:
+        j2, j3 = eng.estimate(pic, [0], [1000.0], [1000.004])
+        g = golden("e2e.npz")
+        d = _count_argmax_diffs(j2[0], g["c1/j2"])
+        assert d <= 1
+        if d == 0:
+            assert np.abs(j3[0] - g["c1/j3"]).max() < 1.0
+    finally:
+        eng.close()
+
+
+def test_full_size_batch_properties(w0):
+    """BASELINE C2 size (64 frames, 128 forwards): finite, in range, root joint at the origin, and identical to the
+    same frames processed as two half batches (bit-exact, independent of batch composition)."""
+    from vnect_b200 import VNectEngine
+    eng = VNectEngine(w0, SCALES2, max_frames=64, max_streams=64)
+    try:
+        frames = np.stack([synth.frame_c2(i) for i in range(64)])
+        ids = np.arange(64)
+        j2, j3 = eng.estimate(frames, ids, np.full(64, 1.0), np.full(64, 1.004))
+        assert np.isfinite(j2).all() and np.isfinite(j3).all()
+        assert j2.min() >= 0 and j2.max() <= 367
+        assert np.all(j3[:, 14, :] == 0)
+        eng.reset()
+        a2, a3 = eng.estimate(frames[:32], ids[:32], np.full(32, 1.0), np.full(32, 1.004))
+        b2, b3 = eng.estimate(frames[32:], ids[32:], np.full(32, 1.0), np.full(32, 1.004))
+        assert np.array_equal(np.concatenate([a2, b2]), j2) and np.array_equal(np.concatenate([a3, b3]), j3)
+        assert eng.launch_count() > 150
+    finally:
+        eng.close()
+
+
+# ------------------------------------------------------------------------------------------------ error behaviour
+def test_errors(engine_w0):
+    img = synth.frame_c2(0)
+    engine_w0.reset()
+    engine_w0.estimate(img, [0], [5.0], [5.1])
+    with pytest.raises(ZeroDivisionError):  # src/OneEuroFilter.py:66 on a repeated timestamp
+        engine_w0.estimate(img, [0], [5.0], [5.2])
+    with pytest.raises(ValueError):  # frames of one stream are sequential
+        engine_w0.estimate(np.stack([img, img]), [1, 1], [6.0, 6.0], [6.1, 6.1])
+    with pytest.raises(ValueError):
+        engine_w0.estimate(np.zeros((9, 368, 368, 3), np.uint8))  # more than max_frames
+    with pytest.raises(ValueError):
+        engine_w0.estimate(np.zeros((1, 600, 368, 3), np.uint8))  # larger than max_input
+    with pytest.raises(ValueError):
+        engine_w0.forward(np.zeros((1, 100, 100, 3), np.float32))
+
+
+def test_weight_ingest_errors(w0):
+    from vnect_b200 import VNectEngine
+    bad = dict(w0)
+    del bad["res4c_branch2b/biases"]
+    with pytest.raises(KeyError):
+        VNectEngine(bad, [1.0])
+    bad = dict(w0)
+    bad["conv1/weights"] = bad["conv1/weights"][:, :, :, :32]
+    with pytest.raises(KeyError):
+        VNectEngine(bad, [1.0])
+
+
+# ------------------------------------------------------------------------------------------------ drop-in class
+def test_vnect_estimator_dropin(w0, oracle_net_w0, capsys):
+    from vnect_b200 import VNectEstimator
+    ticks = iter(np.arange(100.0, 200.0, 0.02))
+    est = VNectEstimator(weights=w0, clock=lambda: float(next(ticks)))
+    assert est.scales == [1, 0.85, 0.7] and est.box_size == 368 and est.hm_factor == 8 and est.joints_sum == 21
+    assert len(est.joint_parents) == 21
+    est.scales = [1.0, 0.7]  # callers may change scales after construction (src/estimator.py:30-32)
+    img = synth.stream_frame(3, 0)[20:340, 30:300]  # a crop view, like run_estimator.py:100
+    j2, j3 = est(img)
+    out = capsys.readouterr().out
+    assert "Initializing VNect Estimator" in out and "FPS:" in out
+    assert j2.shape == (21, 2) and j2.dtype == np.float64 and j3.shape == (21, 3) and j3.dtype == np.float32
+    j2[:, 0] += 5  # callers mutate the result in place (run_estimator.py:104-105)
+    j2b, _ = est(img)
+    assert j2b is not j2
+    clock = Clock()
+    clock.q = [100.0, 100.02]
+    ref = prepost.OracleEstimator(oracle_net_w0, [1.0, 0.7], clock=clock)
+    r2, r3 = ref(np.ascontiguousarray(img))
+    j2[:, 0] -= 5
+    assert _count_argmax_diffs(j2, r2) <= 1
+    batch, scaler, offs = VNectEstimator.gen_input_batch(np.ascontiguousarray(img), 368, [1.0, 0.7])
+    rb, rs, ro = prepost.gen_input_batch(np.ascontiguousarray(img), 368, [1.0, 0.7])
+    assert np.array_equal(batch, rb.astype(np.float16).astype(np.float32)) and scaler == rs and offs == ro
