@@ -22,12 +22,19 @@ namespace vnect {
 
 constexpr int kBlockM = 128;
 constexpr int kGemmThreads = 256;
+constexpr int kSmemBudget = 227 * 1024;
 
 enum EpiKind : int {
   EPI_NHWC_F16 = 0,    // fp16 NHWC, bias (+residual) (+ReLU)
   EPI_PLANAR_F32 = 1,  // fp32 channel-planar [n][c][OH][OW] (heat-map / location-map output, read by the post-process)
-  EPI_DECONV_HEAD = 2  // fused res5c head: BN(folded)+ReLU on cols 0-127, deltas on 128-190, bone lengths -> 191-211
+  EPI_DECONV_HEAD = 2, // fused res5c head: BN(folded)+ReLU on cols 0-127, deltas on 128-190, bone lengths -> 191-211
+  EPI_TMA = 3,         // fp16 NHWC through swizzled smem staging + TMA tensor store (coalesced, clipped), bias (+ReLU)
+  EPI_TMA_RES = 4      // same, plus the residual tile prefetched by TMA (warp 3) while the MMAs run
 };
+
+constexpr int kEpiChunkBytes = kBlockM * 128;  // one 64-column fp16 chunk of a tile: 128 rows x 128 B
+constexpr int kOutStages = 2;
+constexpr int kResStages = 4;
 
 struct ConvGemmParams {
   // ---- tiling of the GEMM rows
@@ -41,6 +48,7 @@ struct ConvGemmParams {
   int b_rows_per_phase;  // padded Cout
   signed char tap_dx[16], tap_dy[16], tap_dp[16];  // [phase * taps + tap]
   uint32_t stage_tx_bytes;
+  uint32_t res_tx_bytes;  // bytes of one residual chunk box (EPI_TMA_RES)
   // ---- epilogue
   int n_valid;    // valid output columns
   int relu_cols;  // ReLU on columns < relu_cols (multiple of 32)
@@ -54,22 +62,27 @@ struct ConvGemmParams {
   int decimate;  // 1: only rows with even (y, x) are stored, at (y/2, x/2) -- feeds the stride-2 1x1 convs
 };
 
-template <int BLOCK_N, int SWZ>
+template <int BLOCK_N, int SWZ, int EPI>
 struct GemmCfg {
   static constexpr int BLOCK_K = SWZ / 2;  // fp16 elements per smem row
   static constexpr int A_BYTES = kBlockM * SWZ;
   static constexpr int B_BYTES = BLOCK_N * SWZ;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int EPI_BYTES = (EPI == EPI_TMA)       ? kOutStages * kEpiChunkBytes
+                                   : (EPI == EPI_TMA_RES) ? (kOutStages + kResStages) * kEpiChunkBytes
+                                                          : 0;
+  static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                         : (2 * BLOCK_N <= 64)  ? 64
                                         : (2 * BLOCK_N <= 128) ? 128
                                         : (2 * BLOCK_N <= 256) ? 256
                                                                : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "epilogue walks 32-column chunks");
+  static_assert((EPI != EPI_TMA && EPI != EPI_TMA_RES) || BLOCK_N % 64 == 0, "TMA epilogue walks 64-column chunks");
 };
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
@@ -80,20 +93,26 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 template <int BLOCK_N, int SWZ, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ ConvGemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, SWZ>;
+  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI>;
+  constexpr bool kTmaEpi = (EPI == EPI_TMA || EPI == EPI_TMA_RES);
   constexpr int BLOCK_K = Cfg::BLOCK_K;
   constexpr int STAGES = Cfg::STAGES;
   constexpr uint32_t IDESC = make_idesc_f16(kBlockM, BLOCK_N, false);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;           // kOutStages x 16 KB (TMA epilogues only)
+  uint8_t* res_stage = out_stage + kOutStages * kEpiChunkBytes;    // kResStages x 16 KB (EPI_TMA_RES only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* res_full = bars + 2 * STAGES + 4;
+  uint64_t* res_empty = bars + 2 * STAGES + 4 + kResStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * kResStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,6 +128,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 4);
     }
+    for (int s = 0; s < kResStages; ++s) {
+      mbar_init(&res_full[s], 1);
+      mbar_init(&res_empty[s], 1);
+    }
+    if constexpr (kTmaEpi) tma_prefetch_desc(&tmap_out);
+    if constexpr (EPI == EPI_TMA_RES) tma_prefetch_desc(&tmap_res);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
@@ -192,6 +217,124 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (acc == 0) acc_phase ^= 1;
       }
     }
+  } else if (warp == 3) {
+    // ================================================================ residual prefetcher (EPI_TMA_RES only)
+    if constexpr (EPI == EPI_TMA_RES) {
+      if (elect_one()) {
+        uint32_t ctr = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int n_tile = tile % p.num_n_tiles;
+          const int m_tile = (tile / p.num_n_tiles) % p.num_m_tiles;
+          int cx, cy, cn;
+          if (p.mode == 0) {
+            cx = m_tile * kBlockM; cy = 0; cn = 0;
+          } else {
+            const int per_img = p.tiles_x * p.tiles_y;
+            cn = m_tile / per_img;
+            const int t2 = m_tile - cn * per_img;
+            cy = (t2 / p.tiles_x) * p.th;
+            cx = (t2 % p.tiles_x) * p.tw;
+          }
+          for (int c0 = 0; c0 < BLOCK_N; c0 += 64, ++ctr) {
+            const int rb = ctr % kResStages;
+            mbar_wait(&res_empty[rb], ((ctr / kResStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&res_full[rb], p.res_tx_bytes);
+            tma_load_5d(res_stage + rb * kEpiChunkBytes, &tmap_res, &res_full[rb], n_tile * BLOCK_N + c0, cx, cy, 0, cn);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && kTmaEpi) {
+    // ================================================================ epilogue through smem staging + TMA store
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const bool leader = (threadIdx.x == 128);
+    const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    int acc = 0;
+    uint32_t acc_phase = 0, ctr = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.num_n_tiles;
+      const int m_tile = (tile / p.num_n_tiles) % p.num_m_tiles;
+      int cx, cy, cn;
+      if (p.mode == 0) {
+        cx = m_tile * kBlockM; cy = 0; cn = 0;
+      } else {
+        const int per_img = p.tiles_x * p.tiles_y;
+        cn = m_tile / per_img;
+        const int t2 = m_tile - cn * per_img;
+        cy = (t2 / p.tiles_x) * p.th;
+        cx = (t2 % p.tiles_x) * p.tw;
+      }
+      const int col_base = n_tile * BLOCK_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 64, ++ctr) {
+        uint32_t v[64];
+        tmem_ld_32x32(t_row + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_32x32(t_row + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_wait();
+        if (c0 + 64 >= BLOCK_N) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const int ob = ctr % kOutStages;
+        const int rb = ctr % kResStages;
+        uint8_t* ostage = out_stage + ob * kEpiChunkBytes;
+        const uint8_t* rstage = res_stage + rb * kEpiChunkBytes;
+        if constexpr (EPI == EPI_TMA_RES) mbar_wait(&res_full[rb], (ctr / kResStages) & 1);
+        if (leader) bulk_wait_group_read<kOutStages - 1>();  // the store that last used `ostage` has read it
+        named_bar_sync(1, 128);
+        const int col0 = col_base + c0;
+        const bool relu = col0 < p.relu_cols;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 8 x 16 B = this row's 64 output channels
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+          if (p.bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * j));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * j + 4));
+            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+          }
+          const uint32_t off = row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);  // 128B swizzle, as the TMA unit does
+          if constexpr (EPI == EPI_TMA_RES) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(rstage + off);
+            const __half2* h = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 t = __half22float2(h[e]);
+              f[2 * e] += t.x;
+              f[2 * e + 1] += t.y;
+            }
+          }
+          if (relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          uint4 o;
+          o.x = pack_half2(f[0], f[1]);
+          o.y = pack_half2(f[2], f[3]);
+          o.z = pack_half2(f[4], f[5]);
+          o.w = pack_half2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(ostage + off) = o;
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(1, 128);
+        if (leader) {
+          tma_store_5d(&tmap_out, ostage, col0, cx, cy, 0, cn);
+          bulk_commit_group();
+          if constexpr (EPI == EPI_TMA_RES) mbar_arrive(&res_empty[rb]);
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (leader) bulk_wait_group<0>();  // all tensor stores complete before the CTA retires its smem
   } else if (warp >= 4) {
     // ================================================================ epilogue (4 warps = 128 TMEM lanes = 128 rows)
     const int q = warp & 3;

@@ -85,7 +85,7 @@ struct ConvSpec {
 };
 
 struct ConvLaunch {
-  CUtensorMap tmap_a, tmap_b;
+  CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res;
   ConvGemmParams p;
   int block_n = 0, swz = 128, epi = 0, grid = 0;
   size_t smem = 0;
@@ -227,6 +227,38 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
   uint64_t bs[1] = {(uint64_t)k_total * 2};
   uint32_t bb[2] = {(uint32_t)block_k, (uint32_t)s.block_n};
   if (!encode_tmap(&L->tmap_b, s.w, 2, bd, bs, bb, swz, err)) return false;
+  L->tmap_out = L->tmap_a;  // placeholders for the epilogues that do not use them
+  L->tmap_res = L->tmap_a;
+  if (s.epi == EPI_TMA || s.epi == EPI_TMA_RES) {
+    // output (and residual) tiles leave / enter through swizzled smem in 64-channel chunks: same row tiling as A
+    if (s.decimate || s.kind == CONV_DECONV4 || s.ldc % 8 != 0) {
+      if (err) *err = "TMA epilogue needs a plain NHWC output";
+      return false;
+    }
+    uint64_t od[5], os[4];
+    uint32_t ob[5];
+    auto act_map = [&](const void* ptr, int ld, CUtensorMap* m) {
+      if (p.mode == 0) {
+        od[0] = ld; od[1] = p.M; od[2] = 1; od[3] = 1; od[4] = 1;
+        os[0] = (uint64_t)ld * 2; os[1] = os[2] = os[3] = (uint64_t)ld * 2 * p.M;
+        ob[0] = 64; ob[1] = kBlockM; ob[2] = 1; ob[3] = 1; ob[4] = 1;
+      } else {
+        od[0] = ld; od[1] = s.W; od[2] = s.H; od[3] = 1; od[4] = s.NB;
+        os[0] = (uint64_t)ld * 2; os[1] = os[0] * s.W; os[2] = os[1] * s.H; os[3] = os[2];
+        ob[0] = 64; ob[1] = p.tw; ob[2] = p.th; ob[3] = 1; ob[4] = 1;
+      }
+      return encode_tmap(m, ptr, 5, od, os, ob, 128, err);
+    };
+    if (!act_map(s.out, s.ldc, &L->tmap_out)) return false;
+    if (s.epi == EPI_TMA_RES) {
+      if (!s.residual) {
+        if (err) *err = "EPI_TMA_RES without a residual";
+        return false;
+      }
+      if (!act_map(s.residual, s.ldr, &L->tmap_res)) return false;
+      p.res_tx_bytes = ob[1] * ob[2] * 128;
+    }
+  }
   const int total = p.phases * p.num_m_tiles * p.num_n_tiles;
   L->grid = total < num_sms ? total : num_sms;
   L->flops = 2.0 * p.phases * (double)p.M * s.n_pad * k_total;
@@ -235,7 +267,7 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
 
 template <int BLOCK_N, int SWZ, int EPI>
 inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
-  using Cfg = GemmCfg<BLOCK_N, SWZ>;
+  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI>;
   static bool attr_set = false;
   auto kern = conv_gemm_kernel<BLOCK_N, SWZ, EPI>;
   if (!attr_set) {
@@ -243,7 +275,7 @@ inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<L.grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(L.tmap_a, L.tmap_b, L.p);
+  kern<<<L.grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(L.tmap_a, L.tmap_b, L.tmap_out, L.tmap_res, L.p);
   return cudaGetLastError();
 }
 
@@ -253,6 +285,17 @@ inline cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
     if (L.block_n == 64) return launch_one<64, 128, EPI_NHWC_F16>(L, st);
     if (L.block_n == 128) return launch_one<128, 128, EPI_NHWC_F16>(L, st);
     if (L.block_n == 256) return launch_one<256, 128, EPI_NHWC_F16>(L, st);
+  }
+  if (L.swz == 64 && L.block_n == 64 && L.epi == EPI_TMA) return launch_one<64, 64, EPI_TMA>(L, st);
+  if (L.swz == 128 && L.epi == EPI_TMA) {
+    if (L.block_n == 64) return launch_one<64, 128, EPI_TMA>(L, st);
+    if (L.block_n == 128) return launch_one<128, 128, EPI_TMA>(L, st);
+    if (L.block_n == 256) return launch_one<256, 128, EPI_TMA>(L, st);
+  }
+  if (L.swz == 128 && L.epi == EPI_TMA_RES) {
+    if (L.block_n == 64) return launch_one<64, 128, EPI_TMA_RES>(L, st);
+    if (L.block_n == 128) return launch_one<128, 128, EPI_TMA_RES>(L, st);
+    if (L.block_n == 256) return launch_one<256, 128, EPI_TMA_RES>(L, st);
   }
   if (L.swz == 128 && L.epi == EPI_PLANAR_F32 && L.block_n == 96) return launch_one<96, 128, EPI_PLANAR_F32>(L, st);
   if (L.swz == 128 && L.epi == EPI_DECONV_HEAD && L.block_n == 192)

@@ -255,6 +255,15 @@ int main(int argc, char** argv) {
       {"3x3 64->64 relu 92x92", CONV_3x3, 2, 92, 92, 64, 64, 64, 64, EPI_NHWC_F16, true, false, 64, 0},
       {"3x3 256->256 relu 23x23", CONV_3x3, 3, 23, 23, 256, 256, 256, 128, EPI_NHWC_F16, true, false, 256, 0},
       {"3x3 128->128 relu 46x46", CONV_3x3, 1, 46, 46, 128, 128, 128, 128, EPI_NHWC_F16, true, false, 128, 0},
+      {"TMA 1x1 64->64 relu 92x92", CONV_1x1, 2, 92, 92, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0},
+      {"TMA 1x1 64->256 lin 92x92", CONV_1x1, 2, 92, 92, 64, 256, 256, 256, EPI_TMA, true, false, 0, 0},
+      {"TMARES 1x1 64->256 +res relu 92x92", CONV_1x1, 2, 92, 92, 64, 256, 256, 256, EPI_TMA_RES, true, true, 256, 0},
+      {"TMARES 1x1 256->1024 +res relu 23x23", CONV_1x1, 7, 23, 23, 256, 1024, 1024, 256, EPI_TMA_RES, true, true, 1024, 0},
+      {"TMARES 1x1 128->512 +res relu 46x46 bn128", CONV_1x1, 3, 46, 46, 128, 512, 512, 128, EPI_TMA_RES, true, true, 512, 0},
+      {"TMA 3x3 64->64 relu 92x92", CONV_3x3, 2, 92, 92, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0},
+      {"TMA 3x3 256->256 relu 23x23", CONV_3x3, 3, 23, 23, 256, 256, 256, 128, EPI_TMA, true, false, 256, 0},
+      {"TMA 3x3 128->128 relu 46x46", CONV_3x3, 1, 46, 46, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0},
+      {"TMA stem 7x7s2 3->64 relu 184x184", CONV_STEM7, 2, 184, 184, 0, 64, 64, 64, EPI_TMA, true, false, 64, 0},
       {"deconv4x4s2 256->192 head 23x23", CONV_DECONV4, 2, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false,
        128, 0},
       {"1x1 128->84 planar f32 46x46", CONV_1x1, 2, 46, 46, 128, 96, 84, 96, EPI_PLANAR_F32, false, false, 0, 0},
@@ -269,6 +278,11 @@ int main(int argc, char** argv) {
         {"BIG 3x3 512->512 23x23 nb64", CONV_3x3, 64, 23, 23, 512, 512, 512, 256, EPI_NHWC_F16, true, false, 512, 0},
         {"BIG 3x3 64->64 92x92 nb32", CONV_3x3, 32, 92, 92, 64, 64, 64, 64, EPI_NHWC_F16, true, false, 64, 0},
         {"BIG 1x1 256->64 92x92 nb32", CONV_1x1, 32, 92, 92, 256, 64, 64, 64, EPI_NHWC_F16, true, false, 64, 0},
+        {"BIG TMARES 1x1 64->256 +res 92x92 nb32", CONV_1x1, 32, 92, 92, 64, 256, 256, 256, EPI_TMA_RES, true, true, 256, 0},
+        {"BIG TMA 1x1 64->256 92x92 nb32", CONV_1x1, 32, 92, 92, 64, 256, 256, 256, EPI_TMA, true, false, 0, 0},
+        {"BIG TMA 3x3 64->64 92x92 nb32", CONV_3x3, 32, 92, 92, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0},
+        {"BIG TMA stem nb32", CONV_STEM7, 32, 184, 184, 0, 64, 64, 64, EPI_TMA, true, false, 64, 0},
+        {"BIG TMARES 1x1 256->1024 +res 23x23 nb128", CONV_1x1, 128, 23, 23, 256, 1024, 1024, 256, EPI_TMA_RES, true, true, 1024, 0},
     };
     for (const auto& c : bigc) fails += run_case(c, sms, true);
   }

@@ -280,7 +280,10 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
     if (r.H != ai.H || r.W != ai.W || r.C != cout) return fail(h, VNECT_E_INVALID, "residual shape mismatch at %s", scope.c_str());
     s.residual = r.p; s.ldr = r.C;
   }
-  s.out = h->acts.at(out).p; s.ldc = cout; s.epi = EPI_NHWC_F16; s.decimate = o.decimate ? 1 : 0;
+  s.out = h->acts.at(out).p; s.ldc = cout; s.decimate = o.decimate ? 1 : 0;
+  // plain NHWC outputs leave through swizzled smem + TMA store (residual prefetched by TMA); the two decimated
+  // block outputs keep the direct register -> global path
+  s.epi = o.decimate ? EPI_NHWC_F16 : (s.residual ? EPI_TMA_RES : EPI_TMA);
   Step st;
   st.kind = 0; st.name = scope;
   std::string err;
@@ -501,7 +504,7 @@ int vnect_finalize(vnect_t* h) {
     s.NB = nb; s.H = S / 2; s.W = S / 2;
     s.in = h->x1; s.stem_rows_per_parity = h->stem_rpp; s.stem_row_pitch = h->stem_pitch;
     s.w = dw; s.n_pad = 64; s.n_valid = 64; s.block_n = 64; s.bias = db; s.relu_cols = 64;
-    s.out = h->acts.at("conv1").p; s.ldc = 64; s.epi = EPI_NHWC_F16;
+    s.out = h->acts.at("conv1").p; s.ldc = 64; s.epi = EPI_TMA;
     Step st;
     st.kind = 0; st.name = "conv1";
     std::string err;
