@@ -49,6 +49,8 @@ struct ConvGemmParams {
   signed char tap_dx[16], tap_dy[16], tap_dp[16];  // [phase * taps + tap]
   uint32_t stage_tx_bytes;
   uint32_t res_tx_bytes;  // bytes of one residual chunk box (EPI_TMA_RES)
+  int in_stride;          // 1, or 2: the conv samples its input at every second pixel (TMA element strides)
+  int res_stride;         // 1, or 2: residual read at every second pixel of a 2H x 2W tensor
   // ---- epilogue
   int n_valid;    // valid output columns
   int relu_cols;  // ReLU on columns < relu_cols (multiple of 32)
@@ -170,7 +172,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int b_row = ph * p.b_rows_per_phase + n_tile * BLOCK_N;
         for (int t = 0; t < p.taps; ++t) {
           const int ti = ph * p.taps + t;
-          const int ax = cx + p.tap_dx[ti], ay = cy + p.tap_dy[ti], ap = p.tap_dp[ti];
+          const int ax = cx * p.in_stride + p.tap_dx[ti], ay = cy * p.in_stride + p.tap_dy[ti], ap = p.tap_dp[ti];
           for (int cb = 0; cb < p.cblocks; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
@@ -239,7 +241,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int rb = ctr % kResStages;
             mbar_wait(&res_empty[rb], ((ctr / kResStages) & 1) ^ 1);
             mbar_arrive_expect_tx(&res_full[rb], p.res_tx_bytes);
-            tma_load_5d(res_stage + rb * kEpiChunkBytes, &tmap_res, &res_full[rb], n_tile * BLOCK_N + c0, cx, cy, 0, cn);
+            tma_load_5d(res_stage + rb * kEpiChunkBytes, &tmap_res, &res_full[rb], n_tile * BLOCK_N + c0,
+                        cx * p.res_stride, cy * p.res_stride, 0, cn);
           }
         }
       }

@@ -31,13 +31,15 @@ inline PFN_encodeTiled get_encode_tiled() {
 }
 
 inline bool encode_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                        const uint32_t* box, int swz_bytes, std::string* err) {
+                        const uint32_t* box, int swz_bytes, std::string* err, const uint32_t* elem_strides = nullptr) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     if (err) *err = "cuTensorMapEncodeTiled entry point unavailable";
     return false;
   }
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides)
+    for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUtensorMapSwizzle sw = swz_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swz_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                             : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -82,6 +84,13 @@ struct ConvSpec {
   int ldc = 0;
   int epi = EPI_NHWC_F16;
   int decimate = 0;
+  // stride-2 sampling (the stride-2 1x1 convs of res3a/res4a only read even pixels of res2c/res3d, so those two
+  // blocks are computed at even pixels only): the conv reads `in` [NB, in_stride*H, in_stride*W, cin_pad] at every
+  // in_stride-th pixel; the residual is [NB, res_stride*H, res_stride*W, ldr] read likewise. 1x1 convs with a
+  // strided operand use spatial tiles.
+  int in_stride = 1;
+  int res_stride = 1;
+  int spatial_1x1 = 0;
 };
 
 struct ConvLaunch {
@@ -139,11 +148,15 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
   p.OH = s.decimate ? s.H / 2 : s.H;
   p.OW = s.decimate ? s.W / 2 : s.W;
   p.oys = p.oxs = 1;
+  p.in_stride = s.in_stride;
+  p.res_stride = s.res_stride;
+  const bool spatial1 = s.kind == CONV_1x1 && (s.spatial_1x1 || s.in_stride != 1 || s.res_stride != 1);
+  uint32_t estr[5] = {1, (uint32_t)s.in_stride, (uint32_t)s.in_stride, 1, 1};
 
   uint64_t dims[5], strides[4];
   uint32_t box[5];
   int k_total;
-  if (s.kind == CONV_1x1) {
+  if (s.kind == CONV_1x1 && !spatial1) {
     p.mode = 0;
     p.taps = 1;
     p.cblocks = s.cin_pad / block_k;
@@ -156,14 +169,17 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     strides[1] = strides[2] = strides[3] = (uint64_t)s.cin_pad * 2 * p.M;
     box[0] = block_k; box[1] = kBlockM; box[2] = 1; box[3] = 1; box[4] = 1;
     k_total = s.cin_pad;
-  } else if (s.kind == CONV_3x3 || s.kind == CONV_DECONV4) {
+  } else if (s.kind == CONV_3x3 || s.kind == CONV_DECONV4 || spatial1) {
     p.mode = 1;
     choose_tile(s.H, s.W, &p.tw, &p.th);
     p.tiles_x = (s.W + p.tw - 1) / p.tw;
     p.tiles_y = (s.H + p.th - 1) / p.th;
     p.num_m_tiles = s.NB * p.tiles_x * p.tiles_y;
     p.cblocks = s.cin_pad / block_k;
-    if (s.kind == CONV_3x3) {
+    if (spatial1) {
+      p.taps = 1;
+      p.tap_dx[0] = p.tap_dy[0] = p.tap_dp[0] = 0;
+    } else if (s.kind == CONV_3x3) {
       p.taps = 9;
       for (int ky = 0; ky < 3; ++ky)
         for (int kx = 0; kx < 3; ++kx) {
@@ -192,12 +208,12 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
           }
       }
     }
-    dims[0] = s.cin_pad; dims[1] = s.W; dims[2] = s.H; dims[3] = 1; dims[4] = s.NB;
+    dims[0] = s.cin_pad; dims[1] = (uint64_t)s.W * s.in_stride; dims[2] = (uint64_t)s.H * s.in_stride; dims[3] = 1; dims[4] = s.NB;
     strides[0] = (uint64_t)s.cin_pad * 2;
-    strides[1] = strides[0] * s.W;
-    strides[2] = strides[1] * s.H;
+    strides[1] = strides[0] * dims[1];
+    strides[2] = strides[1] * dims[2];
     strides[3] = strides[2];
-    box[0] = block_k; box[1] = p.tw; box[2] = p.th; box[3] = 1; box[4] = 1;
+    box[0] = block_k; box[1] = p.tw * s.in_stride; box[2] = p.th * s.in_stride; box[3] = 1; box[4] = 1;
     k_total = p.taps * s.cin_pad;
   } else {  // CONV_STEM7
     p.mode = 1;
@@ -221,8 +237,9 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     box[0] = 32; box[1] = p.tw; box[2] = p.th; box[3] = 1; box[4] = 1;
     k_total = 7 * 32;
   }
-  p.stage_tx_bytes = (uint32_t)(box[0] * box[1] * box[2] * 2 + (uint32_t)s.block_n * block_k * 2);
-  if (!encode_tmap(&L->tmap_a, s.in, 5, dims, strides, box, swz, err)) return false;
+  const int a_stride = (s.kind == CONV_STEM7) ? 1 : s.in_stride;
+  p.stage_tx_bytes = (uint32_t)(box[0] * (box[1] / a_stride) * (box[2] / a_stride) * 2 + (uint32_t)s.block_n * block_k * 2);
+  if (!encode_tmap(&L->tmap_a, s.in, 5, dims, strides, box, swz, err, a_stride != 1 ? estr : nullptr)) return false;
   uint64_t bd[2] = {(uint64_t)k_total, (uint64_t)p.phases * s.n_pad};
   uint64_t bs[1] = {(uint64_t)k_total * 2};
   uint32_t bb[2] = {(uint32_t)block_k, (uint32_t)s.block_n};
@@ -237,26 +254,27 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     }
     uint64_t od[5], os[4];
     uint32_t ob[5];
-    auto act_map = [&](const void* ptr, int ld, CUtensorMap* m) {
+    auto act_map = [&](const void* ptr, int ld, CUtensorMap* m, int stride) {
+      uint32_t es[5] = {1, (uint32_t)stride, (uint32_t)stride, 1, 1};
       if (p.mode == 0) {
         od[0] = ld; od[1] = p.M; od[2] = 1; od[3] = 1; od[4] = 1;
         os[0] = (uint64_t)ld * 2; os[1] = os[2] = os[3] = (uint64_t)ld * 2 * p.M;
         ob[0] = 64; ob[1] = kBlockM; ob[2] = 1; ob[3] = 1; ob[4] = 1;
       } else {
-        od[0] = ld; od[1] = s.W; od[2] = s.H; od[3] = 1; od[4] = s.NB;
-        os[0] = (uint64_t)ld * 2; os[1] = os[0] * s.W; os[2] = os[1] * s.H; os[3] = os[2];
-        ob[0] = 64; ob[1] = p.tw; ob[2] = p.th; ob[3] = 1; ob[4] = 1;
+        od[0] = ld; od[1] = (uint64_t)s.W * stride; od[2] = (uint64_t)s.H * stride; od[3] = 1; od[4] = s.NB;
+        os[0] = (uint64_t)ld * 2; os[1] = os[0] * od[1]; os[2] = os[1] * od[2]; os[3] = os[2];
+        ob[0] = 64; ob[1] = p.tw * stride; ob[2] = p.th * stride; ob[3] = 1; ob[4] = 1;
       }
-      return encode_tmap(m, ptr, 5, od, os, ob, 128, err);
+      return encode_tmap(m, ptr, 5, od, os, ob, 128, err, stride != 1 ? es : nullptr);
     };
-    if (!act_map(s.out, s.ldc, &L->tmap_out)) return false;
+    if (!act_map(s.out, s.ldc, &L->tmap_out, 1)) return false;
     if (s.epi == EPI_TMA_RES) {
       if (!s.residual) {
         if (err) *err = "EPI_TMA_RES without a residual";
         return false;
       }
-      if (!act_map(s.residual, s.ldr, &L->tmap_res)) return false;
-      p.res_tx_bytes = ob[1] * ob[2] * 128;
+      if (!act_map(s.residual, s.ldr, &L->tmap_res, s.res_stride)) return false;
+      p.res_tx_bytes = (ob[1] / s.res_stride) * (ob[2] / s.res_stride) * 128;
     }
   }
   const int total = p.phases * p.num_m_tiles * p.num_n_tiles;

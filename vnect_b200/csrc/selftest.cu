@@ -21,6 +21,7 @@ using namespace vnect;
 struct NaiveGeom {
   int kind, NB, H, W, cin_pad, n_pad, taps, phases, k_total;
   int stem_rpp, stem_pitch;
+  int in_stride;
   signed char dx[16], dy[16], dp[16];
 };
 
@@ -48,9 +49,10 @@ __global__ void naive_acc_kernel(const __half* __restrict__ in, const __half* __
         const __half* a = in + (((size_t)n * 2 + g.dp[ti]) * g.stem_rpp + row) * g.stem_pitch + (size_t)x * 8;
         for (int c = 0; c < 32; ++c) s += __half2float(a[c]) * __half2float(wrow[t * 32 + c]);
       } else {
-        const int yy = y + g.dy[ti], xx = x + g.dx[ti];
-        if (yy < 0 || yy >= g.H || xx < 0 || xx >= g.W) continue;
-        const __half* a = in + (((size_t)n * g.H + yy) * g.W + xx) * g.cin_pad;
+        const int IH = g.H * g.in_stride, IW = g.W * g.in_stride;
+        const int yy = y * g.in_stride + g.dy[ti], xx = x * g.in_stride + g.dx[ti];
+        if (yy < 0 || yy >= IH || xx < 0 || xx >= IW) continue;
+        const __half* a = in + (((size_t)n * IH + yy) * IW + xx) * g.cin_pad;
         for (int c = 0; c < g.cin_pad; ++c) s += __half2float(a[c]) * __half2float(wrow[(size_t)t * g.cin_pad + c]);
       }
     }
@@ -69,6 +71,7 @@ struct Case {
   int kind, NB, H, W, cin_pad, n_pad, n_valid, block_n, epi;
   bool bias, residual;
   int relu_cols, decimate;
+  int in_stride = 1, res_stride = 1;
 };
 
 static int run_case(const Case& c, int num_sms, bool timing) {
@@ -84,6 +87,8 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   s.epi = c.epi;
   s.relu_cols = c.relu_cols;
   s.decimate = c.decimate;
+  s.in_stride = c.in_stride;
+  s.res_stride = c.res_stride;
   const int phases = c.kind == CONV_DECONV4 ? 4 : 1;
   const int taps = c.kind == CONV_1x1 ? 1 : c.kind == CONV_3x3 ? 9 : c.kind == CONV_DECONV4 ? 4 : 7;
   const int k_total = c.kind == CONV_STEM7 ? 7 * 32 : taps * c.cin_pad;
@@ -96,7 +101,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
     s.stem_rows_per_parity = rpp;
     s.stem_row_pitch = pitch;
   } else {
-    in_elems = (size_t)c.NB * c.H * c.W * c.cin_pad;
+    in_elems = (size_t)c.NB * c.H * c.W * c.cin_pad * c.in_stride * c.in_stride;
   }
   std::vector<__half> h_in(in_elems), h_w((size_t)phases * c.n_pad * k_total);
   for (auto& v : h_in) v = __float2half(frand());
@@ -114,7 +119,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   const int ldr = c.n_pad;
   std::vector<__half> h_res;
   if (c.residual) {
-    h_res.resize((size_t)c.NB * c.H * c.W * ldr);
+    h_res.resize((size_t)c.NB * c.H * c.W * ldr * c.res_stride * c.res_stride);
     for (auto& v : h_res) v = __float2half(frand());
   }
 
@@ -158,6 +163,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
 
   NaiveGeom g;
   g.kind = c.kind; g.NB = c.NB; g.H = c.H; g.W = c.W; g.cin_pad = c.cin_pad; g.n_pad = c.n_pad;
+  g.in_stride = c.in_stride;
   g.taps = taps; g.phases = phases; g.k_total = k_total; g.stem_rpp = rpp; g.stem_pitch = pitch;
   memcpy(g.dx, L.p.tap_dx, 16); memcpy(g.dy, L.p.tap_dy, 16); memcpy(g.dp, L.p.tap_dp, 16);
   naive_acc_kernel<<<1184, 256>>>(d_in, d_w, d_acc, g);
@@ -200,7 +206,10 @@ static int run_case(const Case& c, int num_sms, bool timing) {
           float bone[21] = {0};
           for (int col = 0; col < c.n_pad; ++col) {
             float v = a[col] + (c.bias ? h_bias[col] : 0.f);
-            if (c.residual) v += __half2float(h_res[m * ldr + col]);
+            if (c.residual) {
+              const size_t rm = ((size_t)n * c.H * c.res_stride + (size_t)y * c.res_stride) * c.W * c.res_stride + (size_t)x * c.res_stride;
+              v += __half2float(h_res[rm * ldr + col]);
+            }
             if (col < c.relu_cols) v = fmaxf(v, 0.f);
             if (c.epi == EPI_PLANAR_F32) {
               if (col < c.n_valid) check(o32[((size_t)n * c.n_valid + col) * OH * OW + (size_t)oy * OW + ox], v);
@@ -264,6 +273,10 @@ int main(int argc, char** argv) {
       {"TMA 3x3 256->256 relu 23x23", CONV_3x3, 3, 23, 23, 256, 256, 256, 128, EPI_TMA, true, false, 256, 0},
       {"TMA 3x3 128->128 relu 46x46", CONV_3x3, 1, 46, 46, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0},
       {"TMA stem 7x7s2 3->64 relu 184x184", CONV_STEM7, 2, 184, 184, 0, 64, 64, 64, EPI_TMA, true, false, 64, 0},
+      {"S2 3x3 64->64 relu 92->46", CONV_3x3, 2, 46, 46, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0, 2, 1},
+      {"S2 3x3 128->128 relu 46->23", CONV_3x3, 3, 23, 23, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0, 2, 1},
+      {"S2RES 1x1 64->256 +res(92) relu 46x46", CONV_1x1, 2, 46, 46, 64, 256, 256, 256, EPI_TMA_RES, true, true, 256, 0, 1, 2},
+      {"S2RES 1x1 128->512 +res(46) relu 23x23", CONV_1x1, 3, 23, 23, 128, 512, 512, 256, EPI_TMA_RES, true, true, 512, 0, 1, 2},
       {"deconv4x4s2 256->192 head 23x23", CONV_DECONV4, 2, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false,
        128, 0},
       {"1x1 128->84 planar f32 46x46", CONV_1x1, 2, 46, 46, 128, 96, 84, 96, EPI_PLANAR_F32, false, false, 0, 0},

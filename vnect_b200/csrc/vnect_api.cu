@@ -249,7 +249,8 @@ static int new_act(vnect_t* h, const std::string& name, int H, int W, int C) {
 struct ConvOpts {
   bool relu = true;
   std::string residual;  // act name or empty
-  bool decimate = false;
+  int in_stride = 1;     // 2: compute the conv at even input pixels only (output grid is half-size)
+  int res_stride = 1;    // 2: the residual is a full-size tensor read at even pixels
 };
 
 static int pick_block_n(int n) { return n >= 256 ? 256 : n >= 128 ? 128 : 64; }
@@ -266,24 +267,24 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
   if (rc) return rc;
   rc = upload(h, b.data, &db);
   if (rc) return rc;
-  const int OH = o.decimate ? ai.H / 2 : ai.H, OW = o.decimate ? ai.W / 2 : ai.W;
+  const int OH = ai.H / o.in_stride, OW = ai.W / o.in_stride;
   rc = new_act(h, out, OH, OW, cout);
   if (rc) return rc;
   ConvSpec s;
   s.kind = k == 1 ? CONV_1x1 : CONV_3x3;
-  s.NB = h->cap_fw; s.H = ai.H; s.W = ai.W;
-  s.in = ai.p; s.cin_pad = cin_pad;
+  s.NB = h->cap_fw; s.H = OH; s.W = OW;
+  s.in = ai.p; s.cin_pad = cin_pad; s.in_stride = o.in_stride;
   s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout);
   s.bias = db; s.relu_cols = o.relu ? cout : 0;
   if (!o.residual.empty()) {
     const Act& r = h->acts.at(o.residual);
-    if (r.H != ai.H || r.W != ai.W || r.C != cout) return fail(h, VNECT_E_INVALID, "residual shape mismatch at %s", scope.c_str());
-    s.residual = r.p; s.ldr = r.C;
+    if (r.H != OH * o.res_stride || r.W != OW * o.res_stride || r.C != cout)
+      return fail(h, VNECT_E_INVALID, "residual shape mismatch at %s", scope.c_str());
+    s.residual = r.p; s.ldr = r.C; s.res_stride = o.res_stride;
   }
-  s.out = h->acts.at(out).p; s.ldc = cout; s.decimate = o.decimate ? 1 : 0;
-  // plain NHWC outputs leave through swizzled smem + TMA store (residual prefetched by TMA); the two decimated
-  // block outputs keep the direct register -> global path
-  s.epi = o.decimate ? EPI_NHWC_F16 : (s.residual ? EPI_TMA_RES : EPI_TMA);
+  // outputs leave through swizzled smem + TMA tensor stores; residual tiles are prefetched by TMA
+  s.out = h->acts.at(out).p; s.ldc = cout;
+  s.epi = s.residual ? EPI_TMA_RES : EPI_TMA;
   Step st;
   st.kind = 0; st.name = scope;
   std::string err;
@@ -292,9 +293,11 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
   return VNECT_OK;
 }
 
-// bottleneck block (reference: src/vnect_model.py:31-177); `a_in` overrides the 3x3's input (the res2c wiring, :56)
+// bottleneck block (reference: src/vnect_model.py:31-177); `a_override` replaces the 3x3's input (the res2c wiring,
+// :56).  even_only: the block's output feeds nothing but stride-2 1x1 convs (res2c -> res3a, res3d -> res4a), so
+// the 3x3, the last 1x1 and the residual add are evaluated at even pixels only -- same values, a quarter of the work.
 static int add_block(vnect_t* h, const std::string& pre, const std::string& in, int cin, int mid, int cout, bool proj,
-                     const std::string& suf, bool decimate_out, const std::string& a_override = "") {
+                     const std::string& suf, bool even_only, const std::string& a_override = "") {
   int rc;
   ConvOpts lin; lin.relu = false;
   ConvOpts relu;
@@ -310,9 +313,10 @@ static int add_block(vnect_t* h, const std::string& pre, const std::string& in, 
     rc = add_conv(h, a, 1, in, a, cin, mid, relu);
     if (rc) return rc;
   }
-  rc = add_conv(h, pre + "_branch2b" + suf, 3, a, pre + "_branch2b" + suf, mid, mid, relu);
+  ConvOpts mid3; mid3.in_stride = even_only ? 2 : 1;
+  rc = add_conv(h, pre + "_branch2b" + suf, 3, a, pre + "_branch2b" + suf, mid, mid, mid3);
   if (rc) return rc;
-  ConvOpts last; last.relu = true; last.residual = shortcut; last.decimate = decimate_out;
+  ConvOpts last; last.relu = true; last.residual = shortcut; last.res_stride = even_only ? 2 : 1;
   return add_conv(h, pre + "_branch2c" + suf, 1, pre + "_branch2b" + suf, pre, mid, cout, last);
 }
 
@@ -522,7 +526,7 @@ int vnect_finalize(vnect_t* h) {
   }
   if ((rc = add_block(h, "res2a", "pool1", 64, 64, 256, true, "", false))) return rc;
   if ((rc = add_block(h, "res2b", "res2a", 256, 64, 256, false, "", false))) return rc;
-  // res2c: the 3x3 reads res2b_branch2a (vnect_model.py:56); its output only feeds stride-2 1x1 convs -> decimated
+  // res2c: the 3x3 reads res2b_branch2a (vnect_model.py:56); its output only feeds stride-2 1x1 convs -> even pixels only
   if ((rc = add_block(h, "res2c", "res2b", 256, 64, 256, false, "", true, "res2b_branch2a"))) return rc;
   if ((rc = add_block(h, "res3a", "res2c", 256, 128, 512, true, "", false))) return rc;
   if ((rc = add_block(h, "res3b", "res3a", 512, 128, 512, false, "", false))) return rc;
