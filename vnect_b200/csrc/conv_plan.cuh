@@ -8,6 +8,7 @@
 #include <string>
 
 #include "conv_gemm.cuh"
+#include "stem_gemm.cuh"
 
 namespace vnect {
 
@@ -319,6 +320,64 @@ inline cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
   if (L.swz == 128 && L.epi == EPI_DECONV_HEAD && L.block_n == 192)
     return launch_one<192, 128, EPI_DECONV_HEAD>(L, st);
   return cudaErrorInvalidConfiguration;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv1 through stem_gemm_kernel (raw-strip A operand).  Output buffer: [NB][tiles_per_image*128 virtual px][64].
+struct StemLaunch {
+  CUtensorMap tmap_out;
+  StemParams p;
+  int grid = 0;
+  int out_h = 0, out_w = 0;   // S/2
+  int vw = 0;                 // virtual row pitch in pixels (S/2 + 3)
+  int64_t img_px = 0;         // virtual pixels per image (tiles_per_image * 128)
+};
+
+// [64][224] K-major (k = ky*32 + kx*4 + c) -> canonical no-swizzle layout [k/8][n][k%8]
+inline void pack_stem_canonical(const __half* kmajor, __half* out) {
+  for (int n = 0; n < 64; ++n)
+    for (int k = 0; k < 224; ++k) out[((k / 8) * 64 + n) * 8 + (k % 8)] = kmajor[n * 224 + k];
+}
+
+inline bool build_stem(const __half* x1, int S, int rows_per_parity, int row_pitch, const __half* w_canonical,
+                       const float* bias, __half* out, int nb_capacity, int num_sms, StemLaunch* L, std::string* err) {
+  memset(L, 0, sizeof(*L));
+  L->out_h = L->out_w = S / 2;
+  L->vw = S / 2 + 3;
+  if (row_pitch * 2 != L->vw * 16) {
+    if (err) *err = "stem row pitch must be (S/2+3)*16 bytes";
+    return false;
+  }
+  const int tpi = (L->out_h * L->vw + kBlockM - 1) / kBlockM;
+  L->img_px = (int64_t)tpi * kBlockM;
+  L->p.x1 = reinterpret_cast<const uint8_t*>(x1);
+  L->p.plane_bytes = (int64_t)rows_per_parity * row_pitch * 2;
+  L->p.w = reinterpret_cast<const uint8_t*>(w_canonical);
+  L->p.bias = bias;
+  L->p.vw = L->vw;
+  L->p.tiles_per_image = tpi;
+  L->p.num_tiles = nb_capacity * tpi;
+  L->grid = L->p.num_tiles < num_sms ? L->p.num_tiles : num_sms;
+  uint64_t od[5] = {64, (uint64_t)nb_capacity * tpi * kBlockM, 1, 1, 1};
+  uint64_t os[4] = {128, 128ull * od[1], 128ull * od[1], 128ull * od[1]};
+  uint32_t ob[5] = {64, kBlockM, 1, 1, 1};
+  return encode_tmap(&L->tmap_out, out, 5, od, os, ob, 128, err);
+}
+
+inline void stem_set_batch(StemLaunch& L, int nb, int num_sms) {
+  L.p.num_tiles = nb * L.p.tiles_per_image;
+  L.grid = L.p.num_tiles < num_sms ? L.p.num_tiles : num_sms;
+}
+
+inline cudaError_t launch_stem(const StemLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stem_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  stem_gemm_kernel<<<L.grid, kGemmThreads, StemSmem::BYTES, st>>>(L.tmap_out, L.p);
+  return cudaGetLastError();
 }
 
 }  // namespace vnect

@@ -174,8 +174,9 @@ __global__ void stem_to_f32_kernel(const __half* __restrict__ x1, float* __restr
 // ---------------------------------------------------------------------------------------------------------------
 // tc.layers.max_pool2d(kernel 3, stride 2, 'same') on NHWC fp16 (vnect_model.py:29): TF SAME pads (0,1) here and
 // ignores padded cells.  One thread = 8 channels (16 B) of one output pixel.
+// The input may have a virtual row pitch / image stride (in pixels) larger than W / H*W (conv1's output does).
 __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int NB, int H, int W,
-                                    int C, int OH, int OW) {
+                                    int C, int OH, int OW, int in_row_px, int64_t in_img_px) {
   const int cv = C / 8;
   const int64_t total = (int64_t)NB * OH * OW * cv;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -195,7 +196,7 @@ __global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __res
       for (int kx = 0; kx < 3; ++kx) {
         const int x = 2 * ox + kx;
         if (x >= W) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((int64_t)n * H + y) * W + x) * C) + c8);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((int64_t)n * in_img_px + (int64_t)y * in_row_px + x) * C) + c8);
         const __half2* h = reinterpret_cast<const __half2*>(&v);
         if (first) {
           m[0] = h[0]; m[1] = h[1]; m[2] = h[2]; m[3] = h[3];

@@ -249,6 +249,90 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   return bad == 0 ? 0 : 1;
 }
 
+// conv1 through stem_gemm_kernel (strip loads, resident weights) against the same naive reference
+static int run_stem2(int NB, int S, int num_sms) {
+  const int OH = S / 2, vw = OH + 3, rpp = OH + 3, pitch = vw * 8;
+  const size_t in_elems = (size_t)NB * 2 * rpp * pitch + 4096;
+  std::vector<__half> h_in(in_elems), h_w((size_t)64 * 224), h_wc((size_t)64 * 224);
+  for (auto& v : h_in) v = __float2half(frand());
+  for (auto& v : h_w) v = __float2half(frand() * 0.15f);
+  pack_stem_canonical(h_w.data(), h_wc.data());
+  std::vector<float> h_bias(64);
+  for (auto& v : h_bias) v = frand() * 0.5f;
+  __half *d_in, *d_w, *d_wc, *d_out;
+  float *d_bias, *d_acc;
+  CK(cudaMalloc(&d_in, in_elems * 2));
+  CK(cudaMalloc(&d_w, h_w.size() * 2));
+  CK(cudaMalloc(&d_wc, h_wc.size() * 2));
+  CK(cudaMalloc(&d_bias, 64 * 4));
+  CK(cudaMemcpy(d_in, h_in.data(), in_elems * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_w, h_w.data(), h_w.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_wc, h_wc.data(), h_wc.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_bias, h_bias.data(), 64 * 4, cudaMemcpyHostToDevice));
+  StemLaunch L;
+  std::string err;
+  const int tpi = (OH * vw + 127) / 128;
+  const size_t out_elems = (size_t)NB * tpi * 128 * 64;
+  CK(cudaMalloc(&d_out, out_elems * 2));
+  CK(cudaMemset(d_out, 0, out_elems * 2));
+  if (!build_stem(d_in, S, rpp, pitch, d_wc, d_bias, d_out, NB, num_sms, &L, &err)) {
+    printf("[stem2] build FAILED: %s\n", err.c_str());
+    return 1;
+  }
+  CK(launch_stem(L, 0));
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) {
+    printf("[stem2] kernel FAILED: %s\n", cudaGetErrorString(se));
+    exit(3);
+  }
+  NaiveGeom g;
+  memset(&g, 0, sizeof g);
+  g.kind = CONV_STEM7; g.NB = NB; g.H = OH; g.W = OH; g.cin_pad = 0; g.n_pad = 64; g.taps = 7; g.phases = 1;
+  g.k_total = 224; g.stem_rpp = rpp; g.stem_pitch = pitch; g.in_stride = 1;
+  for (int ky = 0; ky < 7; ++ky) { g.dy[ky] = (signed char)(ky >> 1); g.dx[ky] = 0; g.dp[ky] = (signed char)(ky & 1); }
+  const size_t acc_elems = (size_t)NB * OH * OH * 64;
+  CK(cudaMalloc(&d_acc, acc_elems * 4));
+  naive_acc_kernel<<<1184, 256>>>(d_in, d_w, d_acc, g);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> h_acc(acc_elems);
+  std::vector<__half> h_out(out_elems);
+  CK(cudaMemcpy(h_acc.data(), d_acc, acc_elems * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h_out.data(), d_out, out_elems * 2, cudaMemcpyDeviceToHost));
+  long long bad = 0, checked = 0;
+  double max_err = 0;
+  for (int n = 0; n < NB; ++n)
+    for (int y = 0; y < OH; ++y)
+      for (int x = 0; x < OH; ++x)
+        for (int c = 0; c < 64; ++c) {
+          const float exp = fmaxf(h_acc[(((size_t)n * OH + y) * OH + x) * 64 + c] + h_bias[c], 0.f);
+          const float got = __half2float(h_out[((size_t)n * L.img_px + (size_t)y * vw + x) * 64 + c]);
+          const float e = fabsf(got - exp);
+          if (!(e <= 3e-3f * fabsf(exp) + 3e-3f)) {
+            if (bad < 5) printf("   mismatch n%d y%d x%d c%d got %f exp %f\n", n, y, x, c, got, exp);
+            ++bad;
+          }
+          if (e > max_err) max_err = e;
+          ++checked;
+        }
+  printf("[stem2 strip-load conv1 S=%d nb=%d] tiles=%d grid=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n", S, NB,
+         L.p.num_tiles, L.grid, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
+  if (bad == 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CK(launch_stem(L, 0));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 20; ++i) CK(launch_stem(L, 0));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("   timing: %.2f us/launch\n", ms * 1000.0 / 20);
+  }
+  cudaFree(d_in); cudaFree(d_w); cudaFree(d_wc); cudaFree(d_bias); cudaFree(d_out); cudaFree(d_acc);
+  return bad == 0 ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   int dev = 0;
   cudaDeviceProp prop;
@@ -284,7 +368,10 @@ int main(int argc, char** argv) {
   };
   int fails = 0;
   for (const auto& c : cases) fails += run_case(c, sms, true);
+  fails += run_stem2(2, 368, sms);
+  fails += run_stem2(1, 448, sms);
   if (big) {
+    fails += run_stem2(32, 368, sms);
     std::vector<Case> bigc = {
         {"BIG 1x1 1024->1024 23x23 nb128", CONV_1x1, 128, 23, 23, 1024, 1024, 1024, 256, EPI_NHWC_F16, true, false,
          1024, 0},

@@ -18,17 +18,21 @@ namespace {
 struct Act {
   __half* p = nullptr;
   int H = 0, W = 0, C = 0;
+  int row_px = 0;       // row pitch in pixels (== W except for conv1's virtual layout)
+  int64_t img_px = 0;   // image stride in pixels (== H*W except for conv1)
 };
 
 struct Step {
-  int kind = 0;  // 0 = conv, 1 = maxpool
+  int kind = 0;  // 0 = conv GEMM, 1 = maxpool, 2 = stem (conv1)
   std::string name;
   ConvLaunch launch;
+  StemLaunch stem;
   int tiles_per_image = 0;  // spatial
   // pool
   const __half* pin = nullptr;
   __half* pout = nullptr;
-  int H = 0, W = 0, C = 0, OH = 0, OW = 0;
+  int H = 0, W = 0, C = 0, OH = 0, OW = 0, in_row_px = 0;
+  int64_t in_img_px = 0;
 };
 
 struct HostVar {
@@ -239,7 +243,7 @@ static int upload(vnect_t* h, const std::vector<T>& v, T** out) {
 // ------------------------------------------------------------------------------------------------ plan
 static int new_act(vnect_t* h, const std::string& name, int H, int W, int C) {
   Act a;
-  a.H = H; a.W = W; a.C = C;
+  a.H = H; a.W = W; a.C = C; a.row_px = W; a.img_px = (int64_t)H * W;
   int rc = dev_alloc(h, &a.p, (size_t)h->cap_fw * H * W * C, true);
   if (rc) return rc;
   h->acts[name] = a;
@@ -385,7 +389,8 @@ static int alloc_prepost(vnect_t* h) {
   // stem input: parity-split, zero-padded NHWC4 (zeros are written once here and never touched again)
   h->stem_rpp = S / 2 + 3;
   h->stem_pitch = (S + 6) * 4;
-  if ((rc = dev_alloc(h, &h->x1, (size_t)nb * 2 * h->stem_rpp * h->stem_pitch, true))) return rc;
+  // + slack: the last strip of the last image reads a few KB past its parity plane (stem_gemm.cuh)
+  if ((rc = dev_alloc(h, &h->x1, (size_t)nb * 2 * h->stem_rpp * h->stem_pitch + 8192, true))) return rc;
   if ((rc = dev_alloc(h, &h->maps, (size_t)nb * 84 * h->hs * h->hs, true))) return rc;
   const int mf = h->cfg.max_frames, ms = h->cfg.max_streams;
   h->d_frames_bytes = (size_t)mf * h->cfg.max_input_h * h->cfg.max_input_w * 3;
@@ -494,25 +499,23 @@ int vnect_finalize(vnect_t* h) {
 
   const int S = h->S, nb = h->cap_fw;
   int rc;
-  {
+  {  // conv1 (vnect_model.py:27): raw-strip implicit GEMM, weights resident in smem (stem_gemm.cuh)
+    std::vector<__half> wk = to_half(pack_stem(h->vars.at("conv1/weights"))), wc(wk.size());
+    pack_stem_canonical(wk.data(), wc.data());
     __half* dw = nullptr;
     float* db = nullptr;
-    rc = upload(h, to_half(pack_stem(h->vars.at("conv1/weights"))), &dw);
-    if (rc) return rc;
-    rc = upload(h, h->vars.at("conv1/biases").data, &db);
-    if (rc) return rc;
-    rc = new_act(h, "conv1", S / 2, S / 2, 64);
-    if (rc) return rc;
-    ConvSpec s;
-    s.kind = CONV_STEM7;
-    s.NB = nb; s.H = S / 2; s.W = S / 2;
-    s.in = h->x1; s.stem_rows_per_parity = h->stem_rpp; s.stem_row_pitch = h->stem_pitch;
-    s.w = dw; s.n_pad = 64; s.n_valid = 64; s.block_n = 64; s.bias = db; s.relu_cols = 64;
-    s.out = h->acts.at("conv1").p; s.ldc = 64; s.epi = EPI_TMA;
+    if ((rc = upload(h, wc, &dw))) return rc;
+    if ((rc = upload(h, h->vars.at("conv1/biases").data, &db))) return rc;
+    Act a;
+    a.H = S / 2; a.W = S / 2; a.C = 64; a.row_px = S / 2 + 3;
+    a.img_px = (int64_t)((a.H * a.row_px + kBlockM - 1) / kBlockM) * kBlockM;
+    if ((rc = dev_alloc(h, &a.p, (size_t)nb * a.img_px * 64, true))) return rc;
+    h->acts["conv1"] = a;
     Step st;
-    st.kind = 0; st.name = "conv1";
+    st.kind = 2; st.name = "conv1";
     std::string err;
-    if (!build_conv(s, h->num_sms, &st.launch, &err)) return fail(h, VNECT_E_CUDA, "conv1: %s", err.c_str());
+    if (!build_stem(h->x1, S, h->stem_rpp, h->stem_pitch, dw, db, a.p, nb, h->num_sms, &st.stem, &err))
+      return fail(h, VNECT_E_CUDA, "conv1: %s", err.c_str());
     h->steps.push_back(st);
   }
   {  // pool1 (vnect_model.py:29)
@@ -522,6 +525,7 @@ int vnect_finalize(vnect_t* h) {
     st.kind = 1; st.name = "pool1";
     st.pin = h->acts.at("conv1").p; st.pout = h->acts.at("pool1").p;
     st.H = S / 2; st.W = S / 2; st.C = 64; st.OH = S / 4; st.OW = S / 4;
+    st.in_row_px = h->acts.at("conv1").row_px; st.in_img_px = h->acts.at("conv1").img_px;
     h->steps.push_back(st);
   }
   if ((rc = add_block(h, "res2a", "pool1", 64, 64, 256, true, "", false))) return rc;
@@ -592,7 +596,7 @@ int vnect_finalize(vnect_t* h) {
     h->steps.push_back(st);
   }
   h->conv_steps = 0;
-  for (const Step& st : h->steps) h->conv_steps += st.kind == 0;
+  for (const Step& st : h->steps) h->conv_steps += st.kind != 1;
 
   h->vars.clear();  // host copies no longer needed
   h->finalized = true;
@@ -610,9 +614,12 @@ static int run_forward(vnect_t* h, int n, cudaEvent_t* layer_events = nullptr) {
     if (st.kind == 0) {
       set_batch(st.launch, n, h->num_sms);
       CU(h, launch_conv(st.launch, h->stream));
+    } else if (st.kind == 2) {
+      stem_set_batch(st.stem, n, h->num_sms);
+      CU(h, launch_stem(st.stem, h->stream));
     } else {
       const int64_t total = (int64_t)n * st.OH * st.OW * (st.C / 8);
-      maxpool3x3s2_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(st.pin, st.pout, n, st.H, st.W, st.C, st.OH, st.OW);
+      maxpool3x3s2_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(st.pin, st.pout, n, st.H, st.W, st.C, st.OH, st.OW, st.in_row_px, st.in_img_px);
       CU(h, cudaGetLastError());
     }
     ++h->launches;
@@ -909,10 +916,16 @@ int vnect_get_tap(vnect_t* h, const char* name, int32_t n, float* out_nhwc, int6
   const size_t elems = (size_t)n * a.H * a.W * a.C;
   if (!out_nhwc) return VNECT_OK;
   if ((int64_t)elems > capacity_elems) return fail(h, VNECT_E_INVALID, "buffer too small for tap '%s'", name);
-  std::vector<__half> tmp(elems);
+  std::vector<__half> tmp((size_t)n * a.img_px * a.C);
   CU(h, cudaStreamSynchronize(h->stream));
-  CU(h, cudaMemcpy(tmp.data(), a.p, elems * sizeof(__half), cudaMemcpyDeviceToHost));
-  for (size_t i = 0; i < elems; ++i) out_nhwc[i] = __half2float(tmp[i]);
+  CU(h, cudaMemcpy(tmp.data(), a.p, tmp.size() * sizeof(__half), cudaMemcpyDeviceToHost));
+  size_t o = 0;
+  for (int i = 0; i < n; ++i)
+    for (int y = 0; y < a.H; ++y)
+      for (int x = 0; x < a.W; ++x) {
+        const __half* src = tmp.data() + ((size_t)i * a.img_px + (size_t)y * a.row_px + x) * a.C;
+        for (int c = 0; c < a.C; ++c) out_nhwc[o++] = __half2float(src[c]);
+      }
   return VNECT_OK;
 }
 
@@ -933,6 +946,7 @@ double vnect_info(vnect_t* h, const char* key) {
     double f = 0;
     for (const Step& st : h->steps)
       if (st.kind == 0) f += st.launch.flops / h->cap_fw;
+      else if (st.kind == 2) f += 2.0 * st.stem.p.tiles_per_image * kBlockM * 64 * 224;
     return f;
   }
   if (k == "hm_size") return h->hs;
