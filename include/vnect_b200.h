@@ -68,6 +68,15 @@ int vnect_estimate(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H, 
                    int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d,
                    double* joints2d, float* joints3d);
 
+/* pipelined form of vnect_estimate: enqueue one batch on submission lane 0 or 1 and return immediately; the H2D copy
+ * of a lane overlaps the kernels of the other one.  bgr / joints2d / joints3d are HOST pointers that must stay valid
+ * (pinned memory recommended) until vnect_wait(h, lane) returns.  Batches execute in submission order, so frames of one
+ * stream may alternate between lanes.  vnect_estimate == vnect_submit(lane 0) + vnect_wait(lane 0). */
+int vnect_submit(vnect_t* h, int32_t lane, const uint8_t* bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
+                 int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d, double* joints2d,
+                 float* joints3d);
+int vnect_wait(vnect_t* h, int32_t lane);
+
 /* same computation with the frames and the results resident in device memory (dev_bgr, dev_joints2d, dev_joints3d are
  * DEVICE pointers; stream_ids / t2d / t3d stay host arrays).  Asynchronous on the handle's stream. */
 int vnect_estimate_device(vnect_t* h, const uint8_t* dev_bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,

@@ -335,3 +335,21 @@ def test_vnect_estimator_dropin(w0, oracle_net_w0, capsys):
     batch, scaler, offs = VNectEstimator.gen_input_batch(np.ascontiguousarray(img), 368, [1.0, 0.7])
     rb, rs, ro = prepost.gen_input_batch(np.ascontiguousarray(img), 368, [1.0, 0.7])
     assert np.array_equal(batch, rb.astype(np.float16).astype(np.float32)) and scaler == rs and offs == ro
+
+
+def test_pipelined_submit_matches_estimate(engine_w0):
+    """vnect_submit / vnect_wait on alternating lanes give exactly what back-to-back vnect_estimate calls give."""
+    frames = [np.stack([synth.stream_frame(s, k) for s in range(4)]) for k in range(4)]
+    ids = np.arange(4)
+    engine_w0.reset()
+    want = [engine_w0.estimate(frames[k], ids, np.full(4, 7.0 + 0.04 * k), np.full(4, 7.01 + 0.04 * k)) for k in range(4)]
+    engine_w0.reset()
+    got = []
+    for k in range(4):
+        if k >= 2:
+            engine_w0.wait(k & 1)
+        got.append(engine_w0.submit(k & 1, frames[k], ids, np.full(4, 7.0 + 0.04 * k), np.full(4, 7.01 + 0.04 * k)))
+    engine_w0.wait(0)
+    engine_w0.wait(1)
+    for (a2, a3), (b2, b3) in zip(want, got):
+        assert np.array_equal(a2, b2) and np.array_equal(a3, b3)

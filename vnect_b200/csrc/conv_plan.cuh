@@ -364,7 +364,8 @@ inline bool build_stem(const __half* x1, int S, int rows_per_parity, int row_pit
   return encode_tmap(&L->tmap_out, out, 5, od, os, ob, 128, err);
 }
 
-inline void stem_set_batch(StemLaunch& L, int nb, int num_sms) {
+inline void stem_set_batch(StemLaunch& L, int nb, int num_sms, int img0 = 0) {
+  L.p.img0 = img0;
   L.p.num_tiles = nb * L.p.tiles_per_image;
   L.grid = L.p.num_tiles < num_sms ? L.p.num_tiles : num_sms;
 }

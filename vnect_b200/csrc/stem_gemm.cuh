@@ -26,7 +26,8 @@ struct StemParams {
   const float* bias;          // [64]
   int vw;                     // virtual output columns per row (S/2 + 3)
   int tiles_per_image;        // ceil(S/2 * vw / 128)
-  int num_tiles;              // NB * tiles_per_image
+  int num_tiles;              // images in this launch * tiles_per_image
+  int img0;                   // first image of this launch (input side; the output buffer is a per-launch ring)
 };
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -71,6 +72,7 @@ stem_gemm_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
   uint64_t* tmem_empty = bars + 2 * kStemStages + 2;
   uint64_t* w_bar = bars + 2 * kStemStages + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStemStages + 5);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kStemStages + 6);  // 64 floats (BAR region has 512 B)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,6 +90,7 @@ stem_gemm_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (threadIdx.x >= 128 && threadIdx.x < 192) bias_s[threadIdx.x - 128] = p.bias[threadIdx.x - 128];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -102,7 +105,7 @@ stem_gemm_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int img = tile / p.tiles_per_image;
         const int v0 = (tile - img * p.tiles_per_image) * kBlockM;
-        const uint8_t* img_base = p.x1 + static_cast<int64_t>(img) * 2 * p.plane_bytes;
+        const uint8_t* img_base = p.x1 + static_cast<int64_t>(img + p.img0) * 2 * p.plane_bytes;
         for (int ky = 0; ky < 7; ++ky) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], kStemStripBytes);
@@ -172,8 +175,8 @@ stem_gemm_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
       named_bar_sync(1, 128);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + 8 * j));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + 8 * j + 4));
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + 8 * j);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + 8 * j + 4);
         uint4 o;
         o.x = pack_half2(fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f));
         o.y = pack_half2(fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.f));

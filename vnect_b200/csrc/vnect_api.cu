@@ -61,27 +61,39 @@ struct vnect_handle {
   // output maps, planar fp32 [cap_fw][84][hs][hs]
   float* maps = nullptr;
   // pre/post buffers
-  uint8_t* d_frames = nullptr;
   size_t d_frames_bytes = 0;
   uint8_t* d_sq = nullptr;
   float* d_f32_in = nullptr;  // vnect_forward staging [cap_fw][S][S][3]
   ScaleTable* d_tables = nullptr;
-  int* d_stream_ids = nullptr;
-  double *d_t2d = nullptr, *d_t3d = nullptr;
   FilterState *d_st2d = nullptr, *d_st3d = nullptr;
   double* d_j2_box = nullptr;
   float* d_j3_raw = nullptr;
   int* d_raw_argmax = nullptr;
   unsigned int* d_counter = nullptr;
-  double* d_out2d = nullptr;
-  float* d_out3d = nullptr;
   double* d_filter_scratch = nullptr;
-  // pinned host staging for the small per-call arrays
-  int* h_stream_ids = nullptr;
-  double *h_t2d = nullptr, *h_t3d = nullptr;
+  // Two submission lanes: each owns its input staging, per-call meta (pinned host + device) and result buffers, so
+  // the H2D copy of batch k+1 (copy stream) overlaps the kernels of batch k (compute stream).
+  struct Lane {
+    uint8_t* d_frames = nullptr;
+    int* d_stream_ids = nullptr;
+    double *d_t2d = nullptr, *d_t3d = nullptr;
+    double* d_out2d = nullptr;
+    float* d_out3d = nullptr;
+    int* h_stream_ids = nullptr;
+    double *h_t2d = nullptr, *h_t3d = nullptr;
+    cudaEvent_t copy_done = nullptr, done = nullptr;
+    bool pending = false;
+  } lanes[2];
+  Lane* cur = &lanes[0];
+  cudaStream_t copy_stream = nullptr;
+  unsigned device_calls = 0;
   std::vector<double> last_t2d, last_t3d;  // host mirror of the filters' last timestamps (NaN = none yet)
   PyramidParams pyr{};
 };
+
+// Images per conv1+pool1 launch pair.  Chunks of 8 (35 MB, L2-resident) were measured SLOWER on B200 (572 us vs 380 us
+// for 128 images: 32 small launches cost more than the HBM round trip saves), so the whole batch goes in one chunk.
+constexpr int kStemChunk = 1 << 20;
 
 static int fail(vnect_t* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -394,25 +406,30 @@ static int alloc_prepost(vnect_t* h) {
   if ((rc = dev_alloc(h, &h->maps, (size_t)nb * 84 * h->hs * h->hs, true))) return rc;
   const int mf = h->cfg.max_frames, ms = h->cfg.max_streams;
   h->d_frames_bytes = (size_t)mf * h->cfg.max_input_h * h->cfg.max_input_w * 3;
-  if ((rc = dev_alloc(h, &h->d_frames, h->d_frames_bytes))) return rc;
+  CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& L : h->lanes) {
+    if ((rc = dev_alloc(h, &L.d_frames, h->d_frames_bytes))) return rc;
+    if ((rc = dev_alloc(h, &L.d_stream_ids, mf))) return rc;
+    if ((rc = dev_alloc(h, &L.d_t2d, mf))) return rc;
+    if ((rc = dev_alloc(h, &L.d_t3d, mf))) return rc;
+    if ((rc = dev_alloc(h, &L.d_out2d, (size_t)mf * kJoints * 2))) return rc;
+    if ((rc = dev_alloc(h, &L.d_out3d, (size_t)mf * kJoints * 3))) return rc;
+    CU(h, cudaMallocHost(&L.h_stream_ids, mf * sizeof(int)));
+    CU(h, cudaMallocHost(&L.h_t2d, mf * sizeof(double)));
+    CU(h, cudaMallocHost(&L.h_t3d, mf * sizeof(double)));
+    CU(h, cudaEventCreateWithFlags(&L.copy_done, cudaEventDisableTiming));
+    CU(h, cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+  }
   if ((rc = dev_alloc(h, &h->d_sq, (size_t)mf * S * S * 3))) return rc;
   if ((rc = dev_alloc(h, &h->d_f32_in, (size_t)nb * S * S * 3))) return rc;
   if ((rc = build_tables(h))) return rc;
-  if ((rc = dev_alloc(h, &h->d_stream_ids, mf))) return rc;
-  if ((rc = dev_alloc(h, &h->d_t2d, mf))) return rc;
-  if ((rc = dev_alloc(h, &h->d_t3d, mf))) return rc;
   if ((rc = dev_alloc(h, &h->d_st2d, (size_t)ms * kJoints * 2))) return rc;
   if ((rc = dev_alloc(h, &h->d_st3d, (size_t)ms * kJoints * 3))) return rc;
   if ((rc = dev_alloc(h, &h->d_j2_box, (size_t)mf * kJoints * 2))) return rc;
   if ((rc = dev_alloc(h, &h->d_j3_raw, (size_t)mf * kJoints * 3))) return rc;
   if ((rc = dev_alloc(h, &h->d_raw_argmax, (size_t)mf * kJoints * 2))) return rc;
   if ((rc = dev_alloc(h, &h->d_counter, mf))) return rc;
-  if ((rc = dev_alloc(h, &h->d_out2d, (size_t)mf * kJoints * 2))) return rc;
-  if ((rc = dev_alloc(h, &h->d_out3d, (size_t)mf * kJoints * 3))) return rc;
   if ((rc = dev_alloc(h, &h->d_filter_scratch, 64))) return rc;
-  CU(h, cudaMallocHost(&h->h_stream_ids, mf * sizeof(int)));
-  CU(h, cudaMallocHost(&h->h_t2d, mf * sizeof(double)));
-  CU(h, cudaMallocHost(&h->h_t3d, mf * sizeof(double)));
   h->last_t2d.assign(ms, NAN);
   h->last_t3d.assign(ms, NAN);
   PyramidParams& py = h->pyr;
@@ -509,12 +526,14 @@ int vnect_finalize(vnect_t* h) {
     Act a;
     a.H = S / 2; a.W = S / 2; a.C = 64; a.row_px = S / 2 + 3;
     a.img_px = (int64_t)((a.H * a.row_px + kBlockM - 1) / kBlockM) * kBlockM;
-    if ((rc = dev_alloc(h, &a.p, (size_t)nb * a.img_px * 64, true))) return rc;
+    // conv1's output is consumed only by pool1; both run over chunks of kStemChunk images through this buffer
+    const int ring = nb < kStemChunk ? nb : kStemChunk;
+    if ((rc = dev_alloc(h, &a.p, (size_t)ring * a.img_px * 64, true))) return rc;
     h->acts["conv1"] = a;
     Step st;
     st.kind = 2; st.name = "conv1";
     std::string err;
-    if (!build_stem(h->x1, S, h->stem_rpp, h->stem_pitch, dw, db, a.p, nb, h->num_sms, &st.stem, &err))
+    if (!build_stem(h->x1, S, h->stem_rpp, h->stem_pitch, dw, db, a.p, ring, h->num_sms, &st.stem, &err))
       return fail(h, VNECT_E_CUDA, "conv1: %s", err.c_str());
     h->steps.push_back(st);
   }
@@ -615,12 +634,22 @@ static int run_forward(vnect_t* h, int n, cudaEvent_t* layer_events = nullptr) {
       set_batch(st.launch, n, h->num_sms);
       CU(h, launch_conv(st.launch, h->stream));
     } else if (st.kind == 2) {
-      stem_set_batch(st.stem, n, h->num_sms);
-      CU(h, launch_stem(st.stem, h->stream));
+      // conv1 + pool1 chunk by chunk (the next step, pool1, is executed here too and skipped below)
+      Step& pool = *(&st + 1);
+      for (int i0 = 0; i0 < n; i0 += kStemChunk) {
+        const int cn = n - i0 < kStemChunk ? n - i0 : kStemChunk;
+        stem_set_batch(st.stem, cn, h->num_sms, i0);
+        CU(h, launch_stem(st.stem, h->stream));
+        const int64_t total = (int64_t)cn * pool.OH * pool.OW * (pool.C / 8);
+        maxpool3x3s2_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(
+            pool.pin, pool.pout + (size_t)i0 * pool.OH * pool.OW * pool.C, cn, pool.H, pool.W, pool.C, pool.OH, pool.OW,
+            pool.in_row_px, pool.in_img_px);
+        CU(h, cudaGetLastError());
+        h->launches += 2;
+      }
+      continue;
     } else {
-      const int64_t total = (int64_t)n * st.OH * st.OW * (st.C / 8);
-      maxpool3x3s2_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(st.pin, st.pout, n, st.H, st.W, st.C, st.OH, st.OW, st.in_row_px, st.in_img_px);
-      CU(h, cudaGetLastError());
+      continue;  // pool1 ran inside the conv1 step
     }
     ++h->launches;
   }
@@ -674,7 +703,18 @@ static int run_preprocess(vnect_t* h, const uint8_t* dev_bgr, int n_frames, int 
 }
 
 // validates ids / timestamps on the host exactly where the reference would raise, then stages them to the device
-static int stage_frame_meta(vnect_t* h, int n_frames, const int32_t* stream_ids, const double* t2d, const double* t3d) {
+// waits until the lane's previous submission has fully completed (its pinned meta and device buffers are reusable)
+static int lane_acquire(vnect_t* h, int lane) {
+  h->cur = &h->lanes[lane];
+  if (h->cur->pending) {
+    CU(h, cudaEventSynchronize(h->cur->done));
+    h->cur->pending = false;
+  }
+  return VNECT_OK;
+}
+
+static int stage_frame_meta(vnect_t* h, int n_frames, const int32_t* stream_ids, const double* t2d, const double* t3d,
+                            cudaStream_t copy_on) {
   if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames %d not in [1, %d]", n_frames, h->cfg.max_frames);
   std::set<int> seen;
   for (int i = 0; i < n_frames; ++i) {
@@ -690,21 +730,19 @@ static int stage_frame_meta(vnect_t* h, int n_frames, const int32_t* stream_ids,
         return fail(h, VNECT_E_ZERO_DT, "float division by zero (stream %d: repeated 3D timestamp %.17g)", sid, t3d[i]);
     }
   }
-  // the previous call's async H2D of these pinned arrays must be done before they are overwritten
-  CU(h, cudaStreamSynchronize(h->stream));
   for (int i = 0; i < n_frames; ++i) {
     const int sid = stream_ids ? stream_ids[i] : i;
-    h->h_stream_ids[i] = sid;
-    h->h_t2d[i] = t2d ? t2d[i] : 0.0;
-    h->h_t3d[i] = t3d ? t3d[i] : 0.0;
+    h->cur->h_stream_ids[i] = sid;
+    h->cur->h_t2d[i] = t2d ? t2d[i] : 0.0;
+    h->cur->h_t3d[i] = t3d ? t3d[i] : 0.0;
     if (h->cfg.filters) {
       h->last_t2d[sid] = t2d[i];
       h->last_t3d[sid] = t3d[i];
     }
   }
-  CU(h, cudaMemcpyAsync(h->d_stream_ids, h->h_stream_ids, n_frames * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->d_t2d, h->h_t2d, n_frames * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->d_t3d, h->h_t3d, n_frames * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->cur->d_stream_ids, h->cur->h_stream_ids, n_frames * sizeof(int), cudaMemcpyHostToDevice, copy_on));
+  CU(h, cudaMemcpyAsync(h->cur->d_t2d, h->cur->h_t2d, n_frames * sizeof(double), cudaMemcpyHostToDevice, copy_on));
+  CU(h, cudaMemcpyAsync(h->cur->d_t3d, h->cur->h_t3d, n_frames * sizeof(double), cudaMemcpyHostToDevice, copy_on));
   return VNECT_OK;
 }
 
@@ -713,7 +751,7 @@ static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, i
   PostParams p;
   p.n_frames = n_frames; p.n_scales = h->n_scales; p.hs = h->hs; p.S = h->S;
   p.maps = h->maps; p.tables = h->d_tables;
-  p.stream_ids = h->d_stream_ids; p.t2d = h->d_t2d; p.t3d = h->d_t3d;
+  p.stream_ids = h->cur->d_stream_ids; p.t2d = h->cur->d_t2d; p.t3d = h->cur->d_t3d;
   p.st2d = h->d_st2d; p.st3d = h->d_st3d;
   p.cfg2d = {30.0, 1.7, 0.3, 0.4};  // estimator.py:34-39
   p.cfg3d = {30.0, 0.8, 0.4, 0.4};  // estimator.py:40-45
@@ -765,37 +803,64 @@ int vnect_estimate_device(vnect_t* h, const uint8_t* dev_bgr, int32_t n_frames, 
   if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
   if (!dev_bgr || !dev_joints2d || !dev_joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
   if (H < 2 || W < 2 || pitch < (int64_t)W * 3) return fail(h, VNECT_E_INVALID, "bad frame geometry %dx%d pitch %lld", H, W, (long long)pitch);
-  int rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d);
+  // alternate lanes for the per-call meta so the host can run one call ahead of the GPU
+  int rc = lane_acquire(h, (int)(h->device_calls++ & 1));
   if (rc) return rc;
+  if ((rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d, h->stream))) return rc;
   const Geometry g = squarify_geometry(h->S, H, W);
   if ((rc = run_preprocess(h, dev_bgr, n_frames, H, W, pitch, frame_stride, g))) return rc;
   if ((rc = run_forward(h, n_frames * h->n_scales))) return rc;
-  return run_postprocess(h, n_frames, g.scaler, g.off_x, g.off_y, dev_joints2d, dev_joints3d);
+  if ((rc = run_postprocess(h, n_frames, g.scaler, g.off_x, g.off_y, dev_joints2d, dev_joints3d))) return rc;
+  CU(h, cudaEventRecord(h->cur->done, h->stream));
+  h->cur->pending = true;
+  return VNECT_OK;
 }
 
-int vnect_estimate(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
-                   int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d,
-                   double* joints2d, float* joints3d) {
+int vnect_submit(vnect_t* h, int32_t lane, const uint8_t* bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
+                 int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d, double* joints2d,
+                 float* joints3d) {
   if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  if (lane < 0 || lane > 1) return fail(h, VNECT_E_INVALID, "lane must be 0 or 1");
   if (!bgr || !joints2d || !joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
   if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames %d not in [1, %d]", n_frames, h->cfg.max_frames);
   if (H < 2 || W < 2 || H > h->cfg.max_input_h || W > h->cfg.max_input_w)
     return fail(h, VNECT_E_INVALID, "frame %dx%d outside [2, max_input %dx%d]", H, W, h->cfg.max_input_h, h->cfg.max_input_w);
   if (pitch < (int64_t)W * 3) return fail(h, VNECT_E_INVALID, "pitch smaller than a row");
-  // host -> device, tightly packed on the device
+  int rc = lane_acquire(h, lane);
+  if (rc) return rc;
+  // host -> device on the copy stream (tightly packed on the device), overlapping the previous lane's kernels
+  if ((rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d, h->copy_stream))) return rc;
   const int64_t dpitch = (int64_t)W * 3, dstride = dpitch * H;
   if (pitch == dpitch && frame_stride == dstride) {
-    CU(h, cudaMemcpyAsync(h->d_frames, bgr, (size_t)dstride * n_frames, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->cur->d_frames, bgr, (size_t)dstride * n_frames, cudaMemcpyHostToDevice, h->copy_stream));
   } else {
     for (int i = 0; i < n_frames; ++i)
-      CU(h, cudaMemcpy2DAsync(h->d_frames + (size_t)i * dstride, dpitch, bgr + (size_t)i * frame_stride, pitch, dpitch, H, cudaMemcpyHostToDevice, h->stream));
+      CU(h, cudaMemcpy2DAsync(h->cur->d_frames + (size_t)i * dstride, dpitch, bgr + (size_t)i * frame_stride, pitch, dpitch, H, cudaMemcpyHostToDevice, h->copy_stream));
   }
-  int rc = vnect_estimate_device(h, h->d_frames, n_frames, H, W, dpitch, dstride, stream_ids, t2d, t3d, h->d_out2d, h->d_out3d);
-  if (rc) return rc;
-  CU(h, cudaMemcpyAsync(joints2d, h->d_out2d, (size_t)n_frames * kJoints * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaMemcpyAsync(joints3d, h->d_out3d, (size_t)n_frames * kJoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaEventRecord(h->cur->copy_done, h->copy_stream));
+  CU(h, cudaStreamWaitEvent(h->stream, h->cur->copy_done, 0));
+  const Geometry g = squarify_geometry(h->S, H, W);
+  if ((rc = run_preprocess(h, h->cur->d_frames, n_frames, H, W, dpitch, dstride, g))) return rc;
+  if ((rc = run_forward(h, n_frames * h->n_scales))) return rc;
+  if ((rc = run_postprocess(h, n_frames, g.scaler, g.off_x, g.off_y, h->cur->d_out2d, h->cur->d_out3d))) return rc;
+  CU(h, cudaMemcpyAsync(joints2d, h->cur->d_out2d, (size_t)n_frames * kJoints * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(joints3d, h->cur->d_out3d, (size_t)n_frames * kJoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaEventRecord(h->cur->done, h->stream));
+  h->cur->pending = true;
   return VNECT_OK;
+}
+
+int vnect_wait(vnect_t* h, int32_t lane) {
+  if (!h || lane < 0 || lane > 1) return fail(h, VNECT_E_INVALID, "bad handle or lane");
+  return lane_acquire(h, lane);
+}
+
+int vnect_estimate(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
+                   int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d,
+                   double* joints2d, float* joints3d) {
+  int rc = vnect_submit(h, 0, bgr, n_frames, H, W, pitch, frame_stride, stream_ids, t2d, t3d, joints2d, joints3d);
+  if (rc) return rc;
+  return vnect_wait(h, 0);
 }
 
 int vnect_preprocess(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
@@ -805,10 +870,11 @@ int vnect_preprocess(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H
   if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames out of range");
   if (H < 2 || W < 2 || H > h->cfg.max_input_h || W > h->cfg.max_input_w) return fail(h, VNECT_E_INVALID, "frame size outside max_input");
   const int64_t dpitch = (int64_t)W * 3, dstride = dpitch * H;
+  if (lane_acquire(h, 0)) return VNECT_E_CUDA;
   for (int i = 0; i < n_frames; ++i)
-    CU(h, cudaMemcpy2DAsync(h->d_frames + (size_t)i * dstride, dpitch, bgr + (size_t)i * frame_stride, pitch, dpitch, H, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpy2DAsync(h->cur->d_frames + (size_t)i * dstride, dpitch, bgr + (size_t)i * frame_stride, pitch, dpitch, H, cudaMemcpyHostToDevice, h->stream));
   const Geometry g = squarify_geometry(h->S, H, W);
-  int rc = run_preprocess(h, h->d_frames, n_frames, H, W, dpitch, dstride, g);
+  int rc = run_preprocess(h, h->cur->d_frames, n_frames, H, W, dpitch, dstride, g);
   if (rc) return rc;
   const int n = n_frames * h->n_scales, S = h->S;
   stem_to_f32_kernel<<<grid_for((int64_t)n * S * S, 256, h->num_sms), 256, 0, h->stream>>>(h->x1, h->d_f32_in, n, S, h->stem_rpp, h->stem_pitch);
@@ -829,8 +895,9 @@ int vnect_postprocess(vnect_t* h, const float* hm, const float* xm, const float*
                       int32_t offset_y, double* joints2d, float* joints3d, int32_t* raw_argmax) {
   if (!h || !h->x1) return fail(h, VNECT_E_INVALID, "handle not created");
   if (!hm || !xm || !ym || !zm || !joints2d || !joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
-  int rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d);
+  int rc = lane_acquire(h, 0);
   if (rc) return rc;
+  if ((rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d, h->stream))) return rc;
   const int n = n_frames * h->n_scales, hs = h->hs;
   const size_t plane = (size_t)hs * hs;
   std::vector<float> planar((size_t)n * 84 * plane);
@@ -843,9 +910,9 @@ int vnect_postprocess(vnect_t* h, const float* hm, const float* xm, const float*
         for (size_t px = 0; px < plane; ++px) dst[px] = src[px * kJoints];
       }
   CU(h, cudaMemcpyAsync(h->maps, planar.data(), planar.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  if ((rc = run_postprocess(h, n_frames, scaler, offset_x, offset_y, h->d_out2d, h->d_out3d))) return rc;
-  CU(h, cudaMemcpyAsync(joints2d, h->d_out2d, (size_t)n_frames * kJoints * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  CU(h, cudaMemcpyAsync(joints3d, h->d_out3d, (size_t)n_frames * kJoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if ((rc = run_postprocess(h, n_frames, scaler, offset_x, offset_y, h->cur->d_out2d, h->cur->d_out3d))) return rc;
+  CU(h, cudaMemcpyAsync(joints2d, h->cur->d_out2d, (size_t)n_frames * kJoints * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(joints3d, h->cur->d_out3d, (size_t)n_frames * kJoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   if (raw_argmax)
     CU(h, cudaMemcpyAsync(raw_argmax, h->d_raw_argmax, (size_t)n_frames * kJoints * 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
@@ -996,9 +1063,14 @@ void vnect_destroy(vnect_t* h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
-  if (h->h_stream_ids) cudaFreeHost(h->h_stream_ids);
-  if (h->h_t2d) cudaFreeHost(h->h_t2d);
-  if (h->h_t3d) cudaFreeHost(h->h_t3d);
+  for (auto& L : h->lanes) {
+    if (L.h_stream_ids) cudaFreeHost(L.h_stream_ids);
+    if (L.h_t2d) cudaFreeHost(L.h_t2d);
+    if (L.h_t3d) cudaFreeHost(L.h_t3d);
+    if (L.copy_done) cudaEventDestroy(L.copy_done);
+    if (L.done) cudaEventDestroy(L.done);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

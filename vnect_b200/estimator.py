@@ -132,6 +132,25 @@ class VNectEngine:
                                              _ptr(ids), _ptr(t2d), _ptr(t3d), _ptr(j2), _ptr(j3)))
         return j2, j3
 
+    def submit(self, lane, frames, stream_ids=None, t2d=None, t3d=None, out=None):
+        """Pipelined estimate(): enqueue a batch on lane 0/1 and return (joints_2d, joints_3d) arrays that are filled
+        once wait(lane) returns.  `frames` and the result arrays must stay alive until then (pinned memory makes the
+        copies truly asynchronous)."""
+        frames, st = self._frames(frames)
+        n, h, w = frames.shape[:3]
+        ids, t2d, t3d = self._meta(n, stream_ids, t2d, t3d)
+        j2, j3 = out if out is not None else (np.empty((n, JOINTS, 2), np.float64), np.empty((n, JOINTS, 3), np.float32))
+        self._check(self._lib.vnect_submit(self._h, int(lane), _ptr(frames), n, h, w, st[1],
+                                           st[0] if n > 1 else st[1] * h, _ptr(ids), _ptr(t2d), _ptr(t3d), _ptr(j2),
+                                           _ptr(j3)))
+        self._inflight = getattr(self, "_inflight", {})
+        self._inflight[int(lane)] = (frames, j2, j3)  # keep the buffers alive
+        return j2, j3
+
+    def wait(self, lane):
+        self._check(self._lib.vnect_wait(self._h, int(lane)))
+        return self.__dict__.get("_inflight", {}).pop(int(lane), (None, None, None))[1:]
+
     def estimate_device(self, dev_frames_ptr, n, h, w, dev_j2_ptr, dev_j3_ptr, stream_ids=None, t2d=None, t3d=None,
                         pitch=None, frame_stride=None):
         """Same path with frames / results resident in device memory (raw device pointers, e.g. tensor.data_ptr())."""
