@@ -44,7 +44,9 @@ struct ConvGemmParams {
   int tw, th, tiles_x, tiles_y;
   int num_m_tiles, num_n_tiles;
   int phases;            // 1, or 4 for the transposed conv
-  int taps, cblocks;     // K loop = taps * cblocks blocks of BLOCK_K
+  int taps, cblocks;     // K loop = taps * cblocks blocks of BLOCK_K ...
+  int cblocks2;          // ... followed by cblocks2 blocks read from a SECOND activation tensor (1x1, same rows):
+                         // a projection shortcut folded into the block's last conv as extra K (W = [W_2c | W_1])
   int b_rows_per_phase;  // padded Cout
   signed char tap_dx[16], tap_dy[16], tap_dp[16];  // [phase * taps + tap]
   uint32_t stage_tx_bytes;
@@ -96,7 +98,7 @@ template <int BLOCK_N, int SWZ, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                 const __grid_constant__ ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ ConvGemmParams p) {
   using Cfg = GemmCfg<BLOCK_N, SWZ, EPI>;
   constexpr bool kTmaEpi = (EPI == EPI_TMA || EPI == EPI_TMA_RES);
   constexpr int BLOCK_K = Cfg::BLOCK_K;
@@ -122,6 +124,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (p.cblocks2 > 0) tma_prefetch_desc(&tmap_a2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -145,7 +148,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   const int total_tiles = p.phases * p.num_m_tiles * p.num_n_tiles;
-  const int k_iters = p.taps * p.cblocks;
+  const int k_iters = p.taps * p.cblocks + p.cblocks2;
 
   if (warp == 0) {
     // ================================================================ TMA producer
@@ -183,6 +186,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               stage = 0;
               phase ^= 1;
             }
+          }
+        }
+        for (int cb = 0; cb < p.cblocks2; ++cb) {  // folded projection shortcut: second A tensor, 1x1
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          tma_load_5d(sa, &tmap_a2, &full_bar[stage], cb * BLOCK_K, cx, cy, 0, cn);
+          tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (p.taps * p.cblocks + cb) * BLOCK_K, b_row);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }

@@ -92,10 +92,14 @@ struct ConvSpec {
   int in_stride = 1;
   int res_stride = 1;
   int spatial_1x1 = 0;
+  // folded projection shortcut (1x1 convs only): a second activation tensor [NB,H,W,cin2_pad] whose channels extend
+  // the K dimension; `w` is then [n_pad][cin_pad + cin2_pad]
+  const __half* in2 = nullptr;
+  int cin2_pad = 0;
 };
 
 struct ConvLaunch {
-  CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res;
+  CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res, tmap_a2;
   ConvGemmParams p;
   int block_n = 0, swz = 128, epi = 0, grid = 0;
   size_t smem = 0;
@@ -169,7 +173,8 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     strides[0] = (uint64_t)s.cin_pad * 2;
     strides[1] = strides[2] = strides[3] = (uint64_t)s.cin_pad * 2 * p.M;
     box[0] = block_k; box[1] = kBlockM; box[2] = 1; box[3] = 1; box[4] = 1;
-    k_total = s.cin_pad;
+    k_total = s.cin_pad + s.cin2_pad;
+    p.cblocks2 = s.cin2_pad / block_k;
   } else if (s.kind == CONV_3x3 || s.kind == CONV_DECONV4 || spatial1) {
     p.mode = 1;
     choose_tile(s.H, s.W, &p.tw, &p.th);
@@ -247,6 +252,17 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
   if (!encode_tmap(&L->tmap_b, s.w, 2, bd, bs, bb, swz, err)) return false;
   L->tmap_out = L->tmap_a;  // placeholders for the epilogues that do not use them
   L->tmap_res = L->tmap_a;
+  L->tmap_a2 = L->tmap_a;
+  if (s.in2) {
+    if (p.mode != 0 || s.kind != CONV_1x1) {
+      if (err) *err = "a folded shortcut needs a flat 1x1 conv";
+      return false;
+    }
+    uint64_t d2[5] = {(uint64_t)s.cin2_pad, (uint64_t)p.M, 1, 1, 1};
+    uint64_t s2[4] = {(uint64_t)s.cin2_pad * 2, (uint64_t)s.cin2_pad * 2 * p.M, (uint64_t)s.cin2_pad * 2 * p.M,
+                      (uint64_t)s.cin2_pad * 2 * p.M};
+    if (!encode_tmap(&L->tmap_a2, s.in2, 5, d2, s2, box, swz, err)) return false;
+  }
   if (s.epi == EPI_TMA || s.epi == EPI_TMA_RES) {
     // output (and residual) tiles leave / enter through swizzled smem in 64-channel chunks: same row tiling as A
     if (s.decimate || s.kind == CONV_DECONV4 || s.ldc % 8 != 0) {
@@ -294,7 +310,7 @@ inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<L.grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(L.tmap_a, L.tmap_b, L.tmap_out, L.tmap_res, L.p);
+  kern<<<L.grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(L.tmap_a, L.tmap_b, L.tmap_out, L.tmap_res, L.tmap_a2, L.p);
   return cudaGetLastError();
 }
 

@@ -27,7 +27,7 @@ struct NaiveGeom {
 
 // raw fp32 accumulators acc[ph][m][col]
 __global__ void naive_acc_kernel(const __half* __restrict__ in, const __half* __restrict__ w, float* __restrict__ acc,
-                                 NaiveGeom g) {
+                                 NaiveGeom g, const __half* __restrict__ in2 = nullptr, int cin2 = 0) {
   const long long total = (long long)g.phases * g.NB * g.H * g.W * g.n_pad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -56,6 +56,10 @@ __global__ void naive_acc_kernel(const __half* __restrict__ in, const __half* __
         for (int c = 0; c < g.cin_pad; ++c) s += __half2float(a[c]) * __half2float(wrow[(size_t)t * g.cin_pad + c]);
       }
     }
+    if (in2) {  // folded 1x1 shortcut: extra K from a second tensor on the same pixel
+      const __half* a2 = in2 + (((size_t)n * g.H + y) * g.W + x) * cin2;
+      for (int c = 0; c < cin2; ++c) s += __half2float(a2[c]) * __half2float(wrow[(size_t)g.taps * g.cin_pad + c]);
+    }
     acc[i] = s;
   }
 }
@@ -72,6 +76,7 @@ struct Case {
   bool bias, residual;
   int relu_cols, decimate;
   int in_stride = 1, res_stride = 1;
+  int cin2 = 0;  // folded shortcut: second input tensor with cin2 channels (1x1 only)
 };
 
 static int run_case(const Case& c, int num_sms, bool timing) {
@@ -91,7 +96,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   s.res_stride = c.res_stride;
   const int phases = c.kind == CONV_DECONV4 ? 4 : 1;
   const int taps = c.kind == CONV_1x1 ? 1 : c.kind == CONV_3x3 ? 9 : c.kind == CONV_DECONV4 ? 4 : 7;
-  const int k_total = c.kind == CONV_STEM7 ? 7 * 32 : taps * c.cin_pad;
+  const int k_total = c.kind == CONV_STEM7 ? 7 * 32 : taps * c.cin_pad + c.cin2;
   size_t in_elems;
   int rpp = 0, pitch = 0;
   if (c.kind == CONV_STEM7) {
@@ -123,6 +128,14 @@ static int run_case(const Case& c, int num_sms, bool timing) {
     for (auto& v : h_res) v = __float2half(frand());
   }
 
+  __half* d_in2 = nullptr;
+  std::vector<__half> h_in2;
+  if (c.cin2) {
+    h_in2.resize((size_t)c.NB * c.H * c.W * c.cin2);
+    for (auto& v : h_in2) v = __float2half(frand());
+    CK(cudaMalloc(&d_in2, h_in2.size() * 2));
+    CK(cudaMemcpy(d_in2, h_in2.data(), h_in2.size() * 2, cudaMemcpyHostToDevice));
+  }
   __half *d_in, *d_w, *d_res = nullptr;
   float *d_bias, *d_acc;
   void* d_out;
@@ -141,6 +154,8 @@ static int run_case(const Case& c, int num_sms, bool timing) {
     CK(cudaMemcpy(d_res, h_res.data(), h_res.size() * 2, cudaMemcpyHostToDevice));
   }
   s.in = d_in;
+  s.in2 = d_in2;
+  s.cin2_pad = c.cin2;
   s.w = d_w;
   s.bias = c.bias ? d_bias : nullptr;
   s.residual = d_res;
@@ -166,7 +181,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   g.in_stride = c.in_stride;
   g.taps = taps; g.phases = phases; g.k_total = k_total; g.stem_rpp = rpp; g.stem_pitch = pitch;
   memcpy(g.dx, L.p.tap_dx, 16); memcpy(g.dy, L.p.tap_dy, 16); memcpy(g.dp, L.p.tap_dp, 16);
-  naive_acc_kernel<<<1184, 256>>>(d_in, d_w, d_acc, g);
+  naive_acc_kernel<<<1184, 256>>>(d_in, d_w, d_acc, g, d_in2, c.cin2);
   CK(cudaDeviceSynchronize());
   std::vector<float> h_acc(acc_elems);
   CK(cudaMemcpy(h_acc.data(), d_acc, acc_elems * 4, cudaMemcpyDeviceToHost));
@@ -246,6 +261,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   }
   cudaFree(d_in); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_out); cudaFree(d_acc);
   if (d_res) cudaFree(d_res);
+  if (d_in2) cudaFree(d_in2);
   return bad == 0 ? 0 : 1;
 }
 
@@ -361,6 +377,9 @@ int main(int argc, char** argv) {
       {"S2 3x3 128->128 relu 46->23", CONV_3x3, 3, 23, 23, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0, 2, 1},
       {"S2RES 1x1 64->256 +res(92) relu 46x46", CONV_1x1, 2, 46, 46, 64, 256, 256, 256, EPI_TMA_RES, true, true, 256, 0, 1, 2},
       {"S2RES 1x1 128->512 +res(46) relu 23x23", CONV_1x1, 3, 23, 23, 128, 512, 512, 256, EPI_TMA_RES, true, true, 512, 0, 1, 2},
+      {"FOLD 1x1 64(+64)->256 relu 92x92", CONV_1x1, 2, 92, 92, 64, 256, 256, 256, EPI_TMA, true, false, 256, 0, 1, 1, 64},
+      {"FOLD 1x1 128(+256)->512 relu 46x46", CONV_1x1, 3, 46, 46, 128, 512, 512, 256, EPI_TMA, true, false, 512, 0, 1, 1, 256},
+      {"FOLD 1x1 512(+1024)->1024 relu 23x23", CONV_1x1, 5, 23, 23, 512, 1024, 1024, 256, EPI_TMA, true, false, 1024, 0, 1, 1, 1024},
       {"deconv4x4s2 256->192 head 23x23", CONV_DECONV4, 2, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false,
        128, 0},
       {"1x1 128->84 planar f32 46x46", CONV_1x1, 2, 46, 46, 128, 96, 84, 96, EPI_PLANAR_F32, false, false, 0, 0},

@@ -309,20 +309,54 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
   return VNECT_OK;
 }
 
+// Last conv of a projection block with the shortcut folded in (vnect_model.py:32-41, 64-73, 106-115, 168-177):
+//   relu(W_2c * b + bias_2c + W_1 * x + bias_1) == relu([W_2c | W_1] * [b ; x] + (bias_2c + bias_1))
+// one GEMM whose K runs over the 3x3's output and then over the block input; the branch1 tensor never exists.
+static int add_proj_tail(vnect_t* h, const std::string& scope2c, const std::string& scope1, const std::string& in_b,
+                         const std::string& in_x, const std::string& out, int mid, int cin, int cout) {
+  const Act& ab = h->acts.at(in_b);
+  const Act& ax = h->acts.at(in_x);
+  if (ab.H != ax.H || ab.W != ax.W || ab.C != mid || ax.C != cin)
+    return fail(h, VNECT_E_INVALID, "projection fold shape mismatch at %s", scope2c.c_str());
+  const HostVar& w2 = h->vars.at(scope2c + "/weights");
+  const HostVar& w1 = h->vars.at(scope1 + "/weights");
+  const HostVar& b2 = h->vars.at(scope2c + "/biases");
+  const HostVar& b1 = h->vars.at(scope1 + "/biases");
+  const int K = mid + cin;
+  std::vector<float> w((size_t)cout * K), bias(cout);
+  for (int co = 0; co < cout; ++co) {
+    for (int ci = 0; ci < mid; ++ci) w[(size_t)co * K + ci] = w2.data[(size_t)ci * cout + co];
+    for (int ci = 0; ci < cin; ++ci) w[(size_t)co * K + mid + ci] = w1.data[(size_t)ci * cout + co];
+    bias[co] = b2.data[co] + b1.data[co];
+  }
+  __half* dw = nullptr;
+  float* db = nullptr;
+  int rc = upload(h, to_half(w), &dw);
+  if (rc) return rc;
+  if ((rc = upload(h, bias, &db))) return rc;
+  if ((rc = new_act(h, out, ab.H, ab.W, cout))) return rc;
+  ConvSpec s;
+  s.kind = CONV_1x1;
+  s.NB = h->cap_fw; s.H = ab.H; s.W = ab.W;
+  s.in = ab.p; s.cin_pad = mid; s.in2 = ax.p; s.cin2_pad = cin;
+  s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout);
+  s.bias = db; s.relu_cols = cout;
+  s.out = h->acts.at(out).p; s.ldc = cout; s.epi = EPI_TMA;
+  Step st;
+  st.kind = 0; st.name = scope2c + "+" + scope1;
+  std::string err;
+  if (!build_conv(s, h->num_sms, &st.launch, &err)) return fail(h, VNECT_E_CUDA, "%s: %s", st.name.c_str(), err.c_str());
+  h->steps.push_back(st);
+  return VNECT_OK;
+}
+
 // bottleneck block (reference: src/vnect_model.py:31-177); `a_override` replaces the 3x3's input (the res2c wiring,
 // :56).  even_only: the block's output feeds nothing but stride-2 1x1 convs (res2c -> res3a, res3d -> res4a), so
 // the 3x3, the last 1x1 and the residual add are evaluated at even pixels only -- same values, a quarter of the work.
 static int add_block(vnect_t* h, const std::string& pre, const std::string& in, int cin, int mid, int cout, bool proj,
                      const std::string& suf, bool even_only, const std::string& a_override = "") {
   int rc;
-  ConvOpts lin; lin.relu = false;
   ConvOpts relu;
-  std::string shortcut = in;
-  if (proj) {
-    rc = add_conv(h, pre + "_branch1" + suf, 1, in, pre + "_branch1" + suf, cin, cout, lin);
-    if (rc) return rc;
-    shortcut = pre + "_branch1" + suf;
-  }
   std::string a = a_override;
   if (a.empty()) {
     a = pre + "_branch2a" + suf;
@@ -332,7 +366,9 @@ static int add_block(vnect_t* h, const std::string& pre, const std::string& in, 
   ConvOpts mid3; mid3.in_stride = even_only ? 2 : 1;
   rc = add_conv(h, pre + "_branch2b" + suf, 3, a, pre + "_branch2b" + suf, mid, mid, mid3);
   if (rc) return rc;
-  ConvOpts last; last.relu = true; last.residual = shortcut; last.res_stride = even_only ? 2 : 1;
+  if (proj)
+    return add_proj_tail(h, pre + "_branch2c" + suf, pre + "_branch1" + suf, pre + "_branch2b" + suf, in, pre, mid, cin, cout);
+  ConvOpts last; last.relu = true; last.residual = in; last.res_stride = even_only ? 2 : 1;
   return add_conv(h, pre + "_branch2c" + suf, 1, pre + "_branch2b" + suf, pre, mid, cout, last);
 }
 
