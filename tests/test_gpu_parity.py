@@ -85,7 +85,7 @@ def test_preprocess_noncontiguous_crop(engine_w1):
 
 
 # ------------------------------------------------------------------------------------------------ CNN forward
-LAYER_TAPS = ["conv1", "pool1", "res2a_branch2a", "res2a_branch2b", "res2a", "res2b", "res2c", "res3a", "res3d",
+LAYER_TAPS = ["pool1", "res2a_branch2a", "res2a_branch2b", "res2a", "res2b", "res2c", "res3a", "res3d",
               "res4a", "res4f", "res5a", "res5b_branch2c_new", "res5c_branch2a_feat", "res5c_branch2b"]
 
 
@@ -276,7 +276,7 @@ def test_full_size_batch_properties(w0):
         a2, a3 = eng.estimate(frames[:32], ids[:32], np.full(32, 1.0), np.full(32, 1.004))
         b2, b3 = eng.estimate(frames[32:], ids[32:], np.full(32, 1.0), np.full(32, 1.004))
         assert np.array_equal(np.concatenate([a2, b2]), j2) and np.array_equal(np.concatenate([a3, b3]), j3)
-        assert eng.launch_count() > 150
+        assert eng.launch_count() > 100
     finally:
         eng.close()
 

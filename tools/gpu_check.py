@@ -45,7 +45,7 @@ def main():
         x = np.stack([prepost.gen_input_batch(synth.frame_c2(i), 368, [1.0])[0][0] for i in range(2)])
         outs = eng.forward(x)
         (rhm, rxm, rym, rzm), taps = net(x, want_taps=True)
-        order = ["conv1", "pool1", "res2a_branch2a", "res2a_branch2b", "res2a", "res2b_branch2a", "res2b", "res2c",
+        order = ["pool1", "res2a_branch2a", "res2a_branch2b", "res2a", "res2b_branch2a", "res2b", "res2c",
                  "res3a", "res3b", "res3c", "res3d", "res4a", "res4b", "res4f", "res5a", "res5b_branch2c_new",
                  "res5c_branch2a_feat", "res5c_branch2b"]
         for name in order:

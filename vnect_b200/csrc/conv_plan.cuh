@@ -9,6 +9,7 @@
 
 #include "conv_gemm.cuh"
 #include "stem_gemm.cuh"
+#include "stem_pool.cuh"
 
 namespace vnect {
 
@@ -394,6 +395,57 @@ inline cudaError_t launch_stem(const StemLaunch& L, cudaStream_t st) {
     attr_set = true;
   }
   stem_gemm_kernel<<<L.grid, kGemmThreads, StemSmem::BYTES, st>>>(L.tmap_out, L.p);
+  return cudaGetLastError();
+}
+
+// conv1 + pool1 fused (stem_pool.cuh)
+struct StemPoolLaunch {
+  StemPoolParams p;
+  int grid = 0;
+};
+
+inline bool build_stem_pool(const __half* x1, int S, int rows_per_parity, int row_pitch, const __half* w_canonical,
+                            const float* bias, __half* pooled_out, int nb, int num_sms, StemPoolLaunch* L,
+                            std::string* err) {
+  memset(L, 0, sizeof(*L));
+  StemPoolParams& p = L->p;
+  p.vw = S / 2 + 3;
+  if (row_pitch * 2 != p.vw * 16 || S % 16 != 0) {
+    if (err) *err = "stem row pitch must be (S/2+3)*16 bytes and S a multiple of 16";
+    return false;
+  }
+  p.x1 = reinterpret_cast<const uint8_t*>(x1);
+  p.plane_bytes = (int64_t)rows_per_parity * row_pitch * 2;
+  p.w = reinterpret_cast<const uint8_t*>(w_canonical);
+  p.bias = bias;
+  p.out = pooled_out;
+  p.CH = p.CW = S / 2;
+  p.PH = p.PW = S / 4;
+  p.ppb = (5 * p.vw <= kBandTiles * kBlockM) ? 2 : 1;
+  p.band_tiles = ((2 * p.ppb + 1) * p.vw + kBlockM - 1) / kBlockM;
+  if (p.band_tiles > kBandTiles) {
+    if (err) *err = "box size too large for the fused stem";
+    return false;
+  }
+  p.bands_per_image = p.PH / p.ppb;
+  p.num_items = nb * p.bands_per_image;
+  L->grid = p.num_items < num_sms ? p.num_items : num_sms;
+  return true;
+}
+
+inline void stem_pool_set_batch(StemPoolLaunch& L, int nb, int num_sms) {
+  L.p.num_items = nb * L.p.bands_per_image;
+  L.grid = L.p.num_items < num_sms ? L.p.num_items : num_sms;
+}
+
+inline cudaError_t launch_stem_pool(const StemPoolLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemPoolSmem::BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  stem_pool_kernel<<<L.grid, kStemPoolThreads, StemPoolSmem::BYTES, st>>>(L.p);
   return cudaGetLastError();
 }
 

@@ -349,6 +349,95 @@ static int run_stem2(int NB, int S, int num_sms) {
   return bad == 0 ? 0 : 1;
 }
 
+// fused conv1 + pool1 against naive conv + host max-pool
+static int run_stem_pool(int NB, int S, int num_sms) {
+  const int OH = S / 2, PH = S / 4, vw = OH + 3, rpp = OH + 3, pitch = vw * 8;
+  const size_t in_elems = (size_t)NB * 2 * rpp * pitch + 8192;
+  std::vector<__half> h_in(in_elems), h_w((size_t)64 * 224), h_wc((size_t)64 * 224);
+  for (auto& v : h_in) v = __float2half(frand());
+  for (auto& v : h_w) v = __float2half(frand() * 0.15f);
+  pack_stem_canonical(h_w.data(), h_wc.data());
+  std::vector<float> h_bias(64);
+  for (auto& v : h_bias) v = frand() * 0.5f;
+  __half *d_in, *d_w, *d_wc, *d_out;
+  float *d_bias, *d_acc;
+  CK(cudaMalloc(&d_in, in_elems * 2));
+  CK(cudaMalloc(&d_w, h_w.size() * 2));
+  CK(cudaMalloc(&d_wc, h_wc.size() * 2));
+  CK(cudaMalloc(&d_bias, 64 * 4));
+  CK(cudaMemcpy(d_in, h_in.data(), in_elems * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_w, h_w.data(), h_w.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_wc, h_wc.data(), h_wc.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_bias, h_bias.data(), 64 * 4, cudaMemcpyHostToDevice));
+  const size_t out_elems = (size_t)NB * PH * PH * 64;
+  CK(cudaMalloc(&d_out, out_elems * 2));
+  CK(cudaMemset(d_out, 0xff, out_elems * 2));
+  StemPoolLaunch L;
+  std::string err;
+  if (!build_stem_pool(d_in, S, rpp, pitch, d_wc, d_bias, d_out, NB, num_sms, &L, &err)) {
+    printf("[stem_pool] build FAILED: %s\n", err.c_str());
+    return 1;
+  }
+  CK(launch_stem_pool(L, 0));
+  cudaError_t se = cudaDeviceSynchronize();
+  if (se != cudaSuccess) {
+    printf("[stem_pool] kernel FAILED: %s\n", cudaGetErrorString(se));
+    exit(3);
+  }
+  NaiveGeom g;
+  memset(&g, 0, sizeof g);
+  g.kind = CONV_STEM7; g.NB = NB; g.H = OH; g.W = OH; g.n_pad = 64; g.taps = 7; g.phases = 1;
+  g.k_total = 224; g.stem_rpp = rpp; g.stem_pitch = pitch; g.in_stride = 1;
+  for (int ky = 0; ky < 7; ++ky) { g.dy[ky] = (signed char)(ky >> 1); g.dx[ky] = 0; g.dp[ky] = (signed char)(ky & 1); }
+  const size_t acc_elems = (size_t)NB * OH * OH * 64;
+  CK(cudaMalloc(&d_acc, acc_elems * 4));
+  naive_acc_kernel<<<1184, 256>>>(d_in, d_w, d_acc, g);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> h_acc(acc_elems);
+  std::vector<__half> h_out(out_elems);
+  CK(cudaMemcpy(h_acc.data(), d_acc, acc_elems * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h_out.data(), d_out, out_elems * 2, cudaMemcpyDeviceToHost));
+  long long bad = 0, checked = 0;
+  double max_err = 0;
+  for (int n = 0; n < NB; ++n)
+    for (int py = 0; py < PH; ++py)
+      for (int px = 0; px < PH; ++px)
+        for (int c = 0; c < 64; ++c) {
+          float exp = -1e30f;
+          for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+              const int y = 2 * py + a, x = 2 * px + b;
+              if (y >= OH || x >= OH) continue;
+              exp = fmaxf(exp, fmaxf(h_acc[(((size_t)n * OH + y) * OH + x) * 64 + c] + h_bias[c], 0.f));
+            }
+          const float got = __half2float(h_out[(((size_t)n * PH + py) * PH + px) * 64 + c]);
+          const float e = fabsf(got - exp);
+          if (!(e <= 3e-3f * fabsf(exp) + 3e-3f)) {
+            if (bad < 5) printf("   mismatch n%d py%d px%d c%d got %f exp %f\n", n, py, px, c, got, exp);
+            ++bad;
+          }
+          if (e > max_err) max_err = e;
+          ++checked;
+        }
+  printf("[stem_pool fused conv1+pool1 S=%d nb=%d] items=%d grid=%d ppb=%d tiles/band=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n",
+         S, NB, L.p.num_items, L.grid, L.p.ppb, L.p.band_tiles, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
+  if (bad == 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CK(launch_stem_pool(L, 0));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 20; ++i) CK(launch_stem_pool(L, 0));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("   timing: %.2f us/launch\n", ms * 1000.0 / 20);
+  }
+  cudaFree(d_in); cudaFree(d_w); cudaFree(d_wc); cudaFree(d_bias); cudaFree(d_out); cudaFree(d_acc);
+  return bad == 0 ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   int dev = 0;
   cudaDeviceProp prop;
@@ -389,8 +478,13 @@ int main(int argc, char** argv) {
   for (const auto& c : cases) fails += run_case(c, sms, true);
   fails += run_stem2(2, 368, sms);
   fails += run_stem2(1, 448, sms);
+  fails += run_stem_pool(2, 368, sms);
+  fails += run_stem_pool(2, 448, sms);
+  fails += run_stem_pool(1, 64, sms);
   if (big) {
     fails += run_stem2(32, 368, sms);
+    fails += run_stem_pool(32, 368, sms);
+    fails += run_stem_pool(128, 368, sms);
     std::vector<Case> bigc = {
         {"BIG 1x1 1024->1024 23x23 nb128", CONV_1x1, 128, 23, 23, 1024, 1024, 1024, 256, EPI_NHWC_F16, true, false,
          1024, 0},

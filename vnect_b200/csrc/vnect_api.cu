@@ -23,10 +23,11 @@ struct Act {
 };
 
 struct Step {
-  int kind = 0;  // 0 = conv GEMM, 1 = maxpool, 2 = stem (conv1)
+  int kind = 0;  // 0 = conv GEMM, 1 = maxpool, 2 = stem (conv1), 3 = fused conv1 + pool1
   std::string name;
   ConvLaunch launch;
   StemLaunch stem;
+  StemPoolLaunch stem_pool;
   int tiles_per_image = 0;  // spatial
   // pool
   const __half* pin = nullptr;
@@ -438,7 +439,7 @@ static int alloc_prepost(vnect_t* h) {
   h->stem_rpp = S / 2 + 3;
   h->stem_pitch = (S + 6) * 4;
   // + slack: the last strip of the last image reads a few KB past its parity plane (stem_gemm.cuh)
-  if ((rc = dev_alloc(h, &h->x1, (size_t)nb * 2 * h->stem_rpp * h->stem_pitch + 8192, true))) return rc;
+  if ((rc = dev_alloc(h, &h->x1, (size_t)nb * 2 * h->stem_rpp * h->stem_pitch + 16384, true))) return rc;
   if ((rc = dev_alloc(h, &h->maps, (size_t)nb * 84 * h->hs * h->hs, true))) return rc;
   const int mf = h->cfg.max_frames, ms = h->cfg.max_streams;
   h->d_frames_bytes = (size_t)mf * h->cfg.max_input_h * h->cfg.max_input_w * 3;
@@ -552,35 +553,19 @@ int vnect_finalize(vnect_t* h) {
 
   const int S = h->S, nb = h->cap_fw;
   int rc;
-  {  // conv1 (vnect_model.py:27): raw-strip implicit GEMM, weights resident in smem (stem_gemm.cuh)
+  {  // conv1 + pool1 (vnect_model.py:27-29) fused: raw-strip implicit GEMM, smem band, max-pool (stem_pool.cuh)
     std::vector<__half> wk = to_half(pack_stem(h->vars.at("conv1/weights"))), wc(wk.size());
     pack_stem_canonical(wk.data(), wc.data());
     __half* dw = nullptr;
     float* db = nullptr;
     if ((rc = upload(h, wc, &dw))) return rc;
     if ((rc = upload(h, h->vars.at("conv1/biases").data, &db))) return rc;
-    Act a;
-    a.H = S / 2; a.W = S / 2; a.C = 64; a.row_px = S / 2 + 3;
-    a.img_px = (int64_t)((a.H * a.row_px + kBlockM - 1) / kBlockM) * kBlockM;
-    // conv1's output is consumed only by pool1; both run over chunks of kStemChunk images through this buffer
-    const int ring = nb < kStemChunk ? nb : kStemChunk;
-    if ((rc = dev_alloc(h, &a.p, (size_t)ring * a.img_px * 64, true))) return rc;
-    h->acts["conv1"] = a;
+    if ((rc = new_act(h, "pool1", S / 4, S / 4, 64))) return rc;
     Step st;
-    st.kind = 2; st.name = "conv1";
+    st.kind = 3; st.name = "conv1+pool1";
     std::string err;
-    if (!build_stem(h->x1, S, h->stem_rpp, h->stem_pitch, dw, db, a.p, ring, h->num_sms, &st.stem, &err))
-      return fail(h, VNECT_E_CUDA, "conv1: %s", err.c_str());
-    h->steps.push_back(st);
-  }
-  {  // pool1 (vnect_model.py:29)
-    rc = new_act(h, "pool1", S / 4, S / 4, 64);
-    if (rc) return rc;
-    Step st;
-    st.kind = 1; st.name = "pool1";
-    st.pin = h->acts.at("conv1").p; st.pout = h->acts.at("pool1").p;
-    st.H = S / 2; st.W = S / 2; st.C = 64; st.OH = S / 4; st.OW = S / 4;
-    st.in_row_px = h->acts.at("conv1").row_px; st.in_img_px = h->acts.at("conv1").img_px;
+    if (!build_stem_pool(h->x1, S, h->stem_rpp, h->stem_pitch, dw, db, h->acts.at("pool1").p, nb, h->num_sms, &st.stem_pool, &err))
+      return fail(h, VNECT_E_CUDA, "conv1+pool1: %s", err.c_str());
     h->steps.push_back(st);
   }
   if ((rc = add_block(h, "res2a", "pool1", 64, 64, 256, true, "", false))) return rc;
@@ -669,6 +654,9 @@ static int run_forward(vnect_t* h, int n, cudaEvent_t* layer_events = nullptr) {
     if (st.kind == 0) {
       set_batch(st.launch, n, h->num_sms);
       CU(h, launch_conv(st.launch, h->stream));
+    } else if (st.kind == 3) {
+      stem_pool_set_batch(st.stem_pool, n, h->num_sms);
+      CU(h, launch_stem_pool(st.stem_pool, h->stream));
     } else if (st.kind == 2) {
       // conv1 + pool1 chunk by chunk (the next step, pool1, is executed here too and skipped below)
       Step& pool = *(&st + 1);
@@ -1050,6 +1038,7 @@ double vnect_info(vnect_t* h, const char* key) {
     for (const Step& st : h->steps)
       if (st.kind == 0) f += st.launch.flops / h->cap_fw;
       else if (st.kind == 2) f += 2.0 * st.stem.p.tiles_per_image * kBlockM * 64 * 224;
+      else if (st.kind == 3) f += 2.0 * st.stem_pool.p.bands_per_image * st.stem_pool.p.band_tiles * kBlockM * 64 * 224;
     return f;
   }
   if (k == "hm_size") return h->hs;
