@@ -94,6 +94,13 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// fp32 pair -> packed fp16 with ReLU folded into the conversion (lo = a, hi = b)
+__device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+
 template <int BLOCK_N, int SWZ, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -150,9 +157,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int total_tiles = p.phases * p.num_m_tiles * p.num_n_tiles;
   const int k_iters = p.taps * p.cblocks + p.cblocks2;
 
+  // NOTE on the single-lane roles below: the whole warp runs each loop converged and only the issuing instructions are
+  // predicated on one elected lane.  Loop state then stays warp-uniform, so ptxas keeps descriptors, coordinates and
+  // barrier addresses in uniform registers; with the loop inside `if (elect_one())` every UTMALDG / UTCHMMA needed
+  // ~7 R2UR moves and the issue rate, not the tensor pipe, bounded small-N layers.
   if (warp == 0) {
     // ================================================================ TMA producer
-    if (elect_one()) {
+    const bool issuer = elect_one();
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -178,10 +190,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int ax = cx * p.in_stride + p.tap_dx[ti], ay = cy * p.in_stride + p.tap_dy[ti], ap = p.tap_dp[ti];
           for (int cb = 0; cb < p.cblocks; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
-            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            tma_load_5d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
-            tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
+            if (issuer) {
+              mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
+              uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+              tma_load_5d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
+              tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
+            }
+            __syncwarp();
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -190,10 +205,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int cb = 0; cb < p.cblocks2; ++cb) {  // folded projection shortcut: second A tensor, 1x1
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          tma_load_5d(sa, &tmap_a2, &full_bar[stage], cb * BLOCK_K, cx, cy, 0, cn);
-          tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (p.taps * p.cblocks + cb) * BLOCK_K, b_row);
+          if (issuer) {
+            mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            tma_load_5d(sa, &tmap_a2, &full_bar[stage], cb * BLOCK_K, cx, cy, 0, cn);
+            tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (p.taps * p.cblocks + cb) * BLOCK_K, b_row);
+          }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -202,8 +220,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer (single thread)
-    if (elect_one()) {
+    // ================================================================ MMA issuer (one elected lane issues)
+    const bool issuer = elect_one();
+    {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -216,19 +235,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint64_t a_desc = make_kmajor_desc<SWZ>(a_addr);
+          const uint64_t b_desc = make_kmajor_desc<SWZ>(a_addr + Cfg::A_BYTES);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            umma_f16(d_tmem, make_kmajor_desc<SWZ>(a_addr + k * 32), make_kmajor_desc<SWZ>(b_addr + k * 32), IDESC,
-                     (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k)  // +32 B per K step = +2 in the descriptor's (addr >> 4) field
+              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (issuer) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -236,7 +258,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 3) {
     // ================================================================ residual prefetcher (EPI_TMA_RES only)
     if constexpr (EPI == EPI_TMA_RES) {
-      if (elect_one()) {
+      const bool issuer = elect_one();
+      {
         uint32_t ctr = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
           const int n_tile = tile % p.num_n_tiles;
@@ -254,9 +277,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int c0 = 0; c0 < BLOCK_N; c0 += 64, ++ctr) {
             const int rb = ctr % kResStages;
             mbar_wait(&res_empty[rb], ((ctr / kResStages) & 1) ^ 1);
-            mbar_arrive_expect_tx(&res_full[rb], p.res_tx_bytes);
-            tma_load_5d(res_stage + rb * kEpiChunkBytes, &tmap_res, &res_full[rb], n_tile * BLOCK_N + c0,
-                        cx * p.res_stride, cy * p.res_stride, 0, cn);
+            if (issuer) {
+              mbar_arrive_expect_tx(&res_full[rb], p.res_tx_bytes);
+              tma_load_5d(res_stage + rb * kEpiChunkBytes, &tmap_res, &res_full[rb], n_tile * BLOCK_N + c0,
+                          cx * p.res_stride, cy * p.res_stride, 0, cn);
+            }
+            __syncwarp();
           }
         }
       }

@@ -378,6 +378,10 @@ static int run_stem_pool(int NB, int S, int num_sms) {
     printf("[stem_pool] build FAILED: %s\n", err.c_str());
     return 1;
   }
+  unsigned long long* d_dbg;
+  CK(cudaMalloc(&d_dbg, 4 * sizeof(unsigned long long)));
+  CK(cudaMemset(d_dbg, 0, 4 * sizeof(unsigned long long)));
+  L.p.dbg = d_dbg;
   CK(launch_stem_pool(L, 0));
   cudaError_t se = cudaDeviceSynchronize();
   if (se != cudaSuccess) {
@@ -419,6 +423,14 @@ static int run_stem_pool(int NB, int S, int num_sms) {
           if (e > max_err) max_err = e;
           ++checked;
         }
+  {
+    unsigned long long h_dbg[4];
+    CK(cudaMemcpy(h_dbg, d_dbg, sizeof h_dbg, cudaMemcpyDeviceToHost));
+    const double items0 = (double)((L.p.num_items + L.grid - 1) / L.grid);
+    printf("   CTA0 epilogue cycles per band: wait-MMA %.0f, drain %.0f, barrier %.0f, pool %.0f\n", h_dbg[0] / items0,
+           h_dbg[1] / items0, h_dbg[2] / items0, h_dbg[3] / items0);
+    L.p.dbg = nullptr;
+  }
   printf("[stem_pool fused conv1+pool1 S=%d nb=%d] items=%d grid=%d ppb=%d tiles/band=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n",
          S, NB, L.p.num_items, L.grid, L.p.ppb, L.p.band_tiles, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
   if (bad == 0) {

@@ -34,6 +34,7 @@ struct StemPoolParams {
   int band_tiles;       // ceil((2*ppb+1) * vw / 128) <= 8
   int bands_per_image;  // PH / ppb
   int num_items;        // images * bands_per_image
+  unsigned long long* dbg;  // optional [4] cycle counters (selftest only): wait-for-MMA, drain, barrier, pool
 };
 
 struct StemPoolSmem {
@@ -84,9 +85,12 @@ __global__ void __launch_bounds__(kStemPoolThreads, 1) stem_pool_kernel(const __
 
   if (warp == 0) {
     // ================================================================ strip loader
-    if (elect_one()) {
-      mbar_arrive_expect_tx(w_bar, kStemWBytes);
-      bulk_load_1d(w_smem, p.w, kStemWBytes, w_bar);
+    const bool issuer = elect_one();
+    {
+      if (issuer) {
+        mbar_arrive_expect_tx(w_bar, kStemWBytes);
+        bulk_load_1d(w_smem, p.w, kStemWBytes, w_bar);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -97,9 +101,12 @@ __global__ void __launch_bounds__(kStemPoolThreads, 1) stem_pool_kernel(const __
         const uint32_t bytes = static_cast<uint32_t>(p.band_tiles * kBlockM * 16 + 64);
         for (int ky = 0; ky < 7; ++ky) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], bytes);
-          const uint8_t* src = img_base + (ky & 1) * p.plane_bytes + 16ll * (v_base + p.vw * (ky >> 1));
-          bulk_load_1d(strips + stage * kBandStripBytes, src, bytes, &full_bar[stage]);
+          if (issuer) {
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            const uint8_t* src = img_base + (ky & 1) * p.plane_bytes + 16ll * (v_base + p.vw * (ky >> 1));
+            bulk_load_1d(strips + stage * kBandStripBytes, src, bytes, &full_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == kBandStages) {
             stage = 0;
             phase ^= 1;
@@ -109,31 +116,35 @@ __global__ void __launch_bounds__(kStemPoolThreads, 1) stem_pool_kernel(const __
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer: TMEM slot t <-> tile t of the band
-    if (elect_one()) {
+    // (warp-converged loop, one elected lane issues: see the note in conv_gemm.cuh)
+    const bool issuer = elect_one();
+    {
       mbar_wait(w_bar, 0);
       int stage = 0;
       uint32_t phase = 0, item_par = 0;
-      const uint32_t w_addr = smem_u32(w_smem);
+      const uint64_t b_desc0 = make_noswz_desc(smem_u32(w_smem), 1024, 128);
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, item_par ^= 1) {
         for (int ky = 0; ky < 7; ++ky) {  // row tap outer, tile inner: all accumulators of the band are live in TMEM
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(strips + stage * kBandStripBytes);
+          const uint64_t a_desc0 = make_noswz_desc(smem_u32(strips + stage * kBandStripBytes), 16, 128);
+          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>(ky * 256);  // (ky*4 chunks * 1024 B) >> 4
           for (int t = 0; t < p.band_tiles; ++t) {
             if (ky == 0) {
               mbar_wait(&tmem_empty[t], item_par ^ 1);  // previous band's tile t has been drained
               tc_fence_after();
             }
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(t * 64);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const uint64_t ad = make_noswz_desc(a_base + t * (kBlockM * 16) + 32 * j, 16, 128);
-              const uint64_t bd = make_noswz_desc(w_addr + (ky * 4 + 2 * j) * 1024, 1024, 128);
-              umma_f16(d_tmem, ad, bd, IDESC, (ky | j) != 0 ? 1u : 0u);
+            if (issuer) {
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(t * 64);
+              const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(t * 128);  // (t * 2048 B) >> 4
+              umma_f16(d_tmem, a_desc, b_desc, IDESC, ky != 0 ? 1u : 0u);
+              umma_f16(d_tmem, a_desc + 2, b_desc + 128, IDESC, 1u);  // +32 B of A, +2 K-chunks (2048 B) of B
+              if (ky == 6) umma_commit(&tmem_full[t]);
             }
-            if (ky == 6) umma_commit(&tmem_full[t]);
+            __syncwarp();
           }
-          umma_commit(&empty_bar[stage]);
+          if (issuer) umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kBandStages) {
             stage = 0;
             phase ^= 1;
@@ -148,12 +159,22 @@ __global__ void __launch_bounds__(kStemPoolThreads, 1) stem_pool_kernel(const __
     const int chalf = ew >> 2;        // which 32 of the 64 output channels
     const int r = q4 * 32 + lane;     // row within a tile
     const int et = threadIdx.x - 128; // 0..255
+    float bias_r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias_r[i] = bias_s[chalf * 32 + i];
+    // pooling role of this thread: one 16-byte channel chunk, a run of consecutive pooled columns
+    const int pc = et & 7;
+    const int run = (p.PW + 31) / 32;
+    const int px_begin = (et >> 3) * run;
+    const int px_end = min(px_begin + run, p.PW);
     uint32_t item_par = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, item_par ^= 1) {
       const int img = item / p.bands_per_image;
       const int q = item - img * p.bands_per_image;
+      long long c0 = clock64(), c1 = 0;
       for (int t = 0; t < p.band_tiles; ++t) {
         mbar_wait(&tmem_full[t], item_par);
+        if (t == 0) c1 = clock64();
         tc_fence_after();
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + static_cast<uint32_t>(t * 64 + chalf * 32), v);
@@ -166,51 +187,64 @@ __global__ void __launch_bounds__(kStemPoolThreads, 1) stem_pool_kernel(const __
         const uint32_t sw = vrow & 7u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int ch = chalf * 32 + 8 * j;
-          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch);
-          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch + 4);
-          uint4 o;
-          o.x = pack_half2(fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f));
-          o.y = pack_half2(fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.f));
-          o.z = pack_half2(fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.f));
-          o.w = pack_half2(fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.f));
+          uint4 o;  // bias + ReLU + fp16 pack (cvt.rn.relu does the max(.,0) while packing)
+          o.x = pack_half2_relu(__uint_as_float(v[8 * j + 0]) + bias_r[8 * j + 0], __uint_as_float(v[8 * j + 1]) + bias_r[8 * j + 1]);
+          o.y = pack_half2_relu(__uint_as_float(v[8 * j + 2]) + bias_r[8 * j + 2], __uint_as_float(v[8 * j + 3]) + bias_r[8 * j + 3]);
+          o.z = pack_half2_relu(__uint_as_float(v[8 * j + 4]) + bias_r[8 * j + 4], __uint_as_float(v[8 * j + 5]) + bias_r[8 * j + 5]);
+          o.w = pack_half2_relu(__uint_as_float(v[8 * j + 6]) + bias_r[8 * j + 6], __uint_as_float(v[8 * j + 7]) + bias_r[8 * j + 7]);
           const uint32_t chunk = static_cast<uint32_t>(chalf * 4 + j);
           *reinterpret_cast<uint4*>(rowp + ((chunk ^ sw) << 4)) = o;
         }
       }
+      const long long c2 = clock64();
       named_bar_sync(1, 256);  // the whole band is in smem
-      // ---- 3x3/2 max-pool of band rows (TF SAME pads (0,1): windows are clipped at the bottom / right edge)
-      const int total = p.ppb * p.PW * 8;
-      for (int i = et; i < total; i += 256) {
-        const int c = i & 7;
-        const int px = (i >> 3) % p.PW;
-        const int pr = (i >> 3) / p.PW;  // pooled row within the band
+      const long long c3 = clock64();
+      // ---- 3x3/2 max-pool of band rows (TF SAME pads (0,1): windows are clipped at the bottom / right edge).
+      // Separable: vertical max of each conv column once, then the horizontal 3-max; the even column shared by two
+      // neighbouring windows is carried in registers.
+      for (int pr = 0; pr < p.ppb; ++pr) {
         const int py = p.ppb * q + pr;
-        __half2 m[4];
-        bool first = true;
+        const int nrows = min(3, p.CH - 2 * py);
+        const uint32_t row0 = static_cast<uint32_t>(2 * pr * p.vw);
+        auto vmax = [&](int cx, __half2 (&m)[4]) {
+          uint32_t vrow = row0 + static_cast<uint32_t>(cx);
+          uint4 val = *reinterpret_cast<const uint4*>(band + vrow * 128u + ((static_cast<uint32_t>(pc) ^ (vrow & 7u)) << 4));
+          const __half2* hv = reinterpret_cast<const __half2*>(&val);
+          m[0] = hv[0]; m[1] = hv[1]; m[2] = hv[2]; m[3] = hv[3];
+          for (int a = 1; a < nrows; ++a) {
+            vrow += static_cast<uint32_t>(p.vw);
+            val = *reinterpret_cast<const uint4*>(band + vrow * 128u + ((static_cast<uint32_t>(pc) ^ (vrow & 7u)) << 4));
+            m[0] = __hmax2(m[0], hv[0]); m[1] = __hmax2(m[1], hv[1]);
+            m[2] = __hmax2(m[2], hv[2]); m[3] = __hmax2(m[3], hv[3]);
+          }
+        };
+        if (px_begin < px_end) {
+          __half2 carry[4], c1[4], c2[4];
+          vmax(2 * px_begin, carry);
+          __half* o = p.out + ((static_cast<size_t>(img) * p.PH + py) * p.PW + px_begin) * 64 + pc * 8;
+          for (int px = px_begin; px < px_end; ++px, o += 64) {
+            vmax(2 * px + 1, c1);  // 2*px+1 <= CW-1 always
+            __half2 m[4];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-          const int cy = 2 * py + a;
-          if (cy >= p.CH) continue;
-          const int lr = cy - 2 * p.ppb * q;
+            for (int e = 0; e < 4; ++e) m[e] = __hmax2(carry[e], c1[e]);
+            if (2 * px + 2 < p.CW) {
+              vmax(2 * px + 2, c2);
 #pragma unroll
-          for (int b = 0; b < 3; ++b) {
-            const int cx = 2 * px + b;
-            if (cx >= p.CW) continue;
-            const uint32_t vrow = static_cast<uint32_t>(lr * p.vw + cx);
-            const uint4 val = *reinterpret_cast<const uint4*>(band + vrow * 128u + ((static_cast<uint32_t>(c) ^ (vrow & 7u)) << 4));
-            const __half2* hv = reinterpret_cast<const __half2*>(&val);
-            if (first) {
-              m[0] = hv[0]; m[1] = hv[1]; m[2] = hv[2]; m[3] = hv[3];
-              first = false;
-            } else {
-              m[0] = __hmax2(m[0], hv[0]); m[1] = __hmax2(m[1], hv[1]);
-              m[2] = __hmax2(m[2], hv[2]); m[3] = __hmax2(m[3], hv[3]);
+              for (int e = 0; e < 4; ++e) {
+                m[e] = __hmax2(m[e], c2[e]);
+                carry[e] = c2[e];
+              }
             }
+            *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(m);
           }
         }
-        __half* o = p.out + ((static_cast<size_t>(img) * p.PH + py) * p.PW + px) * 64 + c * 8;
-        *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(m);
+      }
+      if (p.dbg != nullptr && et == 0 && blockIdx.x == 0) {
+        const long long c4 = clock64();
+        atomicAdd(&p.dbg[0], (unsigned long long)(c1 - c0));
+        atomicAdd(&p.dbg[1], (unsigned long long)(c2 - c1));
+        atomicAdd(&p.dbg[2], (unsigned long long)(c3 - c2));
+        atomicAdd(&p.dbg[3], (unsigned long long)(c4 - c3));
       }
       named_bar_sync(1, 256);  // band may be overwritten by the next item
     }
