@@ -96,35 +96,60 @@ __global__ void squarify_kernel(const uint8_t* __restrict__ in, uint8_t* __restr
   }
 }
 
+constexpr int kMaxBox = 512;
+
+// Per pyramid scale: the OpenCV coordinate / fixed-point coefficient of every destination column and row, computed
+// once on the host with the same arithmetic as cv_linear_coord / cv_coef (the scales are fixed at vnect_create).
+struct PyramidTable {
+  short xi0[kMaxBox], xi1[kMaxBox], xa0[kMaxBox], xa1[kMaxBox];  // x axis: index clamp + f reset
+  short yj0[kMaxBox], yj1[kMaxBox], yb0[kMaxBox], yb1[kMaxBox];  // y axis: rows clamped, f kept
+};
+
 struct PyramidParams {
   int n_frames, S, n_scales;
   int64_t sq_pitch, sq_frame_stride;  // square u8 input (may alias the raw frames when they are already S x S)
   int R[kMaxScales];                  // resized side cvRound(S*s); == S for s >= 1 (identity)
   int pad0[kMaxScales];               // (S - R) / 2
   double inv_scale[kMaxScales];       // 1 / s
+  const PyramidTable* tables;         // [n_scales], device
   // stem layout: [forward][parity][rows_per_parity][row_pitch] halves, pixel (y, x) lives at padded (y+2, x+2)
   int rows_per_parity, row_pitch;
 };
 
 // estimator.gen_input_batch (estimator.py:70-81): per scale shrink + zero pad (utils.py:123-150), then
 // float32(u8)/255 - 0.4, stored as fp16 in the parity-split padded NHWC4 layout the stem conv's TMA reads.
-__global__ void pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restrict__ x1, PyramidParams p) {
-  const int64_t per_fwd = (int64_t)p.S * p.S;
-  const int64_t total = (int64_t)p.n_frames * p.n_scales * per_fwd;
+// grid.y = scale index (keeps the per-scale parameters uniform per block).
+__global__ void pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restrict__ x1,
+                               const __grid_constant__ PyramidParams p) {
+  const int si = blockIdx.y;
+  const int R = p.R[si], pad0 = p.pad0[si];
+  const PyramidTable* __restrict__ T = p.tables + si;
+  const int64_t per_img = (int64_t)p.S * p.S;
+  const int64_t total = (int64_t)p.n_frames * per_img;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % p.S);
     const int y = (int)((i / p.S) % p.S);
-    const int fwd = (int)(i / per_fwd);
-    const int frame = fwd / p.n_scales, si = fwd - frame * p.n_scales;
+    const int frame = (int)(i / per_img);
+    const int fwd = frame * p.n_scales + si;
     const uint8_t* src = sq + (int64_t)frame * p.sq_frame_stride;
     int v[3] = {0, 0, 0};
-    if (p.R[si] == p.S) {
+    if (R == p.S) {
       const uint8_t* q = src + (int64_t)y * p.sq_pitch + x * 3;
       v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
     } else {
-      const int ry = y - p.pad0[si], rx = x - p.pad0[si];
-      if (ry >= 0 && ry < p.R[si] && rx >= 0 && rx < p.R[si])
-        cv_resize_u8_px(src, p.sq_pitch, p.S, p.S, ry, rx, p.inv_scale[si], v);
+      const int ry = y - pad0, rx = x - pad0;
+      if (ry >= 0 && ry < R && rx >= 0 && rx < R) {
+        const int a0 = T->xa0[rx], a1 = T->xa1[rx], b0 = T->yb0[ry], b1 = T->yb1[ry];
+        const uint8_t* r0 = src + (int64_t)T->yj0[ry] * p.sq_pitch;
+        const uint8_t* r1 = src + (int64_t)T->yj1[ry] * p.sq_pitch;
+        const int o0 = T->xi0[rx] * 3, o1 = T->xi1[rx] * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int t0 = r0[o0 + c] * a0 + r0[o1 + c] * a1;
+          const int t1 = r1[o0 + c] * a0 + r1[o1 + c] * a1;
+          v[c] = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+        }
+      }
     }
     __half h[4];
 #pragma unroll

@@ -3,6 +3,8 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
+#include <tuple>
 #include <map>
 #include <set>
 #include <string>
@@ -66,6 +68,7 @@ struct vnect_handle {
   uint8_t* d_sq = nullptr;
   float* d_f32_in = nullptr;  // vnect_forward staging [cap_fw][S][S][3]
   ScaleTable* d_tables = nullptr;
+  PyramidTable* d_pyr_tables = nullptr;
   FilterState *d_st2d = nullptr, *d_st3d = nullptr;
   double* d_j2_box = nullptr;
   float* d_j3_raw = nullptr;
@@ -88,6 +91,16 @@ struct vnect_handle {
   Lane* cur = &lanes[0];
   cudaStream_t copy_stream = nullptr;
   unsigned device_calls = 0;
+  // CUDA graphs of the kernel sequence of one estimate call, keyed by everything baked into the kernel parameters.
+  // First use of a key runs directly (warm-up), the second captures, later ones replay: ~50 launches -> 1.
+  typedef std::tuple<int, int, int, int, long long, long long, const void*, const void*, const void*> GraphKey;
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+    bool unusable = false;
+  };
+  std::map<GraphKey, GraphEntry> graphs;
+  bool use_graphs = true;
   std::vector<double> last_t2d, last_t3d;  // host mirror of the filters' last timestamps (NaN = none yet)
   PyramidParams pyr{};
 };
@@ -472,12 +485,30 @@ static int alloc_prepost(vnect_t* h) {
   PyramidParams& py = h->pyr;
   py.S = S; py.n_scales = h->n_scales;
   py.rows_per_parity = h->stem_rpp; py.row_pitch = h->stem_pitch;
+  std::vector<PyramidTable> ptab(h->n_scales);
   for (int i = 0; i < h->n_scales; ++i) {
     const double sc = h->cfg.scales[i];
     py.R[i] = sc < 1.0 ? cv_round_host(S * sc) : S;  // estimator.py:77: only scales < 1 are resized
     py.pad0[i] = (S - py.R[i]) / 2;
     py.inv_scale[i] = 1.0 / sc;
+    memset(&ptab[i], 0, sizeof(PyramidTable));
+    for (int d = 0; d < py.R[i] && py.R[i] != S; ++d) {  // same arithmetic as cv_linear_coord / cv_coef on the device
+      int ix, iy;
+      float fx, fy;
+      host_linear_coord(d, py.inv_scale[i], S, true, &ix, &fx);
+      host_linear_coord(d, py.inv_scale[i], S, false, &iy, &fy);
+      ptab[i].xi0[d] = (short)ix;
+      ptab[i].xi1[d] = (short)std::min(ix + 1, S - 1);
+      ptab[i].xa0[d] = (short)std::nearbyint((1.f - fx) * 2048.f);
+      ptab[i].xa1[d] = (short)std::nearbyint(fx * 2048.f);
+      ptab[i].yj0[d] = (short)std::min(std::max(iy, 0), S - 1);
+      ptab[i].yj1[d] = (short)std::min(std::max(iy + 1, 0), S - 1);
+      ptab[i].yb0[d] = (short)std::nearbyint((1.f - fy) * 2048.f);
+      ptab[i].yb1[d] = (short)std::nearbyint(fy * 2048.f);
+    }
   }
+  if ((rc = upload(h, ptab, &h->d_pyr_tables))) return rc;
+  py.tables = h->d_pyr_tables;
   return VNECT_OK;
 }
 
@@ -494,7 +525,7 @@ int vnect_create(vnect_t** out, const vnect_config* cfg) {
   vnect_t* h = new vnect_handle();
   *out = h;  // returned even on failure so the caller can read the error, then destroy
   h->cfg = *cfg;
-  if (cfg->box_size < 64 || cfg->box_size % 16 != 0 || cfg->box_size / 8 > kMaxHm)
+  if (cfg->box_size < 64 || cfg->box_size % 16 != 0 || cfg->box_size / 8 > kMaxHm || cfg->box_size > kMaxBox)
     return fail(h, VNECT_E_INVALID, "box_size %d must be a multiple of 16 in [64, %d]", cfg->box_size, kMaxHm * 8);
   if (cfg->n_scales < 1 || cfg->n_scales > kMaxScales) return fail(h, VNECT_E_INVALID, "n_scales out of range");
   for (int i = 0; i < cfg->n_scales; ++i)
@@ -517,6 +548,7 @@ int vnect_create(vnect_t** out, const vnect_config* cfg) {
   h->num_sms = prop.multiProcessorCount;
   CU(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   h->own_stream = true;
+  h->use_graphs = getenv("VNECT_B200_NO_GRAPH") == nullptr;
   int rc = alloc_prepost(h);
   if (rc) return rc;
   return vnect_reset_stream(h, -1);
@@ -719,8 +751,8 @@ static int run_preprocess(vnect_t* h, const uint8_t* dev_bgr, int n_frames, int 
   }
   PyramidParams py = h->pyr;
   py.n_frames = n_frames; py.sq_pitch = sq_pitch; py.sq_frame_stride = sq_stride;
-  const int64_t total = (int64_t)n_frames * h->n_scales * S * S;
-  pyramid_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(sq, h->x1, py);
+  const int64_t total = (int64_t)n_frames * S * S;
+  pyramid_kernel<<<dim3(grid_for(total, 256, h->num_sms), h->n_scales), 256, 0, h->stream>>>(sq, h->x1, py);
   CU(h, cudaGetLastError());
   ++h->launches;
   return VNECT_OK;
@@ -821,6 +853,57 @@ int vnect_forward(vnect_t* h, const float* nhwc, int32_t n, float* hm, float* xm
   return VNECT_OK;
 }
 
+// pre-process -> CNN -> post-process for one batch, as a replayed CUDA graph when possible
+static int run_pipeline(vnect_t* h, int lane, const uint8_t* dev_bgr, int n_frames, int H, int W, int64_t pitch,
+                        int64_t frame_stride, double* out2d, float* out3d) {
+  const Geometry g = squarify_geometry(h->S, H, W);
+  auto direct = [&]() -> int {
+    int rc;
+    if ((rc = run_preprocess(h, dev_bgr, n_frames, H, W, pitch, frame_stride, g))) return rc;
+    if ((rc = run_forward(h, n_frames * h->n_scales))) return rc;
+    return run_postprocess(h, n_frames, g.scaler, g.off_x, g.off_y, out2d, out3d);
+  };
+  if (!h->use_graphs) return direct();
+  const vnect_handle::GraphKey key(lane, n_frames, H, W, (long long)pitch, (long long)frame_stride, dev_bgr, out2d, out3d);
+  auto it = h->graphs.find(key);
+  if (it == h->graphs.end()) {
+    h->graphs[key] = vnect_handle::GraphEntry();
+    return direct();  // warm-up run: sets function attributes, exercises every launch configuration
+  }
+  vnect_handle::GraphEntry& e = it->second;
+  if (e.unusable) return direct();
+  if (!e.exec) {
+    const long long before = h->launches;
+    if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      e.unusable = true;  // e.g. the legacy default stream cannot be captured
+      return direct();
+    }
+    const int rc = direct();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+    e.launches = h->launches - before;
+    h->launches = before;
+    if (rc != VNECT_OK || ce != cudaSuccess || graph == nullptr) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      e.unusable = true;
+      return rc != VNECT_OK ? rc : direct();
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&e.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      cudaGetLastError();
+      e.exec = nullptr;
+      e.unusable = true;
+      return direct();
+    }
+  }
+  CU(h, cudaGraphLaunch(e.exec, h->stream));
+  h->launches += e.launches;
+  return VNECT_OK;
+}
+
 int vnect_estimate_device(vnect_t* h, const uint8_t* dev_bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
                           int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d,
                           double* dev_joints2d, float* dev_joints3d) {
@@ -831,10 +914,8 @@ int vnect_estimate_device(vnect_t* h, const uint8_t* dev_bgr, int32_t n_frames, 
   int rc = lane_acquire(h, (int)(h->device_calls++ & 1));
   if (rc) return rc;
   if ((rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d, h->stream))) return rc;
-  const Geometry g = squarify_geometry(h->S, H, W);
-  if ((rc = run_preprocess(h, dev_bgr, n_frames, H, W, pitch, frame_stride, g))) return rc;
-  if ((rc = run_forward(h, n_frames * h->n_scales))) return rc;
-  if ((rc = run_postprocess(h, n_frames, g.scaler, g.off_x, g.off_y, dev_joints2d, dev_joints3d))) return rc;
+  const int lane = (int)(h->cur - h->lanes);
+  if ((rc = run_pipeline(h, lane, dev_bgr, n_frames, H, W, pitch, frame_stride, dev_joints2d, dev_joints3d))) return rc;
   CU(h, cudaEventRecord(h->cur->done, h->stream));
   h->cur->pending = true;
   return VNECT_OK;
@@ -863,10 +944,7 @@ int vnect_submit(vnect_t* h, int32_t lane, const uint8_t* bgr, int32_t n_frames,
   }
   CU(h, cudaEventRecord(h->cur->copy_done, h->copy_stream));
   CU(h, cudaStreamWaitEvent(h->stream, h->cur->copy_done, 0));
-  const Geometry g = squarify_geometry(h->S, H, W);
-  if ((rc = run_preprocess(h, h->cur->d_frames, n_frames, H, W, dpitch, dstride, g))) return rc;
-  if ((rc = run_forward(h, n_frames * h->n_scales))) return rc;
-  if ((rc = run_postprocess(h, n_frames, g.scaler, g.off_x, g.off_y, h->cur->d_out2d, h->cur->d_out3d))) return rc;
+  if ((rc = run_pipeline(h, lane, h->cur->d_frames, n_frames, H, W, dpitch, dstride, h->cur->d_out2d, h->cur->d_out3d))) return rc;
   CU(h, cudaMemcpyAsync(joints2d, h->cur->d_out2d, (size_t)n_frames * kJoints * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaMemcpyAsync(joints3d, h->cur->d_out3d, (size_t)n_frames * kJoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaEventRecord(h->cur->done, h->stream));
@@ -1087,6 +1165,8 @@ int vnect_time_forward(vnect_t* h, int32_t n, int32_t reps, float* total_ms, flo
 void vnect_destroy(vnect_t* h) {
   if (!h) return;
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& kv : h->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& L : h->lanes) {
     if (L.h_stream_ids) cudaFreeHost(L.h_stream_ids);
