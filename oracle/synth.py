@@ -42,7 +42,8 @@ def synthetic_maps(seed, n_scales, hs=46, border_joints=True):
             blob = np.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * (sig[j] * s) ** 2))
             maps[0][i, :, :, j] = (blob + 0.02 * rng.standard_normal((hs, hs))).astype(np.float32)
         for m in maps[1:]:
-            coarse = rng.uniform(-5, 5, size=(6, 6, JOINTS))
+            nc = -(-hs // 8)  # 6 for the 46 x 46 maps the committed fixtures were minted with
+            coarse = rng.uniform(-5, 5, size=(nc, nc, JOINTS))
             fine = np.kron(coarse, np.ones((8, 8, 1)))[:hs, :hs, :]
             m[i] = (fine + 0.05 * rng.standard_normal((hs, hs, JOINTS))).astype(np.float32)
     return tuple(maps)

@@ -353,3 +353,84 @@ def test_pipelined_submit_matches_estimate(engine_w0):
     engine_w0.wait(1)
     for (a2, a3), (b2, b3) in zip(want, got):
         assert np.array_equal(a2, b2) and np.array_equal(a3, b3)
+
+
+# ------------------------------------------------------------------------------------------------ other configs
+def test_box448_three_scales(w1):
+    """C5 geometry: 448 x 448 box, scales [1, 0.85, 0.7] (hm 56 x 56; the reference's placeholder is hard-wired to
+    368, vnect_model.py:22, so the oracle here is the CPU restatement at 448)."""
+    from vnect_b200 import VNectEngine
+    scales = [1, 0.85, 0.7]
+    net = OracleNet(w1)
+    eng = VNectEngine(w1, scales, box_size=448, max_frames=2, max_streams=2)
+    try:
+        frames = np.stack([np.random.default_rng(3000 + i).integers(0, 256, (448, 448, 3), dtype=np.uint8)
+                           for i in range(2)])
+        got, scaler, offs = eng.preprocess(frames)
+        for i in range(2):
+            ref, rs, ro = prepost.gen_input_batch(frames[i], 448, scales)
+            assert np.array_equal(got[3 * i:3 * i + 3], ref.astype(np.float16).astype(np.float32))
+        batch = got[:3]
+        outs = eng.forward(batch)
+        refs = net(batch)
+        for a, b in zip(outs, refs):
+            assert a.shape == (3, 56, 56, 21)
+            assert rel_l2(a, b) < 3e-3
+        j2, j3 = eng.estimate(frames, [0, 1], [2.0, 2.0], [2.01, 2.01])
+        for i in range(2):
+            clock = Clock()
+            clock.q = [2.0, 2.01]
+            ref = prepost.OracleEstimator(net, scales, clock=clock, box_size=448)
+            r2, r3 = ref(frames[i])
+            raw_gpu = np.rint(j2[i]).astype(int)
+            assert _assert_only_near_ties(raw_gpu, ref) <= 2
+            same = np.abs(j2[i] - r2).max(axis=1) < 1e-9
+            if same[14]:
+                assert np.abs(j3[i][same] - r3[same]).max() < 1.0
+    finally:
+        eng.close()
+
+
+def test_many_streams_over_time(engine_w0, oracle_net_w0):
+    """C4-style: several video streams advanced together for a few frames (filters live per stream) must equal the
+    same streams advanced one at a time (per-stream state never mixes, results independent of batch composition)."""
+    n_streams, n_steps = 6, 3
+    engine_w0.reset()
+    batched = []
+    for k in range(n_steps):
+        frames = np.stack([synth.stream_frame(s, k) for s in range(n_streams)])
+        batched.append(engine_w0.estimate(frames, np.arange(n_streams), np.full(n_streams, 1000 + k / 30),
+                                          np.full(n_streams, 1000 + k / 30 + 0.004)))
+    engine_w0.reset()
+    for s in range(n_streams):
+        for k in range(n_steps):
+            j2, j3 = engine_w0.estimate(synth.stream_frame(s, k), [s], [1000 + k / 30], [1000 + k / 30 + 0.004])
+            assert np.array_equal(j2[0], batched[k][0][s]) and np.array_equal(j3[0], batched[k][1][s])
+    # and one stream against the oracle, filters included
+    clock = Clock()
+    ref = prepost.OracleEstimator(oracle_net_w0, SCALES2, clock=clock)
+    bad = 0
+    for k in range(n_steps):
+        clock.q = [1000 + k / 30, 1000 + k / 30 + 0.004]
+        r2, r3 = ref(synth.stream_frame(2, k))
+        bad += _count_argmax_diffs(batched[k][0][2], r2)
+    assert bad <= 1
+
+
+def test_postprocess_box448_bit_exact():
+    from vnect_b200 import VNectEngine
+    scales = [1, 0.85, 0.7]
+    eng = VNectEngine(False, scales, box_size=448, max_frames=1, max_streams=1)
+    try:
+        clock = Clock()
+        cur = {}
+        ref = prepost.OracleEstimator(lambda b: cur["m"], scales, clock=clock, box_size=448)
+        for k in range(3):
+            cur["m"] = synth.synthetic_maps(900 + k, 3, hs=56, border_joints=(k != 1))
+            clock.q = [4.0 + 0.03 * k, 4.002 + 0.03 * k]
+            r2, r3 = ref(np.zeros((448, 448, 3), np.uint8))
+            j2, j3, raw = eng.postprocess(cur["m"], 1.0, (0, 0), [0], [4.0 + 0.03 * k], [4.002 + 0.03 * k])
+            assert np.array_equal(raw[0], ref.last["joints_2d_raw"].astype(np.int32))
+            assert np.array_equal(j2[0], r2) and np.array_equal(j3[0], r3)
+    finally:
+        eng.close()

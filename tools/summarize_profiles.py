@@ -1,0 +1,73 @@
+#!/usr/bin/env python3
+"""Turn gpurun_out/{launches.csv, prof_*.ncu-rep} into small text summaries under profiles/ (run in the dev container:
+ncu can read reports without a GPU).   python tools/summarize_profiles.py r01"""
+import csv
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "rXX"
+out_dir = os.path.join(ROOT, "profiles")
+
+METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+]
+
+
+def launches():
+    path = os.path.join(ROOT, "gpurun_out", "launches.csv")
+    if not os.path.isfile(path):
+        return
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    lines, total, agg = [], 0.0, {}
+    for r in rows:
+        name = r[4].split("(")[0].replace("void ", "").replace("vnect::", "")
+        t = float(r[-1])
+        t = t / 1000 if r[-2] in ("ns", "nsecond") else t * 1000 if r[-2] in ("ms", "msecond") else t
+        total += t
+        agg.setdefault(name, [0.0, 0])
+        agg[name][0] += t
+        agg[name][1] += 1
+        lines.append(f"{int(r[0]):4d} {t:9.1f} us  block {r[7]:>14s} grid {r[8]:>14s}  {name}")
+    with open(os.path.join(out_dir, f"{tag}_ncu_launches.txt"), "w") as f:
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: every launch of ONE bench step\n"
+                "# (64 frames, 2 scales = 128 forwards; cold-cache, serialised: compare shares, not absolutes)\n")
+        f.write(f"# total {total:.1f} us over {len(rows)} launches\n\n## by kernel\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            f.write(f"{v[0]:9.1f} us {v[1]:3d}x {100 * v[0] / total:5.1f}%  {k}\n")
+        f.write("\n## in launch order\n" + "\n".join(lines) + "\n")
+    print("wrote launches:", total, "us")
+
+
+def full(rep, label):
+    path = os.path.join(ROOT, "gpurun_out", rep)
+    if not os.path.isfile(path):
+        return
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {m: hdr.index(m) for m in METRICS if m in hdr}
+    kn = hdr.index("Kernel Name")
+    with open(os.path.join(out_dir, f"{tag}_ncu_full_{label}.txt"), "w") as f:
+        f.write(f"# ncu --set full --clock-control none --import-source on ({rep}); one block per captured launch\n")
+        for r in rows[2:]:
+            f.write("\n" + r[kn].replace("CUtensorMap_st, ", "")[:110] + "\n")
+            for m, i in idx.items():
+                f.write(f"    {m:75s} {r[i]:>16s} {units[i]}\n")
+            rd, wr = float(r[idx["dram__bytes_read.sum"]]), float(r[idx["dram__bytes_write.sum"]])
+            u = units[idx["dram__bytes_read.sum"]]
+            f.write(f"    {'traffic = dram read + write':75s} {rd + wr:16.3f} {u}\n")
+    print("wrote", label, len(rows) - 2, "kernels")
+
+
+launches()
+full("prof_conv.ncu-rep", "conv")
+full("prof_prepost.ncu-rep", "prepost")

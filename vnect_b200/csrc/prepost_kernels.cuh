@@ -118,30 +118,38 @@ struct PyramidParams {
 
 // estimator.gen_input_batch (estimator.py:70-81): per scale shrink + zero pad (utils.py:123-150), then
 // float32(u8)/255 - 0.4, stored as fp16 in the parity-split padded NHWC4 layout the stem conv's TMA reads.
-// grid.y = scale index (keeps the per-scale parameters uniform per block).
-__global__ void pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restrict__ x1,
-                               const __grid_constant__ PyramidParams p) {
-  const int si = blockIdx.y;
+// grid = (S rows, n_frames * n_scales forwards): one block per output row, so there is no per-pixel index division
+// (the first version spent ~230 instructions per pixel, mostly 64-bit div/mod, and was issue-bound at 140 us/batch).
+__global__ void __launch_bounds__(128) pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restrict__ x1,
+                                                      const __grid_constant__ PyramidParams p) {
+  const int y = blockIdx.x;
+  const int fwd = blockIdx.y;
+  const int frame = fwd / p.n_scales, si = fwd - frame * p.n_scales;
   const int R = p.R[si], pad0 = p.pad0[si];
   const PyramidTable* __restrict__ T = p.tables + si;
-  const int64_t per_img = (int64_t)p.S * p.S;
-  const int64_t total = (int64_t)p.n_frames * per_img;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int x = (int)(i % p.S);
-    const int y = (int)((i / p.S) % p.S);
-    const int frame = (int)(i / per_img);
-    const int fwd = frame * p.n_scales + si;
-    const uint8_t* src = sq + (int64_t)frame * p.sq_frame_stride;
+  const uint8_t* src = sq + (int64_t)frame * p.sq_frame_stride;
+  const int pr = y + 2;
+  __half* orow = x1 + (((int64_t)fwd * 2 + (pr & 1)) * p.rows_per_parity + (pr >> 1)) * p.row_pitch + 8;  // pc = x + 2
+  const bool identity = (R == p.S);
+  const int ry = y - pad0;
+  const bool row_in = identity || (ry >= 0 && ry < R);
+  int b0 = 0, b1 = 0;
+  const uint8_t *r0 = src + (int64_t)y * p.sq_pitch, *r1 = r0;
+  if (!identity && row_in) {
+    b0 = T->yb0[ry];
+    b1 = T->yb1[ry];
+    r0 = src + (int64_t)T->yj0[ry] * p.sq_pitch;
+    r1 = src + (int64_t)T->yj1[ry] * p.sq_pitch;
+  }
+  for (int x = threadIdx.x; x < p.S; x += blockDim.x) {
     int v[3] = {0, 0, 0};
-    if (R == p.S) {
-      const uint8_t* q = src + (int64_t)y * p.sq_pitch + x * 3;
+    if (identity) {
+      const uint8_t* q = r0 + x * 3;
       v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
     } else {
-      const int ry = y - pad0, rx = x - pad0;
-      if (ry >= 0 && ry < R && rx >= 0 && rx < R) {
-        const int a0 = T->xa0[rx], a1 = T->xa1[rx], b0 = T->yb0[ry], b1 = T->yb1[ry];
-        const uint8_t* r0 = src + (int64_t)T->yj0[ry] * p.sq_pitch;
-        const uint8_t* r1 = src + (int64_t)T->yj1[ry] * p.sq_pitch;
+      const int rx = x - pad0;
+      if (row_in && rx >= 0 && rx < R) {
+        const int a0 = T->xa0[rx], a1 = T->xa1[rx];
         const int o0 = T->xi0[rx] * 3, o1 = T->xi1[rx] * 3;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -155,9 +163,7 @@ __global__ void pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restric
 #pragma unroll
     for (int c = 0; c < 3; ++c) h[c] = __float2half_rn(__fsub_rn(__fdiv_rn((float)v[c], 255.f), 0.4f));
     h[3] = __float2half_rn(0.f);
-    const int pr = y + 2, pc = x + 2;
-    __half* o = x1 + (((int64_t)fwd * 2 + (pr & 1)) * p.rows_per_parity + (pr >> 1)) * p.row_pitch + pc * 4;
-    *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(orow + x * 4) = *reinterpret_cast<const uint2*>(h);
   }
 }
 
@@ -363,6 +369,8 @@ __device__ __forceinline__ void upsample_candidate(int k, int hs, int* d, int* i
 // per-frame tail (root subtraction, 3D filters, 2D rescale).
 __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p) {
   extern __shared__ double s_avg[];  // [hs][hs] averaged heat-map of this joint
+  __shared__ short s_cd[2 * kMaxHm], s_ci[2 * kMaxHm];
+  __shared__ float s_cf[2 * kMaxHm];
   __shared__ double s_val[kPostThreads / 32];
   __shared__ int s_idx[kPostThreads / 32];
   __shared__ int s_is_last;
@@ -371,28 +379,52 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
   const int hs = p.hs, S = p.S;
   const int tid = threadIdx.x;
 
-  // ---- 1. multi-scale float64 average of the heat-map (estimator.py:105-129)
-  for (int c = tid; c < hs * hs; c += kPostThreads) s_avg[c] = averaged_cell(p, frame, joint, c / hs, c % hs);
+  // ---- 1. multi-scale float64 average of the heat-map (estimator.py:105-129).  Warp w owns rows w, w+4, ...; lane l
+  // owns columns l, l+32: row / column table entries are fetched once, not per cell.
+  const int warp_id = tid >> 5, lane_id = tid & 31;
+  {
+    const size_t plane = (size_t)hs * hs;
+    for (int y = warp_id; y < hs; y += kPostThreads / 32) {
+      for (int x = lane_id; x < hs; x += 32) {
+        double acc = 0.0;
+        for (int sc = 0; sc < p.n_scales; ++sc) {
+          const float* m = p.maps + ((size_t)(frame * p.n_scales + sc) * 84 + joint) * plane;
+          acc = __dadd_rn(acc, (double)scaled_cell(m, hs, p.tables[sc], y, x));
+        }
+        s_avg[y * hs + x] = __ddiv_rn(acc, (double)p.n_scales);
+      }
+    }
+  }
+  // per-axis candidate tables of the x8 upsample (see upsample_candidate)
+  const int nc = 2 * hs;
+  for (int k = tid; k < nc; k += kPostThreads) {
+    int d, i;
+    double f;
+    upsample_candidate(k, hs, &d, &i, &f);
+    s_cd[k] = (short)d;
+    s_ci[k] = (short)i;
+    s_cf[k] = (float)f;  // 0, 1/16, 15/16: exact in float
+  }
   __syncthreads();
 
   // ---- 2. argmax of the x8 bilinear upsample (utils.py:153-175), OpenCV+IPP arithmetic: fma(S1-S0, f, S0) per axis
   double best = -INFINITY;
   int best_idx = 0x7fffffff;
-  const int nc = 2 * hs;
-  for (int c = tid; c < nc * nc; c += kPostThreads) {
-    const int ky = c / nc, kx = c - ky * nc;
-    int dy, iy, dx, ix;
-    double fy, fx;
-    upsample_candidate(ky, hs, &dy, &iy, &fy);
-    upsample_candidate(kx, hs, &dx, &ix, &fx);
-    const int iy1 = min(iy + 1, hs - 1), ix1 = min(ix + 1, hs - 1);
-    const double s00 = s_avg[iy * hs + ix], s01 = s_avg[iy * hs + ix1];
-    const double s10 = s_avg[iy1 * hs + ix], s11 = s_avg[iy1 * hs + ix1];
-    const double h0 = __fma_rn(__dsub_rn(s01, s00), fx, s00);
-    const double h1 = __fma_rn(__dsub_rn(s11, s10), fx, s10);
-    const double v = __fma_rn(__dsub_rn(h1, h0), fy, h0);
-    const int idx = dy * S + dx;
-    if (v > best || (v == best && idx < best_idx)) { best = v; best_idx = idx; }
+  for (int ky = warp_id; ky < nc; ky += kPostThreads / 32) {
+    const int dy = s_cd[ky], iy = s_ci[ky];
+    const double fy = (double)s_cf[ky];
+    const double* row0 = s_avg + iy * hs;
+    const double* row1 = s_avg + min(iy + 1, hs - 1) * hs;
+    for (int kx = lane_id; kx < nc; kx += 32) {
+      const int ix = s_ci[kx], ix1 = min(ix + 1, hs - 1);
+      const double fx = (double)s_cf[kx];
+      const double s00 = row0[ix], s01 = row0[ix1], s10 = row1[ix], s11 = row1[ix1];
+      const double h0 = __fma_rn(__dsub_rn(s01, s00), fx, s00);
+      const double h1 = __fma_rn(__dsub_rn(s11, s10), fx, s10);
+      const double v = __fma_rn(__dsub_rn(h1, h0), fy, h0);
+      const int idx = dy * S + s_cd[kx];
+      if (v > best || (v == best && idx < best_idx)) { best = v; best_idx = idx; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

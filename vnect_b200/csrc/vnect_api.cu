@@ -751,8 +751,7 @@ static int run_preprocess(vnect_t* h, const uint8_t* dev_bgr, int n_frames, int 
   }
   PyramidParams py = h->pyr;
   py.n_frames = n_frames; py.sq_pitch = sq_pitch; py.sq_frame_stride = sq_stride;
-  const int64_t total = (int64_t)n_frames * S * S;
-  pyramid_kernel<<<dim3(grid_for(total, 256, h->num_sms), h->n_scales), 256, 0, h->stream>>>(sq, h->x1, py);
+  pyramid_kernel<<<dim3(S, n_frames * h->n_scales), 128, 0, h->stream>>>(sq, h->x1, py);
   CU(h, cudaGetLastError());
   ++h->launches;
   return VNECT_OK;
