@@ -119,7 +119,8 @@ struct PyramidParams {
 // estimator.gen_input_batch (estimator.py:70-81): per scale shrink + zero pad (utils.py:123-150), then
 // float32(u8)/255 - 0.4, stored as fp16 in the parity-split padded NHWC4 layout the stem conv's TMA reads.
 // grid = (S rows, n_frames * n_scales forwards): one block per output row, so there is no per-pixel index division
-// (the first version spent ~230 instructions per pixel, mostly 64-bit div/mod, and was issue-bound at 140 us/batch).
+// (the first version spent ~230 instructions per pixel, mostly 64-bit div/mod, and was issue-bound at 140 us/batch;
+// staging the source rows in shared memory was tried and measured slower: 102 us vs 87 us).
 __global__ void __launch_bounds__(128) pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restrict__ x1,
                                                       const __grid_constant__ PyramidParams p) {
   const int y = blockIdx.x;
@@ -371,6 +372,8 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
   extern __shared__ double s_avg[];  // [hs][hs] averaged heat-map of this joint
   __shared__ short s_cd[2 * kMaxHm], s_ci[2 * kMaxHm];
   __shared__ float s_cf[2 * kMaxHm];
+  __shared__ double s_pt[2];
+  __shared__ float s_gather[12 * kMaxScales];
   __shared__ double s_val[kPostThreads / 32];
   __shared__ int s_idx[kPostThreads / 32];
   __shared__ int s_is_last;
@@ -453,9 +456,44 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
       p.j2_box[(frame * kJoints + joint) * 2 + tid] = coord;
     }
     const double py = __shfl_sync(0xffffffffu, coord, 0), px = __shfl_sync(0xffffffffu, coord, 1);
+    if (tid == 0) { s_pt[0] = py; s_pt[1] = px; }
+  }
+  __syncthreads();
+  // utils.hm_pt_interp_bilinear (utils.py:58-79) on the three averaged location maps.  The 3 maps x 4 cells x n_scales
+  // resampled values are fetched by 12*n_scales threads at once (the first version walked them serially in 3 threads
+  // and the dependent global loads dominated the kernel); the float64 arithmetic and its order are unchanged.
+  {
+    const double py = s_pt[0], px = s_pt[1];
+    const double sx = __dsub_rn(__ddiv_rn(__dadd_rn(px, 0.5), 8.0), 0.5);
+    const double sy = __dsub_rn(__ddiv_rn(__dadd_rn(py, 0.5), 8.0), 0.5);
+    int x0 = (int)sx, y0 = (int)sy;  // truncation toward zero, like int()
+    x0 = min(max(x0, 0), hs - 1);    // memory safety only: filtered joints stay inside the box
+    y0 = min(max(y0, 0), hs - 1);
+    const int x1 = min(x0 + 1, hs - 1), y1 = min(y0 + 1, hs - 1);
+    const int items = 12 * p.n_scales;
+    if (tid < items) {
+      const int sc = tid % p.n_scales;
+      const int cell = (tid / p.n_scales) & 3;
+      const int map = tid / (4 * p.n_scales);
+      const size_t plane = (size_t)hs * hs;
+      const float* m = p.maps + ((size_t)(frame * p.n_scales + sc) * 84 + kJoints * (1 + map) + joint) * plane;
+      s_gather[tid] = scaled_cell(m, hs, p.tables[sc], (cell & 2) ? y1 : y0, (cell & 1) ? x1 : x0);
+    }
+    __syncthreads();
     if (tid < 3) {
-      const double v = point_sample(p, frame, kJoints * (1 + tid) + joint, py, px);
-      p.j3_raw[(frame * kJoints + joint) * 3 + tid] = __double2float_rn(__dmul_rn(v, 100.0));  // mm, float32 store
+      double v[4];
+#pragma unroll
+      for (int cell = 0; cell < 4; ++cell) {
+        double acc = 0.0;
+        for (int sc = 0; sc < p.n_scales; ++sc) acc = __dadd_rn(acc, (double)s_gather[(tid * 4 + cell) * p.n_scales + sc]);
+        v[cell] = __ddiv_rn(acc, (double)p.n_scales);
+      }
+      const double wx1 = __dsub_rn((double)x1, sx), wx0 = __dsub_rn(sx, (double)x0);
+      const double wy1 = __dsub_rn((double)y1, sy), wy0 = __dsub_rn(sy, (double)y0);
+      const double value0 = __dadd_rn(__dmul_rn(wx1, v[0]), __dmul_rn(wx0, v[1]));
+      const double value1 = __dadd_rn(__dmul_rn(wx1, v[2]), __dmul_rn(wx0, v[3]));
+      const double val = __dadd_rn(__dmul_rn(wy1, value0), __dmul_rn(wy0, value1));
+      p.j3_raw[(frame * kJoints + joint) * 3 + tid] = __double2float_rn(__dmul_rn(val, 100.0));  // mm, float32 store
     }
   }
 
