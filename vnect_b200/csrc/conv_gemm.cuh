@@ -153,6 +153,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, descriptor prefetch, TMEM allocation) may overlap the previous layer's tail;
+  // from here on this kernel reads what the previous one wrote.
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int total_tiles = p.phases * p.num_m_tiles * p.num_n_tiles;
   const int k_iters = p.taps * p.cblocks + p.cblocks2;

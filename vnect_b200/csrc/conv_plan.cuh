@@ -301,6 +301,23 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
   return true;
 }
 
+// Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor drains; each of our
+// kernels calls pdl_wait() before it touches the predecessor's output.
+template <typename Kern, typename... Args>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int BLOCK_N, int SWZ, int EPI>
 inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
   using Cfg = GemmCfg<BLOCK_N, SWZ, EPI>;
@@ -311,8 +328,8 @@ inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  kern<<<L.grid, kGemmThreads, Cfg::SMEM_BYTES, st>>>(L.tmap_a, L.tmap_b, L.tmap_out, L.tmap_res, L.tmap_a2, L.p);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(L.grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, st, L.tmap_a, L.tmap_b, L.tmap_out, L.tmap_res,
+                    L.tmap_a2, L.p);
 }
 
 inline cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
@@ -445,8 +462,7 @@ inline cudaError_t launch_stem_pool(const StemPoolLaunch& L, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  stem_pool_kernel<<<L.grid, kStemPoolThreads, StemPoolSmem::BYTES, st>>>(L.p);
-  return cudaGetLastError();
+  return launch_pdl(stem_pool_kernel, dim3(L.grid), dim3(kStemPoolThreads), StemPoolSmem::BYTES, st, L.p);
 }
 
 }  // namespace vnect

@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx.cuh"
+
 namespace vnect {
 
 constexpr int kJoints = 21;
@@ -123,6 +125,8 @@ struct PyramidParams {
 // staging the source rows in shared memory was tried and measured slower: 102 us vs 87 us).
 __global__ void __launch_bounds__(128) pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restrict__ x1,
                                                       const __grid_constant__ PyramidParams p) {
+  pdl_launch_dependents();
+  pdl_wait();  // x1 may still be read by the previous batch's stem kernel
   const int y = blockIdx.x;
   const int fwd = blockIdx.y;
   const int frame = fwd / p.n_scales, si = fwd - frame * p.n_scales;
@@ -381,6 +385,8 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
   const int joint = blockIdx.x - frame * kJoints;
   const int hs = p.hs, S = p.S;
   const int tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();  // the maps come from the last conv
 
   // ---- 1. multi-scale float64 average of the heat-map (estimator.py:105-129).  Warp w owns rows w, w+4, ...; lane l
   // owns columns l, l+32: row / column table entries are fetched once, not per cell.

@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(kStemPoolThreads, 1) stem_pool_kernel(const __
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
   if (threadIdx.x >= 128 && threadIdx.x < 192) bias_s[threadIdx.x - 128] = p.bias[threadIdx.x - 128];
+  pdl_launch_dependents();
+  pdl_wait();  // bias (read above) is a constant; the input strips come from the previous kernel
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

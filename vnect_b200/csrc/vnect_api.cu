@@ -283,7 +283,12 @@ struct ConvOpts {
   int res_stride = 1;    // 2: the residual is a full-size tensor read at even pixels
 };
 
-static int pick_block_n(int n) { return n >= 256 ? 256 : n >= 128 ? 128 : 64; }
+// Output-channel tile.  Throughput plans (many forwards) use the widest tile; latency plans (a handful of forwards, e.g.
+// the drop-in estimator: one frame x n_scales) use 64-wide tiles so that 4x more CTAs share each layer's serial K loop.
+static int pick_block_n(int n, int cap_fw) {
+  if (cap_fw <= 8) return 64;
+  return n >= 256 ? 256 : n >= 128 ? 128 : 64;
+}
 
 static int add_conv(vnect_t* h, const std::string& scope, int k, const std::string& in, const std::string& out,
                     int cin, int cout, const ConvOpts& o) {
@@ -304,7 +309,7 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
   s.kind = k == 1 ? CONV_1x1 : CONV_3x3;
   s.NB = h->cap_fw; s.H = OH; s.W = OW;
   s.in = ai.p; s.cin_pad = cin_pad; s.in_stride = o.in_stride;
-  s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout);
+  s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout, h->cap_fw);
   s.bias = db; s.relu_cols = o.relu ? cout : 0;
   if (!o.residual.empty()) {
     const Act& r = h->acts.at(o.residual);
@@ -353,7 +358,7 @@ static int add_proj_tail(vnect_t* h, const std::string& scope2c, const std::stri
   s.kind = CONV_1x1;
   s.NB = h->cap_fw; s.H = ab.H; s.W = ab.W;
   s.in = ab.p; s.cin_pad = mid; s.in2 = ax.p; s.cin2_pad = cin;
-  s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout);
+  s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout, h->cap_fw);
   s.bias = db; s.relu_cols = cout;
   s.out = h->acts.at(out).p; s.ldc = cout; s.epi = EPI_TMA;
   Step st;
@@ -751,8 +756,7 @@ static int run_preprocess(vnect_t* h, const uint8_t* dev_bgr, int n_frames, int 
   }
   PyramidParams py = h->pyr;
   py.n_frames = n_frames; py.sq_pitch = sq_pitch; py.sq_frame_stride = sq_stride;
-  pyramid_kernel<<<dim3(S, n_frames * h->n_scales), 128, 0, h->stream>>>(sq, h->x1, py);
-  CU(h, cudaGetLastError());
+  CU(h, launch_pdl(pyramid_kernel, dim3(S, n_frames * h->n_scales), dim3(128), 0, h->stream, sq, h->x1, py));
   ++h->launches;
   return VNECT_OK;
 }
@@ -817,8 +821,7 @@ static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, i
   p.out2d = dev_out2d; p.out3d = dev_out3d;
   CU(h, cudaMemsetAsync(h->d_counter, 0, n_frames * sizeof(unsigned int), h->stream));
   const size_t smem = (size_t)h->hs * h->hs * sizeof(double);
-  postprocess_kernel<<<n_frames * kJoints, kPostThreads, smem, h->stream>>>(p);
-  CU(h, cudaGetLastError());
+  CU(h, launch_pdl(postprocess_kernel, dim3(n_frames * kJoints), dim3(kPostThreads), smem, h->stream, p));
   ++h->launches;
   return VNECT_OK;
 }
