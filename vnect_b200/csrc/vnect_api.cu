@@ -1166,6 +1166,7 @@ int vnect_time_forward(vnect_t* h, int32_t n, int32_t reps, float* total_ms, flo
 
 void vnect_destroy(vnect_t* h) {
   if (!h) return;
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& kv : h->graphs)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
