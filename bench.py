@@ -281,10 +281,24 @@ def main():
     peaks, peak_src = measured_peaks()
     achieved = EXECUTED_FLOPS_PER_FORWARD * nf * len(SCALES) / (conv_ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    traffic, traffic_note = None, None
+    try:  # DRAM traffic of the same launches from the committed ncu capture (profiles/r01_step_traffic.txt)
+        with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("frames_per_step") == nf:
+            traffic = tj["conv_family_dram_bytes_per_step"]
+            traffic_note = "dram__bytes_read.sum + dram__bytes_write.sum summed over the family's launches of one step, " + tj["source"]
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<*> (implicit-GEMM conv family, %d launches per forward batch)" % (len(per) - 1),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained (burst %.1f)" % (peak_src, peaks["bf16_tflops"]),
-                "traffic": None, "conv_ms_per_batch": conv_ms, "forward_ms_per_batch": fwd_ms,
+                "traffic": traffic, "traffic_note": traffic_note,
+                "hbm_view": None if traffic is None else {
+                    "achieved_gbs": traffic / (conv_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                    "frac": traffic / (conv_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "note": "the family mixes tensor-bound 3x3 convs with HBM-bound 1x1 expand convs; per-launch numbers in profiles/r01_step_traffic.txt"},
+                "conv_ms_per_batch": conv_ms, "forward_ms_per_batch": fwd_ms,
                 "flops_per_forward_executed": EXECUTED_FLOPS_PER_FORWARD, "flops_per_forward_reference": FLOPS_PER_FORWARD}
 
     # ---------------------------------------------------------------- batch-1 latency (C3-style: one stream, filters on)

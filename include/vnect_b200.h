@@ -77,6 +77,18 @@ int vnect_submit(vnect_t* h, int32_t lane, const uint8_t* bgr, int32_t n_frames,
                  float* joints3d);
 int vnect_wait(vnect_t* h, int32_t lane);
 
+/* Tracked video streams: replaces the loop body of run_estimator.py:98-119 for n streams at once.  Every stream keeps a
+ * crop box on the device; vnect_track crops each FULL frame by its stream's box (run_estimator.py:100), runs
+ * VNectEstimator.__call__ on the crop, shifts joints_2d to full-frame coordinates (:104-105) and updates the box from the
+ * joints (:110-119) -- no host round trip between frames.  vnect_track_set_box seeds a stream's box (what HOGBox does in
+ * run_estimator.py:66-83).  frames: HOST uint8 [n][FH][FW][3]; joints2d are full-frame (row, col); boxes_used (optional)
+ * int32 [n][4] = the (x, y, w, h) each frame was cropped with. */
+int vnect_track_set_box(vnect_t* h, int32_t stream_id, int32_t x, int32_t y, int32_t w, int32_t hh);
+int vnect_track_get_box(vnect_t* h, int32_t stream_id, int32_t* xywh);
+int vnect_track(vnect_t* h, const uint8_t* frames, int32_t n_frames, int32_t FH, int32_t FW, int64_t pitch,
+                int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d, double* joints2d,
+                float* joints3d, int32_t* boxes_used);
+
 /* same computation with the frames and the results resident in device memory (dev_bgr, dev_joints2d, dev_joints3d are
  * DEVICE pointers; stream_ids / t2d / t3d stay host arrays).  Asynchronous on the handle's stream. */
 int vnect_estimate_device(vnect_t* h, const uint8_t* dev_bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,

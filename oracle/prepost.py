@@ -308,3 +308,41 @@ def _legacy_f32_filter(f, x32, t):
     f.x.y = x32
     f.x.s = s
     return s
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# run_estimator.py:98-119, restated: crop by the tracked box, estimate, shift to frame coordinates, update the box
+def tracker_update(joints_2d, w_img, h_img):
+    """run_estimator.py:110-119: next crop box (x, y, w, h) from this frame's full-frame 2D joints."""
+    y_min = np.min(joints_2d[:, 0])
+    y_max = np.max(joints_2d[:, 0])
+    x_min = np.min(joints_2d[:, 1])
+    x_max = np.max(joints_2d[:, 1])
+    buffer_x = 0.8 * (x_max - x_min + 1)
+    buffer_y = 0.2 * (y_max - y_min + 1)
+    x, y = (max(int(x_min - buffer_x / 2), 0), max(int(y_min - buffer_y / 2), 0))
+    w, h = (int(min(x_max - x_min + buffer_x, w_img - x)), int(min(y_max - y_min + buffer_y, h_img - y)))
+    return x, y, w, h
+
+
+class OracleTracker:
+    """The reference's video loop body (run_estimator.py:98-119) around an OracleEstimator."""
+
+    def __init__(self, estimator, rect):
+        self.estimator = estimator
+        self.rect = tuple(int(v) for v in rect)
+
+    def __call__(self, frame):
+        h_img, w_img = frame.shape[:2]
+        x, y, w, h = self.rect
+        # numpy slicing clips to the frame; the CUDA path additionally keeps at least 2 x 2 pixels
+        x = min(max(x, 0), w_img - 2)
+        y = min(max(y, 0), h_img - 2)
+        w = max(min(w, w_img - x), 2)
+        h = max(min(h, h_img - y), 2)
+        used = (x, y, w, h)
+        j2, j3 = self.estimator(np.ascontiguousarray(frame[y:y + h, x:x + w, :]))
+        j2[:, 0] += y
+        j2[:, 1] += x
+        self.rect = tracker_update(j2, w_img, h_img)
+        return j2, j3, used

@@ -434,3 +434,40 @@ def test_postprocess_box448_bit_exact():
             assert np.array_equal(j2[0], r2) and np.array_equal(j3[0], r3)
     finally:
         eng.close()
+
+
+# ------------------------------------------------------------------------------------------------ tracked streams (8f)
+def test_tracked_streams_follow_reference_loop(w0, oracle_net_w0):
+    """vnect_track == the loop body of run_estimator.py:98-119 per stream: crop by the tracked box, estimate, shift to
+    full-frame coordinates, update the box -- boxes live on the device between frames."""
+    from vnect_b200 import VNectEngine
+    fh, fw = 540, 960
+    eng = VNectEngine(w0, SCALES2, max_frames=2, max_streams=2, max_input=(fh, fw))
+    try:
+        rects = [(0, 0, fw, fh), (200, 40, 500, 460)]  # stream 0: whole frame (run_estimator.py:65), stream 1: a HOG-like box
+        clocks = [Clock(), Clock()]
+        refs = [prepost.OracleTracker(prepost.OracleEstimator(oracle_net_w0, SCALES2, clock=clocks[s]), rects[s])
+                for s in range(2)]
+        for s in range(2):
+            eng.set_box(s, rects[s])
+        assert eng.get_box(1) == rects[1]
+        diffs = 0
+        for k in range(3):
+            frames = np.stack([np.random.default_rng(5000 + 10 * s + k).integers(0, 256, (fh, fw, 3), dtype=np.uint8)
+                               for s in range(2)])
+            t2, t3 = 100 + k / 25, 100 + k / 25 + 0.004
+            j2, j3, used = eng.track(frames, [0, 1], [t2, t2], [t3, t3])
+            for s in range(2):
+                clocks[s].q = [t2, t3]
+                r2, r3, rused = refs[s](frames[s])
+                assert tuple(used[s]) == rused, (k, s)
+                d = _count_argmax_diffs(j2[s], r2)
+                diffs += d
+                if d == 0:
+                    assert np.abs(j3[s] - r3).max() < 1.0
+                    assert eng.get_box(s) == refs[s].rect
+                else:  # a near-tie moved one joint: keep both loops on the same box so later frames stay comparable
+                    refs[s].rect = eng.get_box(s)
+        assert diffs <= 2
+    finally:
+        eng.close()

@@ -178,3 +178,28 @@ def test_live_reference_estimator_matches_oracle():
         clock.q = [t2, t3]
         m2, m3 = mine(img)
         assert np.array_equal(r2, m2) and np.array_equal(r3, m3)
+
+
+@pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree only exists in the dev container")
+def test_tracker_update_matches_reference_script_lines():
+    """oracle.prepost.tracker_update against run_estimator.py:110-119 executed verbatim."""
+    import os
+    import textwrap
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, "run_estimator.py")).read().splitlines()
+    first = next(i for i, line in enumerate(src) if "y_min = (np.min(joints_2d[:, 0]))" in line)
+    body = textwrap.dedent("\n".join(src[first:first + 10]))
+    assert "H_img - y" in body
+    rng = np.random.default_rng(21)
+    for _ in range(200):
+        w_img, h_img = int(rng.integers(200, 2000)), int(rng.integers(200, 2000))
+        j2 = np.stack([rng.uniform(-20, h_img + 20, 21), rng.uniform(-20, w_img + 20, 21)], axis=1)
+        ns = dict(np=np, joints_2d=j2.copy(), W_img=w_img, H_img=h_img)
+        exec(body, ns)
+        assert prepost.tracker_update(j2, w_img, h_img) == (ns["x"], ns["y"], ns["w"], ns["h"])
+
+
+def test_tracker_update_known_values():
+    j2 = np.zeros((21, 2))
+    j2[:, 0] = np.linspace(100.0, 400.0, 21)   # rows
+    j2[:, 1] = np.linspace(300.5, 420.25, 21)  # cols
+    assert prepost.tracker_update(j2, 960, 540) == (252, 69, 216, 360)

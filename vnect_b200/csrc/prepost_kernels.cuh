@@ -61,15 +61,57 @@ __device__ __forceinline__ void cv_resize_u8_px(const uint8_t* __restrict__ src,
   }
 }
 
+// Per-frame crop + squarify geometry of the tracked-stream path (run_estimator.py:100 crop, utils.py:107-120 squarify).
+struct FrameGeom {
+  int x, y, w, h;           // crop box inside the full frame
+  int dh, dw;               // scaled content size (cvRound(h*scaler), cvRound(w*scaler))
+  int off_x, off_y;         // placement inside the S x S box (utils.py:82-104)
+  int mode;                 // 0 bilinear, 1 exact 2x decimation (INTER_AREA)
+  int pad_;
+  double scaler, inv_scale;
+};
+
 struct SquarifyParams {
-  int n_frames, H, W;       // raw frames
+  int n_frames, H, W;       // raw frames (when geoms != nullptr: the FULL frame size, crops come from geoms)
   int64_t pitch, frame_stride;
   int S;                    // box size
   int dh, dw;               // scaled content size (cvRound(H*scaler), cvRound(W*scaler))
   int off_x, off_y;         // placement inside the box (utils.py:82-104)
   double inv_scale;         // 1 / scaler
   int mode;                 // 0 = bilinear, 1 = exact 2x decimation (OpenCV switches INTER_LINEAR to INTER_AREA)
+  const FrameGeom* geoms;   // optional per-frame geometry (tracked streams); overrides the uniform fields above
 };
+
+// utils.img_scale_squarify geometry (utils.py:107-120) for box (x, y, w, h) -- same arithmetic as the host version
+__device__ __forceinline__ FrameGeom make_frame_geom(int x, int y, int w, int h, int S) {
+  FrameGeom g;
+  g.x = x; g.y = y; g.w = w; g.h = h;
+  g.scaler = __ddiv_rn((double)S, (double)max(h, w));
+  g.dw = __double2int_rn(__dmul_rn((double)w, g.scaler));
+  g.dh = __double2int_rn(__dmul_rn((double)h, g.scaler));
+  g.off_x = g.off_y = 0;
+  if (g.dh > g.dw) g.off_x = S / 2 - g.dw / 2;
+  else g.off_y = S / 2 - g.dh / 2;
+  g.inv_scale = __ddiv_rn(1.0, g.scaler);
+  g.mode = (g.inv_scale == 2.0) ? 1 : 0;
+  g.pad_ = 0;
+  return g;
+}
+
+// boxes: [max_streams] int4 (x, y, w, h); one thread per frame
+__global__ void track_geometry_kernel(const int4* __restrict__ boxes, const int* __restrict__ stream_ids, int n, int S,
+                                      int FH, int FW, FrameGeom* __restrict__ geoms, int* __restrict__ boxes_used) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 b = boxes[stream_ids[i]];
+  // numpy slicing frame[y:y+h, x:x+w] clips to the frame (run_estimator.py:100); keep at least 2x2 pixels
+  b.x = min(max(b.x, 0), FW - 2);
+  b.y = min(max(b.y, 0), FH - 2);
+  b.z = max(min(b.z, FW - b.x), 2);
+  b.w = max(min(b.w, FH - b.y), 2);
+  geoms[i] = make_frame_geom(b.x, b.y, b.z, b.w, S);
+  boxes_used[4 * i + 0] = b.x; boxes_used[4 * i + 1] = b.y; boxes_used[4 * i + 2] = b.z; boxes_used[4 * i + 3] = b.w;
+}
 
 // utils.img_scale_squarify (utils.py:107-120): resize so the longer side is S, centre on black.  out: u8 [n,S,S,3].
 __global__ void squarify_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, SquarifyParams p) {
@@ -78,12 +120,19 @@ __global__ void squarify_kernel(const uint8_t* __restrict__ in, uint8_t* __restr
     const int x = (int)(i % p.S);
     const int y = (int)((i / p.S) % p.S);
     const int n = (int)(i / ((int64_t)p.S * p.S));
+    int H = p.H, W = p.W, dh = p.dh, dw = p.dw, off_x = p.off_x, off_y = p.off_y, mode = p.mode;
+    double inv_scale = p.inv_scale;
+    const uint8_t* src = in + (int64_t)n * p.frame_stride;
+    if (p.geoms != nullptr) {
+      const FrameGeom g = p.geoms[n];
+      H = g.h; W = g.w; dh = g.dh; dw = g.dw; off_x = g.off_x; off_y = g.off_y; mode = g.mode; inv_scale = g.inv_scale;
+      src += (int64_t)g.y * p.pitch + (int64_t)g.x * 3;
+    }
     int v[3] = {0, 0, 0};
-    const int sy = y - p.off_y, sx = x - p.off_x;
-    if (sy >= 0 && sy < p.dh && sx >= 0 && sx < p.dw) {
-      const uint8_t* src = in + (int64_t)n * p.frame_stride;
-      if (p.mode == 0) {
-        cv_resize_u8_px(src, p.pitch, p.H, p.W, sy, sx, p.inv_scale, v);
+    const int sy = y - off_y, sx = x - off_x;
+    if (sy >= 0 && sy < dh && sx >= 0 && sx < dw) {
+      if (mode == 0) {
+        cv_resize_u8_px(src, p.pitch, H, W, sy, sx, inv_scale, v);
       } else {
         const uint8_t* r0 = src + (int64_t)(2 * sy) * p.pitch + (int64_t)(2 * sx) * 3;
         const uint8_t* r1 = r0 + p.pitch;
@@ -308,6 +357,7 @@ struct PostParams {
   int filters_on;
   double scaler;                  // box px per input px (S / max(H, W))
   int off_x, off_y;
+  const FrameGeom* geoms;         // optional per-frame geometry (tracked streams): scaler, offsets and the crop origin
   double* j2_box;                 // [n_frames][21][2] scratch: filtered 2D joints in box pixels (also an output tap)
   float* j3_raw;                  // [n_frames][21][3] scratch: x100 location-map samples before root subtraction
   int* raw_argmax;                // [n_frames][21][2] unfiltered argmax (row, col), a tap for parity tests
@@ -524,8 +574,50 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
   if (tid < kJoints * 2) {
     const int j = tid >> 1, c = tid & 1;
     const volatile double* jb = p.j2_box + frame * kJoints * 2;
-    const double off = (c == 0) ? (double)p.off_y : (double)p.off_x;  // estimator.py:138-139
-    p.out2d[(frame * kJoints + j) * 2 + c] = __ddiv_rn(__dsub_rn(jb[j * 2 + c], off), p.scaler);
+    double off = (c == 0) ? (double)p.off_y : (double)p.off_x, scaler = p.scaler;  // estimator.py:138-139
+    double v2 = 0.0;
+    if (p.geoms != nullptr) {
+      const FrameGeom g = p.geoms[frame];
+      off = (c == 0) ? (double)g.off_y : (double)g.off_x;
+      scaler = g.scaler;
+      v2 = __ddiv_rn(__dsub_rn(jb[j * 2 + c], off), scaler);
+      v2 = __dadd_rn(v2, (c == 0) ? (double)g.y : (double)g.x);  // joints_2d[:, 0] += y; [:, 1] += x (run_estimator.py:104-105)
+    } else {
+      v2 = __ddiv_rn(__dsub_rn(jb[j * 2 + c], off), scaler);
+    }
+    p.out2d[(frame * kJoints + j) * 2 + c] = v2;
+  }
+}
+
+// Bounding-box tracker of the reference's video loop (run_estimator.py:110-119), one warp per frame:
+//   buffer_x = 0.8 * (x_max - x_min + 1);  buffer_y = 0.2 * (y_max - y_min + 1)
+//   x, y = max(int(x_min - buffer_x / 2), 0), max(int(y_min - buffer_y / 2), 0)
+//   w, h = int(min(x_max - x_min + buffer_x, W_img - x)), int(min(y_max - y_min + buffer_y, H_img - y))
+// joints2d are full-frame (row, col) coordinates; float64 arithmetic without FMA, int() truncates toward zero.
+__global__ void track_update_kernel(const double* __restrict__ joints2d, const int* __restrict__ stream_ids, int n,
+                                    int FH, int FW, int4* __restrict__ boxes) {
+  const int frame = blockIdx.x;
+  const int lane = threadIdx.x;
+  double ymin = INFINITY, ymax = -INFINITY, xmin = INFINITY, xmax = -INFINITY;
+  if (lane < kJoints) {
+    ymin = ymax = joints2d[(frame * kJoints + lane) * 2 + 0];
+    xmin = xmax = joints2d[(frame * kJoints + lane) * 2 + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+    ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+  }
+  if (lane == 0) {
+    const double buffer_x = __dmul_rn(0.8, __dadd_rn(__dsub_rn(xmax, xmin), 1.0));
+    const double buffer_y = __dmul_rn(0.2, __dadd_rn(__dsub_rn(ymax, ymin), 1.0));
+    const int x = max((int)__dsub_rn(xmin, __ddiv_rn(buffer_x, 2.0)), 0);
+    const int y = max((int)__dsub_rn(ymin, __ddiv_rn(buffer_y, 2.0)), 0);
+    const int w = (int)fmin(__dadd_rn(__dsub_rn(xmax, xmin), buffer_x), (double)(FW - x));
+    const int h = (int)fmin(__dadd_rn(__dsub_rn(ymax, ymin), buffer_y), (double)(FH - y));
+    boxes[stream_ids[frame]] = make_int4(x, y, w, h);
   }
 }
 

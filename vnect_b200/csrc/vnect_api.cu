@@ -91,6 +91,10 @@ struct vnect_handle {
   Lane* cur = &lanes[0];
   cudaStream_t copy_stream = nullptr;
   unsigned device_calls = 0;
+  // tracked streams (run_estimator.py:100-119): per-stream crop box on the device, per-call frame geometry
+  int4* d_boxes = nullptr;         // [max_streams] (x, y, w, h)
+  FrameGeom* d_geoms = nullptr;    // [max_frames]
+  int* d_boxes_used = nullptr;     // [max_frames][4]
   // CUDA graphs of the kernel sequence of one estimate call, keyed by everything baked into the kernel parameters.
   // First use of a key runs directly (warm-up), the second captures, later ones replay: ~50 launches -> 1.
   typedef std::tuple<int, int, int, int, long long, long long, const void*, const void*, const void*> GraphKey;
@@ -485,6 +489,9 @@ static int alloc_prepost(vnect_t* h) {
   if ((rc = dev_alloc(h, &h->d_raw_argmax, (size_t)mf * kJoints * 2))) return rc;
   if ((rc = dev_alloc(h, &h->d_counter, mf))) return rc;
   if ((rc = dev_alloc(h, &h->d_filter_scratch, 64))) return rc;
+  if ((rc = dev_alloc(h, &h->d_boxes, ms))) return rc;
+  if ((rc = dev_alloc(h, &h->d_geoms, mf))) return rc;
+  if ((rc = dev_alloc(h, &h->d_boxes_used, (size_t)mf * 4))) return rc;
   h->last_t2d.assign(ms, NAN);
   h->last_t3d.assign(ms, NAN);
   PyramidParams& py = h->pyr;
@@ -740,12 +747,19 @@ static Geometry squarify_geometry(int S, int H, int W) {
 
 // device frames -> x1 (stem layout) for n_frames * n_scales forwards
 static int run_preprocess(vnect_t* h, const uint8_t* dev_bgr, int n_frames, int H, int W, int64_t pitch,
-                          int64_t frame_stride, const Geometry& g) {
+                          int64_t frame_stride, const Geometry& g, bool tracked = false) {
   const int S = h->S;
   const uint8_t* sq = dev_bgr;
   int64_t sq_pitch = pitch, sq_stride = frame_stride;
-  if (!g.alias) {
+  if (tracked) {
+    track_geometry_kernel<<<(n_frames + 63) / 64, 64, 0, h->stream>>>(h->d_boxes, h->cur->d_stream_ids, n_frames, S, H, W,
+                                                                      h->d_geoms, h->d_boxes_used);
+    CU(h, cudaGetLastError());
+    ++h->launches;
+  }
+  if (!g.alias || tracked) {
     SquarifyParams sp;
+    sp.geoms = tracked ? h->d_geoms : nullptr;
     sp.n_frames = n_frames; sp.H = H; sp.W = W; sp.pitch = pitch; sp.frame_stride = frame_stride; sp.S = S;
     sp.dh = g.dh; sp.dw = g.dw; sp.off_x = g.off_x; sp.off_y = g.off_y; sp.inv_scale = 1.0 / g.scaler; sp.mode = g.mode;
     const int64_t total = (int64_t)n_frames * S * S;
@@ -806,8 +820,9 @@ static int stage_frame_meta(vnect_t* h, int n_frames, const int32_t* stream_ids,
 }
 
 static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, int off_y, double* dev_out2d,
-                           float* dev_out3d) {
+                           float* dev_out3d, bool tracked = false) {
   PostParams p;
+  p.geoms = tracked ? h->d_geoms : nullptr;
   p.n_frames = n_frames; p.n_scales = h->n_scales; p.hs = h->hs; p.S = h->S;
   p.maps = h->maps; p.tables = h->d_tables;
   p.stream_ids = h->cur->d_stream_ids; p.t2d = h->cur->d_t2d; p.t3d = h->cur->d_t3d;
@@ -857,16 +872,22 @@ int vnect_forward(vnect_t* h, const float* nhwc, int32_t n, float* hm, float* xm
 
 // pre-process -> CNN -> post-process for one batch, as a replayed CUDA graph when possible
 static int run_pipeline(vnect_t* h, int lane, const uint8_t* dev_bgr, int n_frames, int H, int W, int64_t pitch,
-                        int64_t frame_stride, double* out2d, float* out3d) {
+                        int64_t frame_stride, double* out2d, float* out3d, bool tracked = false) {
   const Geometry g = squarify_geometry(h->S, H, W);
   auto direct = [&]() -> int {
     int rc;
-    if ((rc = run_preprocess(h, dev_bgr, n_frames, H, W, pitch, frame_stride, g))) return rc;
+    if ((rc = run_preprocess(h, dev_bgr, n_frames, H, W, pitch, frame_stride, g, tracked))) return rc;
     if ((rc = run_forward(h, n_frames * h->n_scales))) return rc;
-    return run_postprocess(h, n_frames, g.scaler, g.off_x, g.off_y, out2d, out3d);
+    if ((rc = run_postprocess(h, n_frames, g.scaler, g.off_x, g.off_y, out2d, out3d, tracked))) return rc;
+    if (tracked) {
+      track_update_kernel<<<n_frames, 32, 0, h->stream>>>(out2d, h->cur->d_stream_ids, n_frames, H, W, h->d_boxes);
+      CU(h, cudaGetLastError());
+      ++h->launches;
+    }
+    return VNECT_OK;
   };
   if (!h->use_graphs) return direct();
-  const vnect_handle::GraphKey key(lane, n_frames, H, W, (long long)pitch, (long long)frame_stride, dev_bgr, out2d, out3d);
+  const vnect_handle::GraphKey key(lane + (tracked ? 2 : 0), n_frames, H, W, (long long)pitch, (long long)frame_stride, dev_bgr, out2d, out3d);
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
     h->graphs[key] = vnect_handle::GraphEntry();
@@ -951,6 +972,52 @@ int vnect_submit(vnect_t* h, int32_t lane, const uint8_t* bgr, int32_t n_frames,
   CU(h, cudaMemcpyAsync(joints3d, h->cur->d_out3d, (size_t)n_frames * kJoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaEventRecord(h->cur->done, h->stream));
   h->cur->pending = true;
+  return VNECT_OK;
+}
+
+int vnect_track_set_box(vnect_t* h, int32_t stream_id, int32_t x, int32_t y, int32_t w, int32_t hh) {
+  if (!h || !h->d_boxes) return fail(h, VNECT_E_INVALID, "handle not created");
+  if (stream_id < 0 || stream_id >= h->cfg.max_streams) return fail(h, VNECT_E_INVALID, "stream id out of range");
+  if (x < 0 || y < 0 || w < 2 || hh < 2) return fail(h, VNECT_E_INVALID, "box must have x, y >= 0 and w, h >= 2");
+  const int4 b = make_int4(x, y, w, hh);
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(h->d_boxes + stream_id, &b, sizeof b, cudaMemcpyHostToDevice));
+  return VNECT_OK;
+}
+
+int vnect_track_get_box(vnect_t* h, int32_t stream_id, int32_t* xywh) {
+  if (!h || !h->d_boxes || !xywh) return fail(h, VNECT_E_INVALID, "handle not created / null buffer");
+  if (stream_id < 0 || stream_id >= h->cfg.max_streams) return fail(h, VNECT_E_INVALID, "stream id out of range");
+  CU(h, cudaStreamSynchronize(h->stream));
+  int4 b;
+  CU(h, cudaMemcpy(&b, h->d_boxes + stream_id, sizeof b, cudaMemcpyDeviceToHost));
+  xywh[0] = b.x; xywh[1] = b.y; xywh[2] = b.z; xywh[3] = b.w;
+  return VNECT_OK;
+}
+
+int vnect_track(vnect_t* h, const uint8_t* frames, int32_t n_frames, int32_t FH, int32_t FW, int64_t pitch,
+                int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d, double* joints2d,
+                float* joints3d, int32_t* boxes_used) {
+  if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  if (!frames || !joints2d || !joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
+  if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames %d not in [1, %d]", n_frames, h->cfg.max_frames);
+  if (FH < 2 || FW < 2 || FH > h->cfg.max_input_h || FW > h->cfg.max_input_w)
+    return fail(h, VNECT_E_INVALID, "frame %dx%d outside [2, max_input %dx%d]", FH, FW, h->cfg.max_input_h, h->cfg.max_input_w);
+  if (pitch < (int64_t)FW * 3) return fail(h, VNECT_E_INVALID, "pitch smaller than a row");
+  int rc = lane_acquire(h, 0);
+  if (rc) return rc;
+  if ((rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d, h->copy_stream))) return rc;
+  const int64_t dpitch = (int64_t)FW * 3, dstride = dpitch * FH;
+  for (int i = 0; i < n_frames; ++i)
+    CU(h, cudaMemcpy2DAsync(h->cur->d_frames + (size_t)i * dstride, dpitch, frames + (size_t)i * frame_stride, pitch, dpitch, FH, cudaMemcpyHostToDevice, h->copy_stream));
+  CU(h, cudaEventRecord(h->cur->copy_done, h->copy_stream));
+  CU(h, cudaStreamWaitEvent(h->stream, h->cur->copy_done, 0));
+  if ((rc = run_pipeline(h, 0, h->cur->d_frames, n_frames, FH, FW, dpitch, dstride, h->cur->d_out2d, h->cur->d_out3d, true))) return rc;
+  CU(h, cudaMemcpyAsync(joints2d, h->cur->d_out2d, (size_t)n_frames * kJoints * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(joints3d, h->cur->d_out3d, (size_t)n_frames * kJoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (boxes_used)
+    CU(h, cudaMemcpyAsync(boxes_used, h->d_boxes_used, (size_t)n_frames * 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
   return VNECT_OK;
 }
 

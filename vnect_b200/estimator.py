@@ -151,6 +151,29 @@ class VNectEngine:
         self._check(self._lib.vnect_wait(self._h, int(lane)))
         return self.__dict__.get("_inflight", {}).pop(int(lane), (None, None, None))[1:]
 
+    def set_box(self, stream_id, rect):
+        """Seed the tracked crop box (x, y, w, h) of a stream (what HOGBox provides in run_estimator.py:66-83)."""
+        x, y, w, h = (int(v) for v in rect)
+        self._check(self._lib.vnect_track_set_box(self._h, int(stream_id), x, y, w, h))
+
+    def get_box(self, stream_id):
+        out = (C.c_int32 * 4)()
+        self._check(self._lib.vnect_track_get_box(self._h, int(stream_id), out))
+        return tuple(out)
+
+    def track(self, frames, stream_ids=None, t2d=None, t3d=None):
+        """One step of the reference's video loop (run_estimator.py:98-119) for n streams: crop each full frame by
+        its stream's box, estimate, shift joints_2d to full-frame coordinates, update the box on the device.
+        Returns (joints_2d [n,21,2], joints_3d [n,21,3], boxes_used [n,4])."""
+        frames, st = self._frames(frames)
+        n, h, w = frames.shape[:3]
+        ids, t2d, t3d = self._meta(n, stream_ids, t2d, t3d)
+        j2, j3 = np.empty((n, JOINTS, 2), np.float64), np.empty((n, JOINTS, 3), np.float32)
+        boxes = np.empty((n, 4), np.int32)
+        self._check(self._lib.vnect_track(self._h, _ptr(frames), n, h, w, st[1], st[0] if n > 1 else st[1] * h,
+                                          _ptr(ids), _ptr(t2d), _ptr(t3d), _ptr(j2), _ptr(j3), _ptr(boxes)))
+        return j2, j3, boxes
+
     def estimate_device(self, dev_frames_ptr, n, h, w, dev_j2_ptr, dev_j3_ptr, stream_ids=None, t2d=None, t3d=None,
                         pitch=None, frame_stride=None):
         """Same path with frames / results resident in device memory (raw device pointers, e.g. tensor.data_ptr())."""
