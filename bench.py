@@ -174,8 +174,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     nf = args.frames
     n_streams = nf * world
@@ -249,19 +249,35 @@ def main():
         outs.append((a.numpy(), b.numpy(), a, b))
     j2h, j3h = outs[0][0], outs[0][1]
 
+    # cross-rank gather of a finished step's results: device-side, asynchronous, waited one step later so that it
+    # never stalls the submission pipeline (the only collective on the path, 21 x 5 numbers per frame)
+    g_in = [torch.empty((nf, 21, 5), dtype=torch.float64, device=dev) for _ in range(2)]
+    g_out = [torch.empty((world * nf, 21, 5), dtype=torch.float64, device=dev) for _ in range(2)]
+    g_work = [None, None]
+
+    def gather(lane):
+        if world == 1:
+            return
+        if g_work[lane] is not None:
+            g_work[lane].wait()
+        g_in[lane][:, :, :2].copy_(outs[lane][2], non_blocking=True)
+        g_in[lane][:, :, 2:].copy_(outs[lane][3], non_blocking=True)
+        g_work[lane] = dist.all_gather_into_tensor(g_out[lane], g_in[lane], async_op=True)
+
     def e2e_steps(k):
         for i in range(k):
             lane = i & 1
             if i >= 2:
                 eng.wait(lane)
-                if world > 1:
-                    parallel.gather_results(parallel.pack_results(outs[lane][0], outs[lane][1]), n_streams, device=dev)
+                gather(lane)
             t2, t3 = stamps()
             eng.submit(lane, hf, ids, t2, t3, out=(outs[lane][0], outs[lane][1]))
         for i in range(max(k - 2, 0), k):
             eng.wait(i & 1)
-            if world > 1:
-                parallel.gather_results(parallel.pack_results(outs[i & 1][0], outs[i & 1][1]), n_streams, device=dev)
+            gather(i & 1)
+        for w in g_work:
+            if w is not None:
+                w.wait()
 
     e2e_steps(3)
     barrier()
