@@ -471,3 +471,31 @@ def test_tracked_streams_follow_reference_loop(w0, oracle_net_w0):
         assert diffs <= 2
     finally:
         eng.close()
+
+
+# ------------------------------------------------------------------------------------------------ input edge cases
+@pytest.mark.parametrize("hw", [(16, 16), (7, 300), (1080, 1920), (369, 368), (2, 2)])
+def test_preprocess_extreme_geometries(hw):
+    """Upscaling tiny crops, extreme aspect ratios, a full-HD frame, an off-by-one box: bit-exact like the rest."""
+    from vnect_b200 import VNectEngine
+    h, w = hw
+    eng = VNectEngine(False, SCALES2, max_frames=1, max_input=(max(h, 368), max(w, 368)))
+    try:
+        img = np.random.default_rng(h * 7 + w).integers(0, 256, (h, w, 3), dtype=np.uint8)
+        got, scaler, offs = eng.preprocess(img)
+        ref, rs, ro = prepost.gen_input_batch(img, 368, SCALES2)
+        assert (scaler, offs) == (rs, ro)
+        assert np.array_equal(got, ref.astype(np.float16).astype(np.float32))
+    finally:
+        eng.close()
+
+
+def test_malformed_frames_raise(engine_w0):
+    with pytest.raises(ValueError):
+        engine_w0.estimate(np.zeros((368, 368), np.uint8))  # grey image
+    with pytest.raises(ValueError):
+        engine_w0.estimate(np.zeros((368, 368, 3), np.float32))  # not uint8
+    with pytest.raises(ValueError):
+        engine_w0.estimate(np.zeros((1, 1, 368, 3), np.uint8))  # degenerate height
+    with pytest.raises(ValueError):
+        engine_w0.estimate(np.zeros((2, 368, 368, 3), np.uint8), stream_ids=[0])  # ragged ids

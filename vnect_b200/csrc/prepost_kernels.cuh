@@ -1,8 +1,8 @@
-// Bandwidth-bound kernels around the CNN: bit-exact OpenCV-style preprocessing (K1), 3x3/2 max-pool (K3) and the
+// Bandwidth-bound kernels around the CNN: bit-exact OpenCV-style preprocessing (K1), the bbox tracker and the
 // fused post-process (K8: multi-scale average -> x8 upsample argmax -> 1-euro filters -> location-map gather).
 //
 // Reference semantics being restated (XinArkh/VNect): src/estimator.py:70-81 and src/utils.py:13-21,82-150 (K1),
-// src/vnect_model.py:29 (pool), src/estimator.py:105-142 + src/utils.py:58-79,153-219 + src/OneEuroFilter.py:13-75
+// src/estimator.py:105-142 + src/utils.py:58-79,153-219 + src/OneEuroFilter.py:13-75
 // (K8).  Arithmetic that has to be bit-faithful uses explicit round-to-nearest intrinsics so that nvcc cannot
 // contract a*b+c into an FMA where OpenCV / CPython do not (and uses FMA where OpenCV+IPP does: the float64 x8
 // upsample; see oracle/prepost.py).
@@ -253,46 +253,6 @@ __global__ void stem_to_f32_kernel(const __half* __restrict__ x1, float* __restr
     out[i * 3 + 0] = __half2float(o[0]);
     out[i * 3 + 1] = __half2float(o[1]);
     out[i * 3 + 2] = __half2float(o[2]);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// tc.layers.max_pool2d(kernel 3, stride 2, 'same') on NHWC fp16 (vnect_model.py:29): TF SAME pads (0,1) here and
-// ignores padded cells.  One thread = 8 channels (16 B) of one output pixel.
-// The input may have a virtual row pitch / image stride (in pixels) larger than W / H*W (conv1's output does).
-__global__ void maxpool3x3s2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int NB, int H, int W,
-                                    int C, int OH, int OW, int in_row_px, int64_t in_img_px) {
-  const int cv = C / 8;
-  const int64_t total = (int64_t)NB * OH * OW * cv;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv);
-    int64_t r = i / cv;
-    const int ox = (int)(r % OW);
-    r /= OW;
-    const int oy = (int)(r % OH);
-    const int n = (int)(r / OH);
-    __half2 m[4];
-    bool first = true;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int y = 2 * oy + ky;
-      if (y >= H) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int x = 2 * ox + kx;
-        if (x >= W) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((int64_t)n * in_img_px + (int64_t)y * in_row_px + x) * C) + c8);
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
-        if (first) {
-          m[0] = h[0]; m[1] = h[1]; m[2] = h[2]; m[3] = h[3];
-          first = false;
-        } else {
-          m[0] = __hmax2(m[0], h[0]); m[1] = __hmax2(m[1], h[1]);
-          m[2] = __hmax2(m[2], h[2]); m[3] = __hmax2(m[3], h[3]);
-        }
-      }
-    }
-    *(reinterpret_cast<uint4*>(out + (((int64_t)n * OH + oy) * OW + ox) * C) + c8) = *reinterpret_cast<uint4*>(m);
   }
 }
 

@@ -25,17 +25,10 @@ struct Act {
 };
 
 struct Step {
-  int kind = 0;  // 0 = conv GEMM, 1 = maxpool, 2 = stem (conv1), 3 = fused conv1 + pool1
+  int kind = 0;  // 0 = implicit-GEMM conv (conv_gemm_kernel), 3 = fused conv1 + pool1 (stem_pool_kernel)
   std::string name;
   ConvLaunch launch;
-  StemLaunch stem;
   StemPoolLaunch stem_pool;
-  int tiles_per_image = 0;  // spatial
-  // pool
-  const __half* pin = nullptr;
-  __half* pout = nullptr;
-  int H = 0, W = 0, C = 0, OH = 0, OW = 0, in_row_px = 0;
-  int64_t in_img_px = 0;
 };
 
 struct HostVar {
@@ -108,10 +101,6 @@ struct vnect_handle {
   std::vector<double> last_t2d, last_t3d;  // host mirror of the filters' last timestamps (NaN = none yet)
   PyramidParams pyr{};
 };
-
-// Images per conv1+pool1 launch pair.  Chunks of 8 (35 MB, L2-resident) were measured SLOWER on B200 (572 us vs 380 us
-// for 128 images: 32 small launches cost more than the HBM round trip saves), so the whole batch goes in one chunk.
-constexpr int kStemChunk = 1 << 20;
 
 static int fail(vnect_t* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -680,7 +669,7 @@ int vnect_finalize(vnect_t* h) {
     h->steps.push_back(st);
   }
   h->conv_steps = 0;
-  for (const Step& st : h->steps) h->conv_steps += st.kind != 1;
+  h->conv_steps = (int)h->steps.size();
 
   h->vars.clear();  // host copies no longer needed
   h->finalized = true;
@@ -698,26 +687,9 @@ static int run_forward(vnect_t* h, int n, cudaEvent_t* layer_events = nullptr) {
     if (st.kind == 0) {
       set_batch(st.launch, n, h->num_sms);
       CU(h, launch_conv(st.launch, h->stream));
-    } else if (st.kind == 3) {
+    } else {
       stem_pool_set_batch(st.stem_pool, n, h->num_sms);
       CU(h, launch_stem_pool(st.stem_pool, h->stream));
-    } else if (st.kind == 2) {
-      // conv1 + pool1 chunk by chunk (the next step, pool1, is executed here too and skipped below)
-      Step& pool = *(&st + 1);
-      for (int i0 = 0; i0 < n; i0 += kStemChunk) {
-        const int cn = n - i0 < kStemChunk ? n - i0 : kStemChunk;
-        stem_set_batch(st.stem, cn, h->num_sms, i0);
-        CU(h, launch_stem(st.stem, h->stream));
-        const int64_t total = (int64_t)cn * pool.OH * pool.OW * (pool.C / 8);
-        maxpool3x3s2_kernel<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(
-            pool.pin, pool.pout + (size_t)i0 * pool.OH * pool.OW * pool.C, cn, pool.H, pool.W, pool.C, pool.OH, pool.OW,
-            pool.in_row_px, pool.in_img_px);
-        CU(h, cudaGetLastError());
-        h->launches += 2;
-      }
-      continue;
-    } else {
-      continue;  // pool1 ran inside the conv1 step
     }
     ++h->launches;
   }
@@ -1184,8 +1156,7 @@ double vnect_info(vnect_t* h, const char* key) {
     double f = 0;
     for (const Step& st : h->steps)
       if (st.kind == 0) f += st.launch.flops / h->cap_fw;
-      else if (st.kind == 2) f += 2.0 * st.stem.p.tiles_per_image * kBlockM * 64 * 224;
-      else if (st.kind == 3) f += 2.0 * st.stem_pool.p.bands_per_image * st.stem_pool.p.band_tiles * kBlockM * 64 * 224;
+      else f += 2.0 * st.stem_pool.p.bands_per_image * st.stem_pool.p.band_tiles * kBlockM * 64 * 224;
     return f;
   }
   if (k == "hm_size") return h->hs;
