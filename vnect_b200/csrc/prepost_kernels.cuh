@@ -340,34 +340,6 @@ __device__ __forceinline__ float scaled_cell(const float* __restrict__ m, int hs
   return __fadd_rn(__fmul_rn(t0, T.b0[y]), __fmul_rn(t1, T.b1[y]));
 }
 
-// float64 mean over scales, accumulated in scale order (estimator.py:105-129)
-__device__ __forceinline__ double averaged_cell(const PostParams& p, int frame, int channel, int y, int x) {
-  double acc = 0.0;
-  const size_t plane = (size_t)p.hs * p.hs;
-  for (int s = 0; s < p.n_scales; ++s) {
-    const float* m = p.maps + ((size_t)(frame * p.n_scales + s) * 84 + channel) * plane;
-    acc = __dadd_rn(acc, (double)scaled_cell(m, p.hs, p.tables[s], y, x));
-  }
-  return __ddiv_rn(acc, (double)p.n_scales);
-}
-
-// utils.hm_pt_interp_bilinear (utils.py:58-79) on the averaged map of `channel`, point (row py, col px), float64.
-__device__ __forceinline__ double point_sample(const PostParams& p, int frame, int channel, double py, double px) {
-  const double sx = __dsub_rn(__ddiv_rn(__dadd_rn(px, 0.5), 8.0), 0.5);
-  const double sy = __dsub_rn(__ddiv_rn(__dadd_rn(py, 0.5), 8.0), 0.5);
-  int x0 = (int)sx, y0 = (int)sy;  // truncation toward zero, like int()
-  x0 = min(max(x0, 0), p.hs - 1);  // memory safety only: filtered joints stay inside the box
-  y0 = min(max(y0, 0), p.hs - 1);
-  const int x1 = min(x0 + 1, p.hs - 1), y1 = min(y0 + 1, p.hs - 1);
-  const double wx1 = __dsub_rn((double)x1, sx), wx0 = __dsub_rn(sx, (double)x0);
-  const double wy1 = __dsub_rn((double)y1, sy), wy0 = __dsub_rn(sy, (double)y0);
-  const double v00 = averaged_cell(p, frame, channel, y0, x0), v01 = averaged_cell(p, frame, channel, y0, x1);
-  const double v10 = averaged_cell(p, frame, channel, y1, x0), v11 = averaged_cell(p, frame, channel, y1, x1);
-  const double value0 = __dadd_rn(__dmul_rn(wx1, v00), __dmul_rn(wx0, v01));
-  const double value1 = __dadd_rn(__dmul_rn(wx1, v10), __dmul_rn(wx0, v11));
-  return __dadd_rn(__dmul_rn(wy1, value0), __dmul_rn(wy0, value1));
-}
-
 // Candidate k (0 .. 2*hs-1) of the x8 upsample along one axis: destination index d, source cell i, fraction f.
 // Between two source cell centres the upsample is monotonic, so its maximum over the 8 samples of a segment sits at
 // the first (f = 1/16) or last (f = 15/16) one; d = 0 stands for the exactly-tied samples 0..3 and d = 8*(hs-1)+4 for
@@ -388,7 +360,7 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
   __shared__ float s_cf[2 * kMaxHm];
   __shared__ double s_pt[2];
   __shared__ float s_gather[12 * kMaxScales];
-  __shared__ double s_val[kPostThreads / 32];
+  __shared__ double s_val[kPostThreads / 32], s_amax[kPostThreads / 32];
   __shared__ int s_idx[kPostThreads / 32];
   __shared__ int s_is_last;
   const int frame = blockIdx.x / kJoints;
@@ -399,19 +371,16 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
   pdl_wait();  // the maps come from the last conv
 
   // ---- 1. multi-scale float64 average of the heat-map (estimator.py:105-129).  Warp w owns rows w, w+4, ...; lane l
-  // owns columns l, l+32: row / column table entries are fetched once, not per cell.
+  // owns columns l, l+32.  The whole plane of every scale is first staged in shared memory with coalesced loads (one
+  // round trip to HBM instead of a dependent chain per cell), then resampled from there.
   const int warp_id = tid >> 5, lane_id = tid & 31;
+  const int cells = hs * hs;
+  float* s_raw = reinterpret_cast<float*>(s_avg + cells);  // [n_scales][hs*hs] raw planes
   {
-    const size_t plane = (size_t)hs * hs;
-    for (int y = warp_id; y < hs; y += kPostThreads / 32) {
-      for (int x = lane_id; x < hs; x += 32) {
-        double acc = 0.0;
-        for (int sc = 0; sc < p.n_scales; ++sc) {
-          const float* m = p.maps + ((size_t)(frame * p.n_scales + sc) * 84 + joint) * plane;
-          acc = __dadd_rn(acc, (double)scaled_cell(m, hs, p.tables[sc], y, x));
-        }
-        s_avg[y * hs + x] = __ddiv_rn(acc, (double)p.n_scales);
-      }
+    const size_t plane = (size_t)cells;
+    for (int sc = 0; sc < p.n_scales; ++sc) {
+      const float* m = p.maps + ((size_t)(frame * p.n_scales + sc) * 84 + joint) * plane;
+      for (int c = tid; c < cells; c += kPostThreads) s_raw[sc * cells + c] = __ldg(m + c);
     }
   }
   // per-axis candidate tables of the x8 upsample (see upsample_candidate)
@@ -425,24 +394,102 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
     s_cf[k] = (float)f;  // 0, 1/16, 15/16: exact in float
   }
   __syncthreads();
+  double cell_best = -INFINITY, cell_amax = 0.0;
+  int cell_best_idx = 0;
+  for (int y = warp_id; y < hs; y += kPostThreads / 32) {
+    for (int x = lane_id; x < hs; x += 32) {
+      double acc = 0.0;
+      for (int sc = 0; sc < p.n_scales; ++sc) {
+        const ScaleTable& T = p.tables[sc];
+        const float* m = s_raw + sc * cells;
+        float v;
+        if (T.identity) {
+          v = m[y * hs + x];
+        } else {  // cv2 float32 resize arithmetic: separate multiplies and adds
+          const float* r0 = m + T.j0[y] * hs;
+          const float* r1 = m + T.j1[y] * hs;
+          const int x0 = T.i0[x], x1 = T.i1[x];
+          const float a0 = T.a0[x], a1 = T.a1[x];
+          const float t0 = __fadd_rn(__fmul_rn(r0[x0], a0), __fmul_rn(r0[x1], a1));
+          const float t1 = __fadd_rn(__fmul_rn(r1[x0], a0), __fmul_rn(r1[x1], a1));
+          v = __fadd_rn(__fmul_rn(t0, T.b0[y]), __fmul_rn(t1, T.b1[y]));
+        }
+        acc = __dadd_rn(acc, (double)v);
+      }
+      // hm_avg /= len(scales): for 1, 2 or 4 scales the quotient is an exact scaling, bit-identical to the division
+      const double a = p.n_scales == 1 ? acc : p.n_scales == 2 ? __dmul_rn(acc, 0.5) : p.n_scales == 4 ? __dmul_rn(acc, 0.25)
+                                                                                   : __ddiv_rn(acc, (double)p.n_scales);
+      s_avg[y * hs + x] = a;
+      if (a > cell_best) { cell_best = a; cell_best_idx = y * hs + x; }
+      cell_amax = fmax(cell_amax, fabs(a));
+    }
+  }
+  // block-wide largest cell: its neighbourhood gives a lower bound L0 on the upsampled maximum, which prunes almost
+  // every candidate below (a candidate is a convex combination of its 4 cells, so it cannot beat L0 unless one of
+  // them does, up to rounding -- hence the relative margin)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, cell_best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, cell_best_idx, o);
+    if (ov > cell_best) { cell_best = ov; cell_best_idx = oi; }
+    cell_amax = fmax(cell_amax, __shfl_xor_sync(0xffffffffu, cell_amax, o));
+  }
+  if (lane_id == 0) { s_val[warp_id] = cell_best; s_idx[warp_id] = cell_best_idx; s_amax[warp_id] = cell_amax; }
+  __syncthreads();
+  {
+    cell_best = s_val[0]; cell_best_idx = s_idx[0]; cell_amax = s_amax[0];
+#pragma unroll
+    for (int w = 1; w < kPostThreads / 32; ++w) {
+      if (s_val[w] > cell_best) { cell_best = s_val[w]; cell_best_idx = s_idx[w]; }
+      cell_amax = fmax(cell_amax, s_amax[w]);
+    }
+  }
+  __syncthreads();  // s_val / s_idx are reused below
 
   // ---- 2. argmax of the x8 bilinear upsample (utils.py:153-175), OpenCV+IPP arithmetic: fma(S1-S0, f, S0) per axis
+  auto eval = [&](int ky, int kx, double* v_out, int* idx_out) {
+    const int iy = s_ci[ky], ix = s_ci[kx];
+    const int iy1 = min(iy + 1, hs - 1), ix1 = min(ix + 1, hs - 1);
+    const double fy = (double)s_cf[ky], fx = (double)s_cf[kx];
+    const double s00 = s_avg[iy * hs + ix], s01 = s_avg[iy * hs + ix1];
+    const double s10 = s_avg[iy1 * hs + ix], s11 = s_avg[iy1 * hs + ix1];
+    const double h0 = __fma_rn(__dsub_rn(s01, s00), fx, s00);
+    const double h1 = __fma_rn(__dsub_rn(s11, s10), fx, s10);
+    *v_out = __fma_rn(__dsub_rn(h1, h0), fy, h0);
+    *idx_out = (int)s_cd[ky] * S + (int)s_cd[kx];
+  };
   double best = -INFINITY;
   int best_idx = 0x7fffffff;
-  for (int ky = warp_id; ky < nc; ky += kPostThreads / 32) {
-    const int dy = s_cd[ky], iy = s_ci[ky];
-    const double fy = (double)s_cf[ky];
-    const double* row0 = s_avg + iy * hs;
-    const double* row1 = s_avg + min(iy + 1, hs - 1) * hs;
-    for (int kx = lane_id; kx < nc; kx += 32) {
-      const int ix = s_ci[kx], ix1 = min(ix + 1, hs - 1);
-      const double fx = (double)s_cf[kx];
-      const double s00 = row0[ix], s01 = row0[ix1], s10 = row1[ix], s11 = row1[ix1];
-      const double h0 = __fma_rn(__dsub_rn(s01, s00), fx, s00);
-      const double h1 = __fma_rn(__dsub_rn(s11, s10), fx, s10);
-      const double v = __fma_rn(__dsub_rn(h1, h0), fy, h0);
-      const int idx = dy * S + s_cd[kx];
-      if (v > best || (v == best && idx < best_idx)) { best = v; best_idx = idx; }
+  {  // seed: the 4 x 4 candidates around the largest cell (every thread computes the same bound, no sync needed)
+    const int r0 = cell_best_idx / hs, c0 = cell_best_idx - r0 * hs;
+    const int ky0 = max(2 * r0 - 1, 0), kx0 = max(2 * c0 - 1, 0);
+    const int ky = min(ky0 + (lane_id >> 2), nc - 1), kx = min(kx0 + (lane_id & 3), nc - 1);
+    double v = -INFINITY;
+    int idx = 0x7fffffff;
+    if (lane_id < 16) eval(ky, kx, &v, &idx);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    best = __shfl_sync(0xffffffffu, v, 0);  // only a bound: the index is recovered by the full scan below
+  }
+  const double prune = best - cell_amax * 9.1e-13;  // 2^-40 of the largest |cell|: far above the FMAs' rounding
+  best = -INFINITY;
+  // scan by source quad (cells (qy, qy+1) x (qx, qx+1)): one max-of-4 test prunes all of the quad's candidates
+  // (axis candidates of cell 0: k = 0..2, of cell i: k = 2i+1, 2i+2, of the last cell: k = 2*hs-1)
+  for (int qy = warp_id; qy < hs; qy += kPostThreads / 32) {
+    const int qy1 = min(qy + 1, hs - 1);
+    const int ky_lo = qy == 0 ? 0 : 2 * qy + 1, ky_hi = qy == hs - 1 ? nc - 1 : 2 * qy + 2;
+    for (int qx = lane_id; qx < hs; qx += 32) {
+      const int qx1 = min(qx + 1, hs - 1);
+      const double m4 = fmax(fmax(s_avg[qy * hs + qx], s_avg[qy * hs + qx1]), fmax(s_avg[qy1 * hs + qx], s_avg[qy1 * hs + qx1]));
+      if (m4 < prune) continue;
+      const int kx_lo = qx == 0 ? 0 : 2 * qx + 1, kx_hi = qx == hs - 1 ? nc - 1 : 2 * qx + 2;
+      for (int ky = ky_lo; ky <= ky_hi; ++ky)
+        for (int kx = kx_lo; kx <= kx_hi; ++kx) {
+          double v;
+          int idx;
+          eval(ky, kx, &v, &idx);
+          if (v > best || (v == best && idx < best_idx)) { best = v; best_idx = idx; }
+        }
     }
   }
 #pragma unroll

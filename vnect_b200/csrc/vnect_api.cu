@@ -807,7 +807,13 @@ static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, i
   p.frame_counter = h->d_counter;
   p.out2d = dev_out2d; p.out3d = dev_out3d;
   CU(h, cudaMemsetAsync(h->d_counter, 0, n_frames * sizeof(unsigned int), h->stream));
-  const size_t smem = (size_t)h->hs * h->hs * sizeof(double);
+  // averaged plane (float64) + the raw plane of every scale (float32)
+  const size_t smem = (size_t)h->hs * h->hs * (sizeof(double) + h->n_scales * sizeof(float));
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(h, cudaFuncSetAttribute(postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
   CU(h, launch_pdl(postprocess_kernel, dim3(n_frames * kJoints), dim3(kPostThreads), smem, h->stream, p));
   ++h->launches;
   return VNECT_OK;
