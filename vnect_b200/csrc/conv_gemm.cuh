@@ -21,7 +21,8 @@
 namespace vnect {
 
 constexpr int kBlockM = 128;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 256;      // 4 control warps + 4 epilogue warps
+constexpr int kGemmThreadsTma = 384;   // TMA epilogues: two epilogue warpgroups working on alternate 64-column chunks
 constexpr int kSmemBudget = 227 * 1024;
 
 enum EpiKind : int {
@@ -33,7 +34,8 @@ enum EpiKind : int {
 };
 
 constexpr int kEpiChunkBytes = kBlockM * 128;  // one 64-column fp16 chunk of a tile: 128 rows x 128 B
-constexpr int kOutStages = 2;
+constexpr int kOutStages = 1;   // per epilogue warpgroup (two groups alternate, so each ring needs one slot)
+constexpr int kEpiGroups = 2;
 constexpr int kResStages = 4;
 
 struct ConvGemmParams {
@@ -72,9 +74,10 @@ struct GemmCfg {
   static constexpr int A_BYTES = kBlockM * SWZ;
   static constexpr int B_BYTES = BLOCK_N * SWZ;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = (EPI == EPI_TMA)       ? kOutStages * kEpiChunkBytes
-                                   : (EPI == EPI_TMA_RES) ? (kOutStages + kResStages) * kEpiChunkBytes
+  static constexpr int EPI_BYTES = (EPI == EPI_TMA)       ? kEpiGroups * kOutStages * kEpiChunkBytes
+                                   : (EPI == EPI_TMA_RES) ? (kEpiGroups * kOutStages + kResStages) * kEpiChunkBytes
                                                           : 0;
+  static constexpr int THREADS = (EPI == EPI_TMA || EPI == EPI_TMA_RES) ? kGemmThreadsTma : kGemmThreads;
   static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
@@ -102,7 +105,7 @@ __device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
 }
 
 template <int BLOCK_N, int SWZ, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__((EPI == EPI_TMA || EPI == EPI_TMA_RES) ? kGemmThreadsTma : kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ ConvGemmParams p) {
@@ -114,8 +117,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;           // kOutStages x 16 KB (TMA epilogues only)
-  uint8_t* res_stage = out_stage + kOutStages * kEpiChunkBytes;    // kResStages x 16 KB (EPI_TMA_RES only)
+  uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;                        // 2 groups x kOutStages x 16 KB
+  uint8_t* res_stage = out_stage + kEpiGroups * kOutStages * kEpiChunkBytes;    // kResStages x 16 KB (EPI_TMA_RES)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -138,7 +141,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      // one arrive per epilogue warp that reads the accumulator: both groups when a tile has >= 2 chunks
+      mbar_init(&tmem_empty[s], (kTmaEpi && BLOCK_N >= 128) ? 8 : 4);
     }
     for (int s = 0; s < kResStages; ++s) {
       mbar_init(&res_full[s], 1);
@@ -293,13 +297,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp >= 4 && kTmaEpi) {
     // ================================================================ epilogue through smem staging + TMA store
+    // Two warpgroups (warps 4-7 and 8-11) take alternate 64-column chunks of the global chunk sequence, each with its
+    // own staging ring, so one group's TMEM load / barrier / store latencies hide behind the other's arithmetic.
+    constexpr int CH = BLOCK_N / 64;  // chunks per tile
+    const int grp = (warp - 4) >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    const bool leader = (threadIdx.x == 128);
+    const bool leader = (threadIdx.x == 128 + grp * 128);
     const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
+    uint8_t* my_out = out_stage + grp * kOutStages * kEpiChunkBytes;
     int acc = 0;
-    uint32_t acc_phase = 0, ctr = 0;
+    uint32_t acc_phase = 0, ctr = 0, mine = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = (tile / p.num_n_tiles) % p.num_m_tiles;
@@ -314,27 +323,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         cx = (t2 % p.tiles_x) * p.tw;
       }
       const int col_base = n_tile * BLOCK_N;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+      bool waited = false;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 64, ++ctr) {
+      for (int c = 0; c < CH; ++c, ++ctr) {
+        if ((ctr & 1u) != static_cast<uint32_t>(grp)) continue;
+        const int c0 = c * 64;
+        if (!waited) {
+          mbar_wait(&tmem_full[acc], acc_phase);
+          tc_fence_after();
+          waited = true;
+        }
         uint32_t v[64];
         tmem_ld_32x32(t_row + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         tmem_ld_32x32(t_row + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_ld_wait();
-        if (c0 + 64 >= BLOCK_N) {  // accumulator fully read: hand the TMEM stage back to the MMA warp early
+        if (c + 2 >= CH) {  // this group's last chunk of the tile: its share of the accumulator has been read
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        const int ob = ctr % kOutStages;
         const int rb = ctr % kResStages;
-        uint8_t* ostage = out_stage + ob * kEpiChunkBytes;
+        uint8_t* ostage = my_out + (mine % kOutStages) * kEpiChunkBytes;
+        ++mine;
         const uint8_t* rstage = res_stage + rb * kEpiChunkBytes;
         if constexpr (EPI == EPI_TMA_RES) mbar_wait(&res_full[rb], (ctr / kResStages) & 1);
         if (leader) bulk_wait_group_read<kOutStages - 1>();  // the store that last used `ostage` has read it
-        named_bar_sync(1, 128);
+        named_bar_sync(1 + grp, 128);
         const int col0 = col_base + c0;
         const bool relu = col0 < p.relu_cols;
 #pragma unroll
@@ -359,19 +374,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               f[2 * e + 1] += t.y;
             }
           }
-          if (relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-          }
           uint4 o;
-          o.x = pack_half2(f[0], f[1]);
-          o.y = pack_half2(f[2], f[3]);
-          o.z = pack_half2(f[4], f[5]);
-          o.w = pack_half2(f[6], f[7]);
+          if (relu) {
+            o.x = pack_half2_relu(f[0], f[1]);
+            o.y = pack_half2_relu(f[2], f[3]);
+            o.z = pack_half2_relu(f[4], f[5]);
+            o.w = pack_half2_relu(f[6], f[7]);
+          } else {
+            o.x = pack_half2(f[0], f[1]);
+            o.y = pack_half2(f[2], f[3]);
+            o.z = pack_half2(f[4], f[5]);
+            o.w = pack_half2(f[6], f[7]);
+          }
           *reinterpret_cast<uint4*>(ostage + off) = o;
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(1, 128);
+        named_bar_sync(1 + grp, 128);
         if (leader) {
           tma_store_5d(&tmap_out, ostage, col0, cx, cy, 0, cn);
           bulk_commit_group();

@@ -328,7 +328,7 @@ inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_pdl(kern, dim3(L.grid), dim3(kGemmThreads), Cfg::SMEM_BYTES, st, L.tmap_a, L.tmap_b, L.tmap_out, L.tmap_res,
+  return launch_pdl(kern, dim3(L.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, L.tmap_a, L.tmap_b, L.tmap_out, L.tmap_res,
                     L.tmap_a2, L.p);
 }
 
