@@ -68,6 +68,47 @@ def full(rep, label):
     print("wrote", label, len(rows) - 2, "kernels")
 
 
+def traffic():
+    """gpurun_out/step_traffic.csv (ncu metrics pass over one step) -> profiles/<tag>_step_traffic.txt + conv_traffic.json"""
+    import collections
+    import json
+    path = os.path.join(ROOT, "gpurun_out", "step_traffic.csv")
+    if not os.path.isfile(path):
+        return
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    per = collections.OrderedDict()
+    for r in rows:
+        d = per.setdefault(int(r[0]), {"name": r[4].split("(")[0].replace("void ", "").replace("vnect::", "")})
+        m, unit, val = r[-3], r[-2], float(r[-1].replace(",", ""))
+        if m.startswith("dram__bytes") or m.startswith("l1tex"):
+            val *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        if m == "gpu__time_duration.sum":
+            val *= {"ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}[unit]
+        d[m] = val
+    conv = [d for d in per.values() if "conv_gemm" in d["name"] or "stem_pool" in d["name"]]
+    ct = sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in conv)
+    tt = sum(d["gpu__time_duration.sum"] for d in conv)
+    out = ["# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
+           "sm__pipe_tensor_cycles_active...,l1tex__m_xbar2l1tex_read_bytes.sum --clock-control none",
+           "# one bench step (64 frames, 2 scales = 128 forwards), every launch",
+           f"# implicit-GEMM family ({len(conv)} launches): {tt:.1f} us, DRAM traffic {ct / 1e9:.3f} GB = "
+           f"{ct / len(conv) / 1e6:.1f} MB per launch on average, {ct / tt / 1e6:.2f} TB/s", "",
+           f"{'#':>3} {'us':>8} {'rd MB':>9} {'wr MB':>9} {'TB/s':>6} {'tensor%':>8} {'L2->SM MB':>10} {'L2->SM TB/s':>11}  kernel"]
+    for lid, d in per.items():
+        t, rd, wr = d["gpu__time_duration.sum"], d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+        l2 = d.get("l1tex__m_xbar2l1tex_read_bytes.sum", 0)
+        out.append(f"{lid:3d} {t:8.1f} {rd / 1e6:9.1f} {wr / 1e6:9.1f} {(rd + wr) / t / 1e6:6.2f} "
+                   f"{d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 0):8.1f} {l2 / 1e6:10.1f} "
+                   f"{l2 / t / 1e6:11.2f}  {d['name']}")
+    open(os.path.join(out_dir, f"{tag}_step_traffic.txt"), "w").write("\n".join(out) + "\n")
+    json.dump({"source": f"profiles/{tag}_step_traffic.txt (ncu, one step of 64 frames x 2 scales)",
+               "conv_family_launches": len(conv), "conv_family_dram_bytes_per_step": ct,
+               "conv_family_dram_bytes_per_launch_avg": ct / len(conv), "conv_family_time_us_under_ncu": tt,
+               "frames_per_step": 64}, open(os.path.join(out_dir, "conv_traffic.json"), "w"), indent=1)
+    print("wrote traffic:", ct / 1e9, "GB")
+
+
 launches()
+traffic()
 full("prof_conv.ncu-rep", "conv")
 full("prof_prepost.ncu-rep", "prepost")
