@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -232,7 +232,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -289,6 +288,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = n_streams * args.steps / float(t.item())
+    clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions (value and e2e)
 
     # ---------------------------------------------------------------- roofline of the conv-GEMM kernel family
     barrier()
