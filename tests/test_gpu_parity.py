@@ -499,3 +499,48 @@ def test_malformed_frames_raise(engine_w0):
         engine_w0.estimate(np.zeros((1, 1, 368, 3), np.uint8))  # degenerate height
     with pytest.raises(ValueError):
         engine_w0.estimate(np.zeros((2, 368, 368, 3), np.uint8), stream_ids=[0])  # ragged ids
+
+
+def _special_heatmaps(hs=46):
+    """Heat-maps that stress the tie / border semantics of the x8 upsample argmax."""
+    rng = np.random.default_rng(77)
+    yy, xx = np.mgrid[0:hs, 0:hs].astype(np.float32)
+    maps = []
+    maps.append(np.full((hs, hs), 0.25, np.float32))                      # constant: every sample ties -> (0, 0)
+    maps.append(xx / hs)                                                   # ramp: maximum on the replicated right border
+    maps.append(-(yy / hs))                                                # all negative, maximum on the top border
+    m = np.zeros((hs, hs), np.float32); m[10, 20] = m[10, 21] = 1.0; maps.append(m)      # horizontal 2-cell plateau
+    m = np.zeros((hs, hs), np.float32); m[30, 5] = m[31, 5] = 1.0; maps.append(m)        # vertical plateau
+    m = np.zeros((hs, hs), np.float32); m[7:9, 7:9] = 2.0; maps.append(m)                # 2 x 2 plateau
+    m = np.zeros((hs, hs), np.float32); m[3, 40] = 1.0; m[40, 3] = 1.0; maps.append(m)   # two equal far-apart peaks
+    m = np.zeros((hs, hs), np.float32); m[0, 0] = m[hs - 1, hs - 1] = 1.0; maps.append(m)  # equal peaks in two corners
+    m = (rng.standard_normal((hs, hs)) * 1e-30).astype(np.float32); maps.append(m)       # tiny magnitudes
+    m = (rng.standard_normal((hs, hs)) * 1e30).astype(np.float32); maps.append(m)        # huge magnitudes
+    m = -np.abs(rng.standard_normal((hs, hs))).astype(np.float32) - 5; maps.append(m)    # strictly negative noise
+    m = np.zeros((hs, hs), np.float32); m[22, :] = 1.0; maps.append(m)                   # a whole row ties
+    m = np.zeros((hs, hs), np.float32); m[:, 45] = 3.0; maps.append(m)                   # last column ties
+    for _ in range(8):
+        maps.append(rng.standard_normal((hs, hs)).astype(np.float32))                    # plain noise
+    return maps
+
+
+def test_argmax_tie_and_border_semantics():
+    """Unfiltered argmax against cv2.resize + np.argmax on adversarial maps, single scale (no averaging noise)."""
+    import cv2
+    from vnect_b200 import VNectEngine
+    specials = _special_heatmaps()
+    eng = VNectEngine(False, [1.0], max_frames=1, max_streams=1, filters=False)
+    try:
+        for start in range(0, len(specials), 21):
+            chunk = specials[start:start + 21]
+            hm = np.zeros((1, 46, 46, 21), np.float32)
+            for j, m in enumerate(chunk):
+                hm[0, :, :, j] = m
+            loc = np.zeros_like(hm)
+            _, _, raw = eng.postprocess((hm, loc, loc, loc), 1.0, (0, 0), [0], [1.0], [1.0])
+            for j, m in enumerate(chunk):
+                up = cv2.resize(m.astype(np.float64), (0, 0), fx=8, fy=8, interpolation=cv2.INTER_LINEAR)
+                want = np.unravel_index(np.argmax(up), up.shape)
+                assert tuple(raw[0, j]) == tuple(int(v) for v in want), (start + j, raw[0, j], want)
+    finally:
+        eng.close()
