@@ -53,6 +53,8 @@ struct ConvGemmParams {
   signed char tap_dx[16], tap_dy[16], tap_dp[16];  // [phase * taps + tap]
   uint32_t stage_tx_bytes;
   uint32_t res_tx_bytes;  // bytes of one residual chunk box (EPI_TMA_RES)
+  int reverse;            // 1: walk the tiles from last to first.  Consecutive layers alternate, so a layer starts on
+                          // the part of its input that the previous layer wrote last and that is still in L2
   int in_stride;          // 1, or 2: the conv samples its input at every second pixel (TMA element strides)
   int res_stride;         // 1, or 2: residual read at every second pixel of a 2H x 2W tensor
   // ---- epilogue
@@ -175,7 +177,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int it = blockIdx.x; it < total_tiles; it += gridDim.x) {
+        const int tile = p.reverse ? total_tiles - 1 - it : it;
         const int n_tile = tile % p.num_n_tiles;
         const int rest = tile / p.num_n_tiles;
         const int m_tile = rest % p.num_m_tiles;
@@ -269,7 +272,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool issuer = elect_one();
       {
         uint32_t ctr = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int it = blockIdx.x; it < total_tiles; it += gridDim.x) {
+          const int tile = p.reverse ? total_tiles - 1 - it : it;
           const int n_tile = tile % p.num_n_tiles;
           const int m_tile = (tile / p.num_n_tiles) % p.num_m_tiles;
           int cx, cy, cn;
@@ -309,7 +313,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* my_out = out_stage + grp * kOutStages * kEpiChunkBytes;
     int acc = 0;
     uint32_t acc_phase = 0, ctr = 0, mine = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int it = blockIdx.x; it < total_tiles; it += gridDim.x) {
+      const int tile = p.reverse ? total_tiles - 1 - it : it;
       const int n_tile = tile % p.num_n_tiles;
       const int m_tile = (tile / p.num_n_tiles) % p.num_m_tiles;
       int cx, cy, cn;
@@ -406,7 +411,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int r = q * 32 + lane;  // row of the tile owned by this thread
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int it = blockIdx.x; it < total_tiles; it += gridDim.x) {
+      const int tile = p.reverse ? total_tiles - 1 - it : it;
       const int n_tile = tile % p.num_n_tiles;
       const int rest = tile / p.num_n_tiles;
       const int m_tile = rest % p.num_m_tiles;

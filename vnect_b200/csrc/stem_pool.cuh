@@ -34,6 +34,7 @@ struct StemPoolParams {
   int band_tiles;       // ceil((2*ppb+1) * vw / 128) <= 8
   int bands_per_image;  // PH / ppb
   int num_items;        // images * bands_per_image
+  int reverse;          // 1: walk the bands from last to first (see ConvGemmParams::reverse)
   unsigned long long* dbg;  // optional [4] cycle counters (selftest only): wait-for-MMA, drain, barrier, pool
 };
 
@@ -95,7 +96,8 @@ __global__ void __launch_bounds__(kStemPoolThreads, 1) stem_pool_kernel(const __
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
+        const int item = p.reverse ? p.num_items - 1 - it : it;
         const int img = item / p.bands_per_image;
         const int q = item - img * p.bands_per_image;
         const uint8_t* img_base = p.x1 + static_cast<int64_t>(img) * 2 * p.plane_bytes;
@@ -170,7 +172,8 @@ __global__ void __launch_bounds__(kStemPoolThreads, 1) stem_pool_kernel(const __
     const int px_begin = (et >> 3) * run;
     const int px_end = min(px_begin + run, p.PW);
     uint32_t item_par = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, item_par ^= 1) {
+    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x, item_par ^= 1) {
+      const int item = p.reverse ? p.num_items - 1 - it : it;
       const int img = item / p.bands_per_image;
       const int q = item - img * p.bands_per_image;
       long long c0 = clock64(), c1 = 0;

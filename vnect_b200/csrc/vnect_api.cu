@@ -670,6 +670,15 @@ int vnect_finalize(vnect_t* h) {
   }
   h->conv_steps = 0;
   h->conv_steps = (int)h->steps.size();
+  // ping-pong tile order: layer i walks its tiles in the opposite direction of layer i-1, so it starts on the data
+  // that is still in the 126 MB L2 (the pyramid kernel writes forwards in ascending order, hence the stem reverses)
+  const char* order = getenv("VNECT_B200_TILE_ORDER");  // "forward" turns the ping-pong off (profiling A/B only)
+  const bool pingpong = !(order && strcmp(order, "forward") == 0);
+  for (size_t i = 0; i < h->steps.size(); ++i) {
+    const int rev = (pingpong && i % 2 == 0) ? 1 : 0;
+    if (h->steps[i].kind == 0) h->steps[i].launch.p.reverse = rev;
+    else h->steps[i].stem_pool.p.reverse = rev;
+  }
 
   h->vars.clear();  // host copies no longer needed
   h->finalized = true;
