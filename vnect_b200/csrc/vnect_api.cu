@@ -498,10 +498,10 @@ static int alloc_prepost(vnect_t* h) {
       float fx, fy;
       host_linear_coord(d, py.inv_scale[i], S, true, &ix, &fx);
       host_linear_coord(d, py.inv_scale[i], S, false, &iy, &fy);
-      ptab[i].xi0[d] = (short)ix;
-      ptab[i].xi1[d] = (short)std::min(ix + 1, S - 1);
-      ptab[i].xa0[d] = (short)std::nearbyint((1.f - fx) * 2048.f);
-      ptab[i].xa1[d] = (short)std::nearbyint(fx * 2048.f);
+      ptab[i].xt[d].x = (short)(3 * ix);
+      ptab[i].xt[d].y = (short)(3 * std::min(ix + 1, S - 1));
+      ptab[i].xt[d].z = (short)std::nearbyint((1.f - fx) * 2048.f);
+      ptab[i].xt[d].w = (short)std::nearbyint(fx * 2048.f);
       ptab[i].yj0[d] = (short)std::min(std::max(iy, 0), S - 1);
       ptab[i].yj1[d] = (short)std::min(std::max(iy + 1, 0), S - 1);
       ptab[i].yb0[d] = (short)std::nearbyint((1.f - fy) * 2048.f);
