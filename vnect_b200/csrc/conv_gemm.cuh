@@ -70,11 +70,14 @@ struct ConvGemmParams {
   int decimate;  // 1: only rows with even (y, x) are stored, at (y/2, x/2) -- feeds the stride-2 1x1 convs
 };
 
-template <int BLOCK_N, int SWZ, int EPI>
+// CG = 2: CTA pair (cluster of two SMs) working on one 256-row x BLOCK_N tile with tcgen05.mma.cta_group::2.  Each CTA
+// stages its own 128 rows of A and only HALF of the B tile, so the MMA reads (128 + BLOCK_N/2) smem rows per K step
+// instead of (128 + BLOCK_N): the single-CTA MMA rate is bound by exactly that operand traffic (~57 B/clk measured).
+template <int BLOCK_N, int SWZ, int EPI, int CG = 1>
 struct GemmCfg {
   static constexpr int BLOCK_K = SWZ / 2;  // fp16 elements per smem row
   static constexpr int A_BYTES = kBlockM * SWZ;
-  static constexpr int B_BYTES = BLOCK_N * SWZ;
+  static constexpr int B_BYTES = (BLOCK_N / CG) * SWZ;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = (EPI == EPI_TMA)       ? kEpiGroups * kOutStages * kEpiChunkBytes
                                    : (EPI == EPI_TMA_RES) ? (kEpiGroups * kOutStages + kResStages) * kEpiChunkBytes
@@ -91,6 +94,8 @@ struct GemmCfg {
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "epilogue walks 32-column chunks");
+  static_assert(CG == 1 || CG == 2, "a CTA pair at most");
+  static_assert(CG == 1 || (BLOCK_N / 2) % 8 == 0, "each CTA of a pair stages whole 8-row swizzle atoms of B");
   static_assert((EPI != EPI_TMA && EPI != EPI_TMA_RES) || BLOCK_N % 64 == 0, "TMA epilogue walks 64-column chunks");
 };
 
@@ -106,16 +111,19 @@ __device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
   return d;
 }
 
-template <int BLOCK_N, int SWZ, int EPI>
+template <int BLOCK_N, int SWZ, int EPI, int CG = 1>
 __global__ void __launch_bounds__((EPI == EPI_TMA || EPI == EPI_TMA_RES) ? kGemmThreadsTma : kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ ConvGemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI>;
+  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI, CG>;
   constexpr bool kTmaEpi = (EPI == EPI_TMA || EPI == EPI_TMA_RES);
   constexpr int BLOCK_K = Cfg::BLOCK_K;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr uint32_t IDESC = make_idesc_f16(kBlockM, BLOCK_N, false);
+  constexpr uint32_t IDESC = make_idesc_f16(kBlockM * CG, BLOCK_N, false);
+  // CTA pair: rank 0 leads (issues the MMAs, owns full_bar / tmem_empty); a pair takes GEMM rows 256 at a time
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -144,7 +152,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       // one arrive per epilogue warp that reads the accumulator: both groups when a tile has >= 2 chunks
-      mbar_init(&tmem_empty[s], (kTmaEpi && BLOCK_N >= 128) ? 8 : 4);
+      mbar_init(&tmem_empty[s], CG * ((kTmaEpi && BLOCK_N >= 128) ? 8 : 4));
     }
     for (int s = 0; s < kResStages; ++s) {
       mbar_init(&res_full[s], 1);
@@ -154,9 +162,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if constexpr (EPI == EPI_TMA_RES) tma_prefetch_desc(&tmap_res);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // PDL: everything above (barrier init, descriptor prefetch, TMEM allocation) may overlap the previous layer's tail;
@@ -164,7 +176,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   pdl_launch_dependents();
   pdl_wait();
 
-  const int total_tiles = p.phases * p.num_m_tiles * p.num_n_tiles;
+  const int m_units = (p.num_m_tiles + CG - 1) / CG;  // with an odd tile count the last pair's second half is all
+                                                      // out of bounds: zero-filled loads, fully clipped stores
+  const int total_tiles = p.phases * m_units * p.num_n_tiles;
   const int k_iters = p.taps * p.cblocks + p.cblocks2;
 
   // NOTE on the single-lane roles below: the whole warp runs each loop converged and only the issuing instructions are
@@ -177,12 +191,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int it = blockIdx.x; it < total_tiles; it += gridDim.x) {
+      for (int it = worker; it < total_tiles; it += n_workers) {
         const int tile = p.reverse ? total_tiles - 1 - it : it;
         const int n_tile = tile % p.num_n_tiles;
         const int rest = tile / p.num_n_tiles;
-        const int m_tile = rest % p.num_m_tiles;
-        const int ph = rest / p.num_m_tiles;
+        const int m_tile = (rest % m_units) * CG + cta_rank;
+        const int ph = rest / m_units;
         int cx, cy, cn;
         if (p.mode == 0) {
           cx = m_tile * kBlockM;
@@ -195,17 +209,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           cy = (t2 / p.tiles_x) * p.th;
           cx = (t2 % p.tiles_x) * p.tw;
         }
-        const int b_row = ph * p.b_rows_per_phase + n_tile * BLOCK_N;
+        const int b_row = ph * p.b_rows_per_phase + n_tile * BLOCK_N + cta_rank * (BLOCK_N / CG);
         for (int t = 0; t < p.taps; ++t) {
           const int ti = ph * p.taps + t;
           const int ax = cx * p.in_stride + p.tap_dx[ti], ay = cy * p.in_stride + p.tap_dy[ti], ap = p.tap_dp[ti];
           for (int cb = 0; cb < p.cblocks; ++cb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (issuer) {
-              mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-              tma_load_5d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
-              tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
+              if constexpr (CG == 2) {  // both CTAs' bytes are counted on the leader's barrier
+                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * p.stage_tx_bytes);
+                tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
+                tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
+                tma_load_5d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
+                tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
+              }
             }
             __syncwarp();
             if (++stage == STAGES) {
@@ -217,12 +237,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int cb = 0; cb < p.cblocks2; ++cb) {  // folded projection shortcut: second A tensor, 1x1
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (issuer) {
-            mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
             uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-            tma_load_5d(sa, &tmap_a2, &full_bar[stage], cb * BLOCK_K, cx, cy, 0, cn);
-            tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (p.taps * p.cblocks + cb) * BLOCK_K, b_row);
+            if constexpr (CG == 2) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * p.stage_tx_bytes);
+              tma_load_5d_pair(sa, &tmap_a2, &full_bar[stage], cb * BLOCK_K, cx, cy, 0, cn);
+              tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (p.taps * p.cblocks + cb) * BLOCK_K, b_row);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
+              tma_load_5d(sa, &tmap_a2, &full_bar[stage], cb * BLOCK_K, cx, cy, 0, cn);
+              tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (p.taps * p.cblocks + cb) * BLOCK_K, b_row);
+            }
           }
           __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+      if constexpr (CG == 2) {
+        // drain: the leader's multicast commits still arrive on this CTA's empty barriers after the last load was
+        // issued; do not let the CTA retire (and its smem be reused) before every slot has been released
+        for (int s2 = 0; s2 < STAGES; ++s2) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -233,12 +270,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ================================================================ MMA issuer (one elected lane issues)
     const bool issuer = elect_one();
-    {
+    if (cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -250,9 +287,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t b_desc = make_kmajor_desc<SWZ>(a_addr + Cfg::A_BYTES);
           if (issuer) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k)  // +32 B per K step = +2 in the descriptor's (addr >> 4) field
-              umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
-            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            for (int k = 0; k < BLOCK_K / 16; ++k) {  // +32 B per K step = +2 in the descriptor's (addr >> 4) field
+              if constexpr (CG == 2) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+            if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]);
+            else umma_commit(&empty_bar[stage]);
           }
           __syncwarp();
           if (++stage == STAGES) {
@@ -260,7 +301,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             phase ^= 1;
           }
         }
-        if (issuer) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (issuer) {  // accumulator complete -> epilogue (of both CTAs of a pair)
+          if constexpr (CG == 2) umma_commit_pair(&tmem_full[acc]);
+          else umma_commit(&tmem_full[acc]);
+        }
         __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -272,10 +316,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool issuer = elect_one();
       {
         uint32_t ctr = 0;
-        for (int it = blockIdx.x; it < total_tiles; it += gridDim.x) {
+        for (int it = worker; it < total_tiles; it += n_workers) {
           const int tile = p.reverse ? total_tiles - 1 - it : it;
           const int n_tile = tile % p.num_n_tiles;
-          const int m_tile = (tile / p.num_n_tiles) % p.num_m_tiles;
+          const int m_tile = ((tile / p.num_n_tiles) % m_units) * CG + cta_rank;
           int cx, cy, cn;
           if (p.mode == 0) {
             cx = m_tile * kBlockM; cy = 0; cn = 0;
@@ -313,10 +357,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* my_out = out_stage + grp * kOutStages * kEpiChunkBytes;
     int acc = 0;
     uint32_t acc_phase = 0, ctr = 0, mine = 0;
-    for (int it = blockIdx.x; it < total_tiles; it += gridDim.x) {
+    for (int it = worker; it < total_tiles; it += n_workers) {
       const int tile = p.reverse ? total_tiles - 1 - it : it;
       const int n_tile = tile % p.num_n_tiles;
-      const int m_tile = (tile / p.num_n_tiles) % p.num_m_tiles;
+      const int m_tile = ((tile / p.num_n_tiles) % m_units) * CG + cta_rank;
       int cx, cy, cn;
       if (p.mode == 0) {
         cx = m_tile * kBlockM; cy = 0; cn = 0;
@@ -346,7 +390,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (c + 2 >= CH) {  // this group's last chunk of the tile: its share of the accumulator has been read
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[acc]);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         }
         const int rb = ctr % kResStages;
         uint8_t* ostage = my_out + (mine % kOutStages) * kEpiChunkBytes;
@@ -411,12 +458,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int r = q * 32 + lane;  // row of the tile owned by this thread
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int it = blockIdx.x; it < total_tiles; it += gridDim.x) {
+    for (int it = worker; it < total_tiles; it += n_workers) {
       const int tile = p.reverse ? total_tiles - 1 - it : it;
       const int n_tile = tile % p.num_n_tiles;
       const int rest = tile / p.num_n_tiles;
-      const int m_tile = rest % p.num_m_tiles;
-      const int ph = rest / p.num_m_tiles;
+      const int m_tile = (rest % m_units) * CG + cta_rank;
+      const int ph = rest / m_units;
       bool valid;
       int n, y, x;
       if (p.mode == 0) {
@@ -434,7 +481,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int ly = r / p.tw, lx = r - ly * p.tw;
         y = (t2 / p.tiles_x) * p.th + ly;
         x = (t2 % p.tiles_x) * p.tw + lx;
-        valid = (ly < p.th) && (y < p.H) && (x < p.W);
+        valid = (ly < p.th) && (y < p.H) && (x < p.W) && (n < p.NB);
       }
       int oy, ox;
       if (p.decimate) {
@@ -554,17 +601,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[acc]);
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA may retire while its partner can still signal it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 

@@ -97,15 +97,24 @@ struct ConvSpec {
   // the K dimension; `w` is then [n_pad][cin_pad + cin2_pad]
   const __half* in2 = nullptr;
   int cin2_pad = 0;
+  // 2: run on CTA pairs (tcgen05 cta_group::2, 256-row tiles); 1: one CTA per tile
+  int cg = 1;
 };
 
 struct ConvLaunch {
   CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res, tmap_a2;
   ConvGemmParams p;
-  int block_n = 0, swz = 128, epi = 0, grid = 0;
+  int block_n = 0, swz = 128, epi = 0, grid = 0, cg = 1;
   size_t smem = 0;
   double flops = 0;  // algorithmic: 2 * valid rows * n_valid * taps * real Cin is tracked by the caller; this is GEMM work
 };
+
+// persistent grid: one CTA (or CTA pair) per SM (pair of SMs), never more workers than tiles
+inline int conv_grid(const ConvGemmParams& p, int cg, int num_sms) {
+  const int units = p.phases * ((p.num_m_tiles + cg - 1) / cg) * p.num_n_tiles;
+  const int workers = num_sms / cg;
+  return cg * (units < workers ? units : workers);
+}
 
 inline void choose_tile(int H, int W, int* tw_out, int* th_out) {
   int best_tiles = 1 << 30, btw = 1, bth = 1;
@@ -132,6 +141,11 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
   L->swz = swz;
   L->block_n = s.block_n;
   L->epi = s.epi;
+  L->cg = s.cg;
+  if (s.cg != 1 && (s.cg != 2 || s.kind == CONV_STEM7 || (s.block_n / 2) % 8 != 0)) {
+    if (err) *err = "unsupported CTA-pair configuration";
+    return false;
+  }
   if (s.n_pad % s.block_n != 0) {
     if (err) *err = "n_pad must be a multiple of block_n";
     return false;
@@ -245,11 +259,12 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     k_total = 7 * 32;
   }
   const int a_stride = (s.kind == CONV_STEM7) ? 1 : s.in_stride;
-  p.stage_tx_bytes = (uint32_t)(box[0] * (box[1] / a_stride) * (box[2] / a_stride) * 2 + (uint32_t)s.block_n * block_k * 2);
+  // per CTA: its A rows plus its share of the B tile (half of it in a CTA pair)
+  p.stage_tx_bytes = (uint32_t)(box[0] * (box[1] / a_stride) * (box[2] / a_stride) * 2 + (uint32_t)(s.block_n / s.cg) * block_k * 2);
   if (!encode_tmap(&L->tmap_a, s.in, 5, dims, strides, box, swz, err, a_stride != 1 ? estr : nullptr)) return false;
   uint64_t bd[2] = {(uint64_t)k_total, (uint64_t)p.phases * s.n_pad};
   uint64_t bs[1] = {(uint64_t)k_total * 2};
-  uint32_t bb[2] = {(uint32_t)block_k, (uint32_t)s.block_n};
+  uint32_t bb[2] = {(uint32_t)block_k, (uint32_t)(s.block_n / s.cg)};
   if (!encode_tmap(&L->tmap_b, s.w, 2, bd, bs, bb, swz, err)) return false;
   L->tmap_out = L->tmap_a;  // placeholders for the epilogues that do not use them
   L->tmap_res = L->tmap_a;
@@ -295,8 +310,7 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
       p.res_tx_bytes = (ob[1] / s.res_stride) * (ob[2] / s.res_stride) * 128;
     }
   }
-  const int total = p.phases * p.num_m_tiles * p.num_n_tiles;
-  L->grid = total < num_sms ? total : num_sms;
+  L->grid = conv_grid(p, s.cg, num_sms);
   L->flops = 2.0 * p.phases * (double)p.M * s.n_pad * k_total;
   return true;
 }
@@ -304,35 +318,63 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
 // Launch with programmatic stream serialization (PDL): the kernel may start while its predecessor drains; each of our
 // kernels calls pdl_wait() before it touches the predecessor's output.
 template <typename Kern, typename... Args>
-inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl_cluster(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                                      Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (cluster_x > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cluster_x;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kern, args...);
 }
+template <typename Kern, typename... Args>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  return launch_pdl_cluster(kern, grid, block, smem, st, 1, args...);
+}
 
-template <int BLOCK_N, int SWZ, int EPI>
+template <int BLOCK_N, int SWZ, int EPI, int CG = 1>
 inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
-  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI>;
+  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI, CG>;
   static bool attr_set = false;
-  auto kern = conv_gemm_kernel<BLOCK_N, SWZ, EPI>;
+  auto kern = conv_gemm_kernel<BLOCK_N, SWZ, EPI, CG>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  return launch_pdl(kern, dim3(L.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, L.tmap_a, L.tmap_b, L.tmap_out, L.tmap_res,
-                    L.tmap_a2, L.p);
+  return launch_pdl_cluster(kern, dim3(L.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, CG, L.tmap_a, L.tmap_b,
+                            L.tmap_out, L.tmap_res, L.tmap_a2, L.p);
 }
 
 inline cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
+  if (L.cg == 2) {  // CTA pairs: the production epilogues only
+    if (L.swz != 128) return cudaErrorInvalidConfiguration;
+    if (L.epi == EPI_TMA) {
+      if (L.block_n == 64) return launch_one<64, 128, EPI_TMA, 2>(L, st);
+      if (L.block_n == 128) return launch_one<128, 128, EPI_TMA, 2>(L, st);
+      if (L.block_n == 256) return launch_one<256, 128, EPI_TMA, 2>(L, st);
+    }
+    if (L.epi == EPI_TMA_RES) {
+      if (L.block_n == 64) return launch_one<64, 128, EPI_TMA_RES, 2>(L, st);
+      if (L.block_n == 128) return launch_one<128, 128, EPI_TMA_RES, 2>(L, st);
+      if (L.block_n == 256) return launch_one<256, 128, EPI_TMA_RES, 2>(L, st);
+    }
+    if (L.epi == EPI_PLANAR_F32 && L.block_n == 96) return launch_one<96, 128, EPI_PLANAR_F32, 2>(L, st);
+    if (L.epi == EPI_DECONV_HEAD && L.block_n == 192) return launch_one<192, 128, EPI_DECONV_HEAD, 2>(L, st);
+    return cudaErrorInvalidConfiguration;
+  }
   if (L.swz == 64 && L.block_n == 64 && L.epi == EPI_NHWC_F16) return launch_one<64, 64, EPI_NHWC_F16>(L, st);
   if (L.swz == 128 && L.epi == EPI_NHWC_F16) {
     if (L.block_n == 64) return launch_one<64, 128, EPI_NHWC_F16>(L, st);

@@ -3,6 +3,7 @@
 //   build: make -C vnect_b200/csrc selftest      run (on a B200): build/selftest
 #include <cmath>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "conv_plan.cuh"
@@ -77,6 +78,7 @@ struct Case {
   int relu_cols, decimate;
   int in_stride = 1, res_stride = 1;
   int cin2 = 0;  // folded shortcut: second input tensor with cin2 channels (1x1 only)
+  int cg = 1;    // 2: CTA pairs (tcgen05 cta_group::2)
 };
 
 static int run_case(const Case& c, int num_sms, bool timing) {
@@ -94,6 +96,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   s.decimate = c.decimate;
   s.in_stride = c.in_stride;
   s.res_stride = c.res_stride;
+  s.cg = c.cg;
   const int phases = c.kind == CONV_DECONV4 ? 4 : 1;
   const int taps = c.kind == CONV_1x1 ? 1 : c.kind == CONV_3x3 ? 9 : c.kind == CONV_DECONV4 ? 4 : 7;
   const int k_total = c.kind == CONV_STEM7 ? 7 * 32 : taps * c.cin_pad + c.cin2;
@@ -488,6 +491,17 @@ int main(int argc, char** argv) {
   };
   int fails = 0;
   for (const auto& c : cases) fails += run_case(c, sms, true);
+  // every production epilogue again on CTA pairs (odd tile counts included: 2x92x92 1x1 = 133 tiles)
+  std::vector<std::string> pair_names;
+  pair_names.reserve(cases.size());
+  for (const auto& c : cases) {
+    if (c.kind == CONV_STEM7 || c.epi == EPI_NHWC_F16) continue;
+    Case c2 = c;
+    pair_names.push_back(std::string("PAIR ") + c.name);
+    c2.name = pair_names.back().c_str();
+    c2.cg = 2;
+    fails += run_case(c2, sms, true);
+  }
   fails += run_stem2(2, 368, sms);
   fails += run_stem2(1, 448, sms);
   fails += run_stem_pool(2, 368, sms);
@@ -510,6 +524,25 @@ int main(int argc, char** argv) {
         {"BIG TMARES 1x1 256->1024 +res 23x23 nb128", CONV_1x1, 128, 23, 23, 256, 1024, 1024, 256, EPI_TMA_RES, true, true, 1024, 0},
     };
     for (const auto& c : bigc) fails += run_case(c, sms, true);
+    std::vector<Case> pairc = {
+        {"BIG TMA 3x3 512->512 23x23 nb64", CONV_3x3, 64, 23, 23, 512, 512, 512, 256, EPI_TMA, true, false, 512, 0},
+        {"BIG TMA 3x3 256->256 23x23 nb128", CONV_3x3, 128, 23, 23, 256, 256, 256, 256, EPI_TMA, true, false, 256, 0},
+        {"BIG TMA 3x3 128->128 46x46 nb128", CONV_3x3, 128, 46, 46, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0},
+        {"BIG TMA 3x3 64->64 92x92 nb128", CONV_3x3, 128, 92, 92, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0},
+        {"BIG TMA 1x1 1024->256 23x23 nb128", CONV_1x1, 128, 23, 23, 1024, 256, 256, 256, EPI_TMA, true, false, 256, 0},
+        {"BIG TMA 1x1 512->128 46x46 nb128", CONV_1x1, 128, 46, 46, 512, 128, 128, 128, EPI_TMA, true, false, 128, 0},
+        {"BIG TMARES 1x1 256->1024 +res 23x23 nb128", CONV_1x1, 128, 23, 23, 256, 1024, 1024, 256, EPI_TMA_RES, true, true, 1024, 0},
+        {"BIG TMARES 1x1 128->512 +res 46x46 nb128", CONV_1x1, 128, 46, 46, 128, 512, 512, 256, EPI_TMA_RES, true, true, 512, 0},
+        {"BIG TMARES 1x1 64->256 +res 92x92 nb128", CONV_1x1, 128, 92, 92, 64, 256, 256, 256, EPI_TMA_RES, true, true, 256, 0},
+    };
+    for (const auto& c : pairc) {  // same layer on single CTAs and on CTA pairs, timings side by side
+      fails += run_case(c, sms, true);
+      Case c2 = c;
+      std::string nm = std::string("PAIR ") + c.name;
+      c2.name = nm.c_str();
+      c2.cg = 2;
+      fails += run_case(c2, sms, true);
+    }
   }
   printf("SELFTEST %s (%d failing cases)\n", fails == 0 ? "PASSED" : "FAILED", fails);
   return fails == 0 ? 0 : 1;

@@ -283,6 +283,16 @@ static int pick_block_n(int n, int cap_fw) {
   return n >= 256 ? 256 : n >= 128 ? 128 : 64;
 }
 
+// CTA pairs (tcgen05 cta_group::2) pay off where the MMA's smem operand reads are the limit: N >= 128 tiles
+// (measured 5-8 % on the tensor-bound layers, nothing at N = 64).  VNECT_B200_PAIRS=0 / 64 moves the threshold (A/B).
+static int pick_cg(int block_n) {
+  static const int min_n = [] {
+    const char* e = getenv("VNECT_B200_PAIRS");
+    return e ? (atoi(e) > 0 ? atoi(e) : 1 << 30) : 128;
+  }();
+  return block_n >= min_n ? 2 : 1;
+}
+
 static int add_conv(vnect_t* h, const std::string& scope, int k, const std::string& in, const std::string& out,
                     int cin, int cout, const ConvOpts& o) {
   const Act& ai = h->acts.at(in);
@@ -302,7 +312,7 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
   s.kind = k == 1 ? CONV_1x1 : CONV_3x3;
   s.NB = h->cap_fw; s.H = OH; s.W = OW;
   s.in = ai.p; s.cin_pad = cin_pad; s.in_stride = o.in_stride;
-  s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout, h->cap_fw);
+  s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout, h->cap_fw); s.cg = pick_cg(s.block_n);
   s.bias = db; s.relu_cols = o.relu ? cout : 0;
   if (!o.residual.empty()) {
     const Act& r = h->acts.at(o.residual);
@@ -351,7 +361,7 @@ static int add_proj_tail(vnect_t* h, const std::string& scope2c, const std::stri
   s.kind = CONV_1x1;
   s.NB = h->cap_fw; s.H = ab.H; s.W = ab.W;
   s.in = ab.p; s.cin_pad = mid; s.in2 = ax.p; s.cin2_pad = cin;
-  s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout, h->cap_fw);
+  s.w = dw; s.n_pad = cout; s.n_valid = cout; s.block_n = pick_block_n(cout, h->cap_fw); s.cg = pick_cg(s.block_n);
   s.bias = db; s.relu_cols = cout;
   s.out = h->acts.at(out).p; s.ldc = cout; s.epi = EPI_TMA;
   Step st;
@@ -389,8 +399,7 @@ static void set_batch(ConvLaunch& L, int nb, int sms) {
   p.NB = nb;
   p.M = nb * p.H * p.W;
   p.num_m_tiles = p.mode == 0 ? (p.M + kBlockM - 1) / kBlockM : nb * p.tiles_x * p.tiles_y;
-  const int total = p.phases * p.num_m_tiles * p.num_n_tiles;
-  L.grid = total < sms ? total : sms;
+  L.grid = conv_grid(p, L.cg, sms);
 }
 
 // cv2 INTER_LINEAR coordinate rule on the host, identical arithmetic to cv_linear_coord (double -> float)
@@ -642,7 +651,7 @@ int vnect_finalize(vnect_t* h) {
     ConvSpec s;
     s.kind = CONV_DECONV4;
     s.NB = nb; s.H = ai.H; s.W = ai.W; s.in = ai.p; s.cin_pad = 256;
-    s.w = dw; s.n_pad = 192; s.n_valid = 191; s.block_n = 192; s.bias = db; s.relu_cols = 128;
+    s.w = dw; s.n_pad = 192; s.n_valid = 191; s.block_n = 192; s.bias = db; s.relu_cols = 128; s.cg = pick_cg(192);
     s.out = h->acts.at("res5c_branch2a_feat").p; s.ldc = 256; s.epi = EPI_DECONV_HEAD;
     Step st;
     st.kind = 0; st.name = "res5c_deconv_head";
@@ -660,7 +669,7 @@ int vnect_finalize(vnect_t* h) {
     ConvSpec s;
     s.kind = CONV_1x1;
     s.NB = nb; s.H = ai.H; s.W = ai.W; s.in = ai.p; s.cin_pad = 128;
-    s.w = dw; s.n_pad = 96; s.n_valid = 84; s.block_n = 96; s.bias = nullptr; s.relu_cols = 0;
+    s.w = dw; s.n_pad = 96; s.n_valid = 84; s.block_n = 96; s.bias = nullptr; s.relu_cols = 0; s.cg = pick_cg(96);
     s.out = h->maps; s.ldc = 0; s.epi = EPI_PLANAR_F32;
     Step st;
     st.kind = 0; st.name = "res5c_branch2c";
