@@ -73,24 +73,29 @@ struct ConvGemmParams {
 // CG = 2: CTA pair (cluster of two SMs) working on one 256-row x BLOCK_N tile with tcgen05.mma.cta_group::2.  Each CTA
 // stages its own 128 rows of A and only HALF of the B tile, so the MMA reads (128 + BLOCK_N/2) smem rows per K step
 // instead of (128 + BLOCK_N): the single-CTA MMA rate is bound by exactly that operand traffic (~57 B/clk measured).
-template <int BLOCK_N, int SWZ, int EPI, int CG = 1>
+// BRES: the whole weight matrix of the layer (<= kMaxResidentKBlocks K blocks, one N tile) is loaded into smem once
+// per CTA and stays there; the pipeline stages then carry activations only.  For the 64-channel 3x3 convs this cuts
+// the L2->SM traffic per tile from 9 x 24 KB to 9 x 16 KB, and those layers are bound by exactly that traffic.
+constexpr int kMaxResidentKBlocks = 9;
+template <int BLOCK_N, int SWZ, int EPI, int CG = 1, bool BRES = false>
 struct GemmCfg {
   static constexpr int BLOCK_K = SWZ / 2;  // fp16 elements per smem row
   static constexpr int A_BYTES = kBlockM * SWZ;
   static constexpr int B_BYTES = (BLOCK_N / CG) * SWZ;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = BRES ? A_BYTES : A_BYTES + B_BYTES;
+  static constexpr int BRES_BYTES = BRES ? kMaxResidentKBlocks * B_BYTES : 0;
   static constexpr int EPI_BYTES = (EPI == EPI_TMA)       ? kEpiGroups * kOutStages * kEpiChunkBytes
                                    : (EPI == EPI_TMA_RES) ? (kEpiGroups * kOutStages + kResStages) * kEpiChunkBytes
                                                           : 0;
   static constexpr int THREADS = (EPI == EPI_TMA || EPI == EPI_TMA_RES) ? kGemmThreadsTma : kGemmThreads;
-  static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - EPI_BYTES - BRES_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                         : (2 * BLOCK_N <= 64)  ? 64
                                         : (2 * BLOCK_N <= 128) ? 128
                                         : (2 * BLOCK_N <= 256) ? 256
                                                                : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "epilogue walks 32-column chunks");
@@ -111,12 +116,13 @@ __device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
   return d;
 }
 
-template <int BLOCK_N, int SWZ, int EPI, int CG = 1>
+template <int BLOCK_N, int SWZ, int EPI, int CG = 1, bool BRES = false>
 __global__ void __launch_bounds__((EPI == EPI_TMA || EPI == EPI_TMA_RES) ? kGemmThreadsTma : kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ ConvGemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI, CG>;
+  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI, CG, BRES>;
+  static_assert(!BRES || CG == 1, "resident weights are a single-CTA variant");
   constexpr bool kTmaEpi = (EPI == EPI_TMA || EPI == EPI_TMA_RES);
   constexpr int BLOCK_K = Cfg::BLOCK_K;
   constexpr int STAGES = Cfg::STAGES;
@@ -127,16 +133,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;                        // 2 groups x kOutStages x 16 KB
+  uint8_t* b_res = smem + STAGES * Cfg::STAGE_BYTES;                            // BRES: k_iters x B_BYTES, resident
+  uint8_t* out_stage = b_res + Cfg::BRES_BYTES;                                 // 2 groups x kOutStages x 16 KB
   uint8_t* res_stage = out_stage + kEpiGroups * kOutStages * kEpiChunkBytes;    // kResStages x 16 KB (EPI_TMA_RES)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BRES_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint64_t* res_full = bars + 2 * STAGES + 4;
   uint64_t* res_empty = bars + 2 * STAGES + 4 + kResStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + 2 * kResStages);
+  uint64_t* bres_full = bars + 2 * STAGES + 4 + 2 * kResStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5 + 2 * kResStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -158,6 +166,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&res_full[s], 1);
       mbar_init(&res_empty[s], 1);
     }
+    mbar_init(bres_full, 1);
     if constexpr (kTmaEpi) tma_prefetch_desc(&tmap_out);
     if constexpr (EPI == EPI_TMA_RES) tma_prefetch_desc(&tmap_res);
     fence_barrier_init();
@@ -189,6 +198,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ================================================================ TMA producer
     const bool issuer = elect_one();
     {
+      if constexpr (BRES) {  // weights are constants: no dependency on the previous layer, but pdl_wait came first anyway
+        if (issuer && worker < total_tiles) {
+          mbar_arrive_expect_tx(bres_full, static_cast<uint32_t>(k_iters) * Cfg::B_BYTES);
+          for (int kb = 0; kb < k_iters; ++kb)
+            tma_load_2d(b_res + kb * Cfg::B_BYTES, &tmap_b, bres_full, kb * BLOCK_K, 0);
+        }
+        __syncwarp();
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int it = worker; it < total_tiles; it += n_workers) {
@@ -224,7 +241,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               } else {
                 mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
                 tma_load_5d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
-                tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
+                if constexpr (!BRES)
+                  tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
               }
             }
             __syncwarp();
@@ -275,6 +293,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if constexpr (BRES) {
+        if (worker < total_tiles) mbar_wait(bres_full, 0);
+      }
       for (int tile = worker; tile < total_tiles; tile += n_workers) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -284,7 +305,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t a_desc = make_kmajor_desc<SWZ>(a_addr);
-          const uint64_t b_desc = make_kmajor_desc<SWZ>(a_addr + Cfg::A_BYTES);
+          const uint64_t b_desc = BRES ? make_kmajor_desc<SWZ>(smem_u32(b_res + kb * Cfg::B_BYTES))
+                                       : make_kmajor_desc<SWZ>(a_addr + Cfg::A_BYTES);
           if (issuer) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {  // +32 B per K step = +2 in the descriptor's (addr >> 4) field

@@ -99,12 +99,14 @@ struct ConvSpec {
   int cin2_pad = 0;
   // 2: run on CTA pairs (tcgen05 cta_group::2, 256-row tiles); 1: one CTA per tile
   int cg = 1;
+  // 1: keep the layer's whole weight matrix resident in smem (single N tile, <= kMaxResidentKBlocks K blocks, no pairs)
+  int b_resident = 0;
 };
 
 struct ConvLaunch {
   CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res, tmap_a2;
   ConvGemmParams p;
-  int block_n = 0, swz = 128, epi = 0, grid = 0, cg = 1;
+  int block_n = 0, swz = 128, epi = 0, grid = 0, cg = 1, b_resident = 0;
   size_t smem = 0;
   double flops = 0;  // algorithmic: 2 * valid rows * n_valid * taps * real Cin is tracked by the caller; this is GEMM work
 };
@@ -142,6 +144,7 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
   L->block_n = s.block_n;
   L->epi = s.epi;
   L->cg = s.cg;
+  L->b_resident = s.b_resident;
   if (s.cg != 1 && (s.cg != 2 || s.kind == CONV_STEM7 || (s.block_n / 2) % 8 != 0)) {
     if (err) *err = "unsupported CTA-pair configuration";
     return false;
@@ -259,8 +262,14 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     k_total = 7 * 32;
   }
   const int a_stride = (s.kind == CONV_STEM7) ? 1 : s.in_stride;
-  // per CTA: its A rows plus its share of the B tile (half of it in a CTA pair)
-  p.stage_tx_bytes = (uint32_t)(box[0] * (box[1] / a_stride) * (box[2] / a_stride) * 2 + (uint32_t)(s.block_n / s.cg) * block_k * 2);
+  // per CTA: its A rows plus its share of the B tile (half of it in a CTA pair; nothing when the weights are resident)
+  p.stage_tx_bytes = (uint32_t)(box[0] * (box[1] / a_stride) * (box[2] / a_stride) * 2 +
+                                (s.b_resident ? 0u : (uint32_t)(s.block_n / s.cg) * block_k * 2));
+  if (s.b_resident && (s.cg != 1 || p.num_n_tiles != 1 || p.phases != 1 || s.in2 || k_total / block_k > kMaxResidentKBlocks ||
+                       s.block_n != 64 || s.epi != EPI_TMA || swz != 128)) {
+    if (err) *err = "resident weights need a single-tile 64-column EPI_TMA layer of at most 9 K blocks";
+    return false;
+  }
   if (!encode_tmap(&L->tmap_a, s.in, 5, dims, strides, box, swz, err, a_stride != 1 ? estr : nullptr)) return false;
   uint64_t bd[2] = {(uint64_t)k_total, (uint64_t)p.phases * s.n_pad};
   uint64_t bs[1] = {(uint64_t)k_total * 2};
@@ -358,7 +367,22 @@ inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
                             L.tmap_out, L.tmap_res, L.tmap_a2, L.p);
 }
 
+template <int BLOCK_N, int SWZ, int EPI>
+inline cudaError_t launch_one_bres(const ConvLaunch& L, cudaStream_t st) {
+  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI, 1, true>;
+  static bool attr_set = false;
+  auto kern = conv_gemm_kernel<BLOCK_N, SWZ, EPI, 1, true>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return launch_pdl(kern, dim3(L.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, L.tmap_a, L.tmap_b, L.tmap_out,
+                    L.tmap_res, L.tmap_a2, L.p);
+}
+
 inline cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
+  if (L.b_resident) return launch_one_bres<64, 128, EPI_TMA>(L, st);
   if (L.cg == 2) {  // CTA pairs: the production epilogues only
     if (L.swz != 128) return cudaErrorInvalidConfiguration;
     if (L.epi == EPI_TMA) {

@@ -79,6 +79,7 @@ struct Case {
   int in_stride = 1, res_stride = 1;
   int cin2 = 0;  // folded shortcut: second input tensor with cin2 channels (1x1 only)
   int cg = 1;    // 2: CTA pairs (tcgen05 cta_group::2)
+  int bres = 0;  // 1: weights resident in smem
 };
 
 static int run_case(const Case& c, int num_sms, bool timing) {
@@ -97,6 +98,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   s.in_stride = c.in_stride;
   s.res_stride = c.res_stride;
   s.cg = c.cg;
+  s.b_resident = c.bres;
   const int phases = c.kind == CONV_DECONV4 ? 4 : 1;
   const int taps = c.kind == CONV_1x1 ? 1 : c.kind == CONV_3x3 ? 9 : c.kind == CONV_DECONV4 ? 4 : 7;
   const int k_total = c.kind == CONV_STEM7 ? 7 * 32 : taps * c.cin_pad + c.cin2;
@@ -502,6 +504,15 @@ int main(int argc, char** argv) {
     c2.cg = 2;
     fails += run_case(c2, sms, true);
   }
+  {  // resident weights: the 64-channel 3x3 convs (stride 1 and stride 2) and a 1x1
+    Case r1 = {"BRES TMA 3x3 64->64 relu 92x92", CONV_3x3, 2, 92, 92, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0};
+    Case r2 = {"BRES S2 3x3 64->64 relu 92->46", CONV_3x3, 2, 46, 46, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0, 2, 1};
+    Case r3 = {"BRES TMA 1x1 256->64 relu 92x92", CONV_1x1, 2, 92, 92, 256, 64, 64, 64, EPI_TMA, true, false, 64, 0};
+    r1.bres = r2.bres = r3.bres = 1;
+    fails += run_case(r1, sms, true);
+    fails += run_case(r2, sms, true);
+    fails += run_case(r3, sms, true);
+  }
   fails += run_stem2(2, 368, sms);
   fails += run_stem2(1, 448, sms);
   fails += run_stem_pool(2, 368, sms);
@@ -535,6 +546,16 @@ int main(int argc, char** argv) {
         {"BIG TMARES 1x1 128->512 +res 46x46 nb128", CONV_1x1, 128, 46, 46, 128, 512, 512, 256, EPI_TMA_RES, true, true, 512, 0},
         {"BIG TMARES 1x1 64->256 +res 92x92 nb128", CONV_1x1, 128, 92, 92, 64, 256, 256, 256, EPI_TMA_RES, true, true, 256, 0},
     };
+    {
+      Case b1 = {"BRES BIG TMA 3x3 64->64 92x92 nb128", CONV_3x3, 128, 92, 92, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0};
+      Case b2 = {"BRES BIG TMA 1x1 256->64 92x92 nb128", CONV_1x1, 128, 92, 92, 256, 64, 64, 64, EPI_TMA, true, false, 64, 0};
+      Case b3 = b2;
+      b3.name = "BIG TMA 1x1 256->64 92x92 nb128";
+      b1.bres = b2.bres = 1;
+      fails += run_case(b1, sms, true);
+      fails += run_case(b2, sms, true);
+      fails += run_case(b3, sms, true);
+    }
     for (const auto& c : pairc) {  // same layer on single CTAs and on CTA pairs, timings side by side
       fails += run_case(c, sms, true);
       Case c2 = c;

@@ -323,6 +323,11 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
   // outputs leave through swizzled smem + TMA tensor stores; residual tiles are prefetched by TMA
   s.out = h->acts.at(out).p; s.ldc = cout;
   s.epi = s.residual ? EPI_TMA_RES : EPI_TMA;
+  // 64-channel convs whose whole weight matrix fits 9 K blocks keep it resident in smem: the 3x3s of res2 are bound
+  // by L2->SM traffic (158 -> 135 us), the 1x1 256->64 convs gain a few percent
+  static const bool bres_on = [] { const char* e = getenv("VNECT_B200_BRES"); return !(e && atoi(e) == 0); }();
+  if (bres_on && cout == 64 && s.block_n == 64 && s.cg == 1 && s.epi == EPI_TMA && k * k * cin_pad / 64 <= kMaxResidentKBlocks)
+    s.b_resident = 1;
   Step st;
   st.kind = 0; st.name = scope;
   std::string err;
