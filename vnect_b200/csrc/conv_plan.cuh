@@ -10,6 +10,7 @@
 #include "conv_gemm.cuh"
 #include "stem_gemm.cuh"
 #include "stem_pool.cuh"
+#include "stem_roll.cuh"
 
 namespace vnect {
 
@@ -483,14 +484,85 @@ inline cudaError_t launch_stem(const StemLaunch& L, cudaStream_t st) {
 
 // conv1 + pool1 fused (stem_pool.cuh)
 struct StemPoolLaunch {
-  StemPoolParams p;
-  int grid = 0;
+  StemPoolParams p;   // band kernel (stem_pool.cuh), kept as the A/B baseline
+  StemRollParams r;   // rolling kernel (stem_roll.cuh), used when stacked weights are supplied
+  bool roll = false;
+  int grid = 0, grid_roll = 0;
 };
+
+// [64][224] K-major (k = ky*32 + kx*4 + c) -> the rolling kernel's stacked weights: rows (ky = 6, 4, 2, 0) x 64 couts for
+// even input rows, then rows (ky = 5, 3, 1) x 64 couts for odd ones; every row is the 32 K values (64 B) of one row tap
+// in the 64B-swizzled K-major UMMA layout (16-byte chunk index ^= (row >> 1) & 3)
+inline void pack_stem_stacked(const __half* kmajor, __half* out) {
+  __half* even = out;
+  __half* odd = out + kRollWEvenBytes / 2;
+  for (int n = 0; n < 64; ++n)
+    for (int k = 0; k < 32; ++k) {
+      const int c = k >> 3, e = k & 7;
+      for (int g = 0; g < 4; ++g) {
+        const int row = g * 64 + n;
+        even[row * 32 + ((c ^ ((row >> 1) & 3)) << 3) + e] = kmajor[n * 224 + (6 - 2 * g) * 32 + k];
+      }
+      for (int g = 0; g < 3; ++g) {
+        const int row = g * 64 + n;
+        odd[row * 32 + ((c ^ ((row >> 1) & 3)) << 3) + e] = kmajor[n * 224 + (5 - 2 * g) * 32 + k];
+      }
+    }
+}
+
+// segment length (pooled rows) of the rolling kernel: fewest (waves x input rows per item); a segment re-reads 6
+// input rows of its upper neighbour, so longer is cheaper until the last wave goes idle
+inline void stem_roll_set_batch(StemRollParams& r, int nb, int num_sms, int* grid) {
+  int best_rows = r.PH;
+  long best_cost = -1;
+  for (int rows = 1; rows <= r.PH; ++rows) {
+    const int segs = (r.PH + rows - 1) / rows;
+    const long items = (long)nb * segs * r.n_xt;
+    const long waves = (items + num_sms - 1) / num_sms;
+    const long cost = waves * (4 * rows + 7);
+    if (best_cost < 0 || cost <= best_cost) {
+      best_cost = cost;
+      best_rows = rows;
+    }
+  }
+  r.seg_rows = best_rows;
+  r.segs_per_image = (r.PH + best_rows - 1) / best_rows;
+  r.num_items = nb * r.segs_per_image * r.n_xt;
+  *grid = r.num_items < num_sms ? r.num_items : num_sms;
+}
 
 inline bool build_stem_pool(const __half* x1, int S, int rows_per_parity, int row_pitch, const __half* w_canonical,
                             const float* bias, __half* pooled_out, int nb, int num_sms, StemPoolLaunch* L,
-                            std::string* err) {
+                            std::string* err, const __half* w_stacked = nullptr) {
   memset(L, 0, sizeof(*L));
+  if (w_stacked) {
+    StemRollParams& r = L->r;
+    r.x1 = reinterpret_cast<const uint8_t*>(x1);
+    r.plane_bytes = (int64_t)rows_per_parity * row_pitch * 2;
+    r.w = reinterpret_cast<const uint8_t*>(w_stacked);
+    r.bias = bias;
+    r.out = pooled_out;
+    r.vw = S / 2 + 3;
+    r.CH = r.CW = S / 2;
+    r.PH = r.PW = S / 4;
+    int pb = 0;
+    while (pb < r.PW) {  // x tiles: 128 conv columns each, pooled columns split where a 3-wide window would cross
+      if (r.n_xt == kMaxXTiles) {
+        if (err) *err = "box size too large for the rolling stem";
+        return false;
+      }
+      int x0 = 2 * pb < r.CW - kBlockM ? 2 * pb : r.CW - kBlockM;
+      if (x0 < 0) x0 = 0;
+      const int pe = x0 + kBlockM >= r.CW ? r.PW : (x0 + kBlockM - 3) / 2 + 1;
+      r.xt_x0[r.n_xt] = x0;
+      r.xt_pb[r.n_xt] = pb;
+      r.xt_pe[r.n_xt] = pe;
+      ++r.n_xt;
+      pb = pe;
+    }
+    stem_roll_set_batch(r, nb, num_sms, &L->grid_roll);
+    L->roll = true;
+  }
   StemPoolParams& p = L->p;
   p.vw = S / 2 + 3;
   if (row_pitch * 2 != p.vw * 16 || S % 16 != 0) {
@@ -519,9 +591,19 @@ inline bool build_stem_pool(const __half* x1, int S, int rows_per_parity, int ro
 inline void stem_pool_set_batch(StemPoolLaunch& L, int nb, int num_sms) {
   L.p.num_items = nb * L.p.bands_per_image;
   L.grid = L.p.num_items < num_sms ? L.p.num_items : num_sms;
+  if (L.roll) stem_roll_set_batch(L.r, nb, num_sms, &L.grid_roll);
 }
 
 inline cudaError_t launch_stem_pool(const StemPoolLaunch& L, cudaStream_t st) {
+  if (L.roll) {
+    static bool roll_attr_set = false;
+    if (!roll_attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(stem_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemRollSmem::BYTES);
+      if (e != cudaSuccess) return e;
+      roll_attr_set = true;
+    }
+    return launch_pdl(stem_roll_kernel, dim3(L.grid_roll), dim3(kRollThreads), StemRollSmem::BYTES, st, L.r);
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemPoolSmem::BYTES);

@@ -355,16 +355,19 @@ static int run_stem2(int NB, int S, int num_sms) {
 }
 
 // fused conv1 + pool1 against naive conv + host max-pool
-static int run_stem_pool(int NB, int S, int num_sms) {
+static int run_stem_pool(int NB, int S, int num_sms, bool roll = false) {
   const int OH = S / 2, PH = S / 4, vw = OH + 3, rpp = OH + 3, pitch = vw * 8;
   const size_t in_elems = (size_t)NB * 2 * rpp * pitch + 8192;
-  std::vector<__half> h_in(in_elems), h_w((size_t)64 * 224), h_wc((size_t)64 * 224);
+  std::vector<__half> h_in(in_elems), h_w((size_t)64 * 224), h_wc((size_t)64 * 224), h_ws((size_t)64 * 224);
   for (auto& v : h_in) v = __float2half(frand());
   for (auto& v : h_w) v = __float2half(frand() * 0.15f);
   pack_stem_canonical(h_w.data(), h_wc.data());
+  pack_stem_stacked(h_w.data(), h_ws.data());
   std::vector<float> h_bias(64);
   for (auto& v : h_bias) v = frand() * 0.5f;
-  __half *d_in, *d_w, *d_wc, *d_out;
+  __half *d_in, *d_w, *d_wc, *d_ws, *d_out;
+  CK(cudaMalloc(&d_ws, h_ws.size() * 2));
+  CK(cudaMemcpy(d_ws, h_ws.data(), h_ws.size() * 2, cudaMemcpyHostToDevice));
   float *d_bias, *d_acc;
   CK(cudaMalloc(&d_in, in_elems * 2));
   CK(cudaMalloc(&d_w, h_w.size() * 2));
@@ -379,14 +382,15 @@ static int run_stem_pool(int NB, int S, int num_sms) {
   CK(cudaMemset(d_out, 0xff, out_elems * 2));
   StemPoolLaunch L;
   std::string err;
-  if (!build_stem_pool(d_in, S, rpp, pitch, d_wc, d_bias, d_out, NB, num_sms, &L, &err)) {
+  if (!build_stem_pool(d_in, S, rpp, pitch, d_wc, d_bias, d_out, NB, num_sms, &L, &err, roll ? d_ws : nullptr)) {
     printf("[stem_pool] build FAILED: %s\n", err.c_str());
     return 1;
   }
   unsigned long long* d_dbg;
-  CK(cudaMalloc(&d_dbg, 4 * sizeof(unsigned long long)));
-  CK(cudaMemset(d_dbg, 0, 4 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&d_dbg, 8 * sizeof(unsigned long long)));
+  CK(cudaMemset(d_dbg, 0, 8 * sizeof(unsigned long long)));
   L.p.dbg = d_dbg;
+  L.r.dbg = d_dbg;
   CK(launch_stem_pool(L, 0));
   cudaError_t se = cudaDeviceSynchronize();
   if (se != cudaSuccess) {
@@ -429,15 +433,22 @@ static int run_stem_pool(int NB, int S, int num_sms) {
           ++checked;
         }
   {
-    unsigned long long h_dbg[4];
+    unsigned long long h_dbg[8];
     CK(cudaMemcpy(h_dbg, d_dbg, sizeof h_dbg, cudaMemcpyDeviceToHost));
     const double items0 = (double)((L.p.num_items + L.grid - 1) / L.grid);
-    printf("   CTA0 epilogue cycles per band: wait-MMA %.0f, drain %.0f, barrier %.0f, pool %.0f\n", h_dbg[0] / items0,
+    if (!roll) printf("   CTA0 epilogue cycles per band: wait-MMA %.0f, drain %.0f, barrier %.0f, pool %.0f\n", h_dbg[0] / items0,
            h_dbg[1] / items0, h_dbg[2] / items0, h_dbg[3] / items0);
+    if (roll) printf("   CTA0 epilogue cycles: wait-MMA %llu, drain %llu, pool %llu, total %llu\n", h_dbg[0], h_dbg[1], h_dbg[2], h_dbg[3]);
+    if (roll) printf("   CTA0 MMA warp cycles: wait-strips %llu, wait-slot %llu, total %llu\n", h_dbg[4], h_dbg[5], h_dbg[6]);
     L.p.dbg = nullptr;
+    L.r.dbg = nullptr;
   }
-  printf("[stem_pool fused conv1+pool1 S=%d nb=%d] items=%d grid=%d ppb=%d tiles/band=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n",
-         S, NB, L.p.num_items, L.grid, L.p.ppb, L.p.band_tiles, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
+  if (roll)
+    printf("[stem_roll rolling conv1+pool1 S=%d nb=%d] items=%d grid=%d x-tiles=%d seg_rows=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n",
+           S, NB, L.r.num_items, L.grid_roll, L.r.n_xt, L.r.seg_rows, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
+  else
+    printf("[stem_pool fused conv1+pool1 S=%d nb=%d] items=%d grid=%d ppb=%d tiles/band=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n",
+           S, NB, L.p.num_items, L.grid, L.p.ppb, L.p.band_tiles, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
   if (bad == 0) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -518,10 +529,16 @@ int main(int argc, char** argv) {
   fails += run_stem_pool(2, 368, sms);
   fails += run_stem_pool(2, 448, sms);
   fails += run_stem_pool(1, 64, sms);
+  fails += run_stem_pool(2, 368, sms, true);
+  fails += run_stem_pool(2, 448, sms, true);
+  fails += run_stem_pool(1, 64, sms, true);
+  fails += run_stem_pool(1, 512, sms, true);
   if (big) {
     fails += run_stem2(32, 368, sms);
     fails += run_stem_pool(32, 368, sms);
     fails += run_stem_pool(128, 368, sms);
+    fails += run_stem_pool(32, 368, sms, true);
+    fails += run_stem_pool(128, 368, sms, true);
     std::vector<Case> bigc = {
         {"BIG 1x1 1024->1024 23x23 nb128", CONV_1x1, 128, 23, 23, 1024, 1024, 1024, 256, EPI_NHWC_F16, true, false,
          1024, 0},

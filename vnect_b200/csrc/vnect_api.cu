@@ -600,18 +600,23 @@ int vnect_finalize(vnect_t* h) {
 
   const int S = h->S, nb = h->cap_fw;
   int rc;
-  {  // conv1 + pool1 (vnect_model.py:27-29) fused: raw-strip implicit GEMM, smem band, max-pool (stem_pool.cuh)
-    std::vector<__half> wk = to_half(pack_stem(h->vars.at("conv1/weights"))), wc(wk.size());
+  {  // conv1 + pool1 (vnect_model.py:27-29) fused: rolling raw-strip implicit GEMM + max-pool (stem_roll.cuh);
+     // VNECT_B200_STEM=band selects the older band kernel (stem_pool.cuh) for A/B runs
+    std::vector<__half> wk = to_half(pack_stem(h->vars.at("conv1/weights"))), wc(wk.size()), ws(wk.size());
     pack_stem_canonical(wk.data(), wc.data());
+    pack_stem_stacked(wk.data(), ws.data());
     __half* dw = nullptr;
+    __half* dws = nullptr;
     float* db = nullptr;
     if ((rc = upload(h, wc, &dw))) return rc;
+    const char* stem_env = getenv("VNECT_B200_STEM");
+    if (!(stem_env && strcmp(stem_env, "band") == 0) && (rc = upload(h, ws, &dws))) return rc;
     if ((rc = upload(h, h->vars.at("conv1/biases").data, &db))) return rc;
     if ((rc = new_act(h, "pool1", S / 4, S / 4, 64))) return rc;
     Step st;
     st.kind = 3; st.name = "conv1+pool1";
     std::string err;
-    if (!build_stem_pool(h->x1, S, h->stem_rpp, h->stem_pitch, dw, db, h->acts.at("pool1").p, nb, h->num_sms, &st.stem_pool, &err))
+    if (!build_stem_pool(h->x1, S, h->stem_rpp, h->stem_pitch, dw, db, h->acts.at("pool1").p, nb, h->num_sms, &st.stem_pool, &err, dws))
       return fail(h, VNECT_E_CUDA, "conv1+pool1: %s", err.c_str());
     h->steps.push_back(st);
   }
@@ -691,7 +696,7 @@ int vnect_finalize(vnect_t* h) {
   for (size_t i = 0; i < h->steps.size(); ++i) {
     const int rev = (pingpong && i % 2 == 0) ? 1 : 0;
     if (h->steps[i].kind == 0) h->steps[i].launch.p.reverse = rev;
-    else h->steps[i].stem_pool.p.reverse = rev;
+    else h->steps[i].stem_pool.p.reverse = h->steps[i].stem_pool.r.reverse = rev;
   }
 
   h->vars.clear();  // host copies no longer needed
