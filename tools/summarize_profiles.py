@@ -85,7 +85,7 @@ def traffic():
         if m == "gpu__time_duration.sum":
             val *= {"ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}[unit]
         d[m] = val
-    conv = [d for d in per.values() if "conv_gemm" in d["name"] or "stem_pool" in d["name"]]
+    conv = [d for d in per.values() if "conv_gemm" in d["name"] or "stem_pool" in d["name"] or "stem_roll" in d["name"]]
     ct = sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in conv)
     tt = sum(d["gpu__time_duration.sum"] for d in conv)
     out = ["# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
