@@ -19,3 +19,10 @@ eng.set_box(1, (0, 0, 420, 300))
 j2, j3, boxes = eng.track(frames, [0, 1], [5.0, 5.0], [5.01, 5.01])
 print("ok", float(np.abs(j3).max()), boxes.tolist())
 eng.close()
+
+# 5 frames x 2 scales = 10 forwards: past the small-batch plan, so the CTA-pair (cta_group::2) and 256-column kernels run
+eng = VNectEngine(seeded_init("W1"), [1.0, 0.7], max_frames=5, max_streams=5)
+frames = np.random.default_rng(1).integers(0, 256, (5, 368, 368, 3), dtype=np.uint8)
+j2, j3 = eng.estimate(frames, list(range(5)), [1.0] * 5, [1.01] * 5)
+print("ok pairs", float(np.abs(j3).max()), eng.launch_count())
+eng.close()
