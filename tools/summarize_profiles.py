@@ -48,12 +48,20 @@ def launches():
 
 
 def full(rep, label):
-    path = os.path.join(ROOT, "gpurun_out", rep)
-    if not os.path.isfile(path):
+    """rep: one report, or a glob of single-launch reports (gpurun_out/ is capped at 64 MiB, a full-set launch is ~6 MB)"""
+    import glob
+    paths = sorted(glob.glob(os.path.join(ROOT, "gpurun_out", rep)))
+    if not paths:
         return
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
+    hdr = units = None
+    rows = [None, None]
+    for path in paths:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        part = list(csv.reader(raw.splitlines()))
+        if hdr is None:
+            hdr, units = part[0], part[1]
+            rows = [hdr, units]
+        rows += [r for r in part[2:] if len(r) == len(hdr)]
     idx = {m: hdr.index(m) for m in METRICS if m in hdr}
     kn = hdr.index("Kernel Name")
     with open(os.path.join(out_dir, f"{tag}_ncu_full_{label}.txt"), "w") as f:
@@ -110,5 +118,5 @@ def traffic():
 
 launches()
 traffic()
-full("prof_conv.ncu-rep", "conv")
+full("prof_conv*.ncu-rep", "conv")
 full("prof_prepost.ncu-rep", "prepost")

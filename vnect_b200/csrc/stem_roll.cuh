@@ -28,6 +28,7 @@ constexpr int kRollRowBufs = 2;         // column-maxima buffers (alternating po
 constexpr int kRollSlots = 8;                // 8 x 64 fp32 columns = all of TMEM
 constexpr int kRollRowBytes = kBlockM * 128;
 constexpr int kMaxXTiles = 4;
+constexpr int kRollMaxInputRows = 4 * 128 + 8;  // a segment of up to 128 pooled rows (box size 512)
 constexpr int kRollWEvenBytes = 256 * 64;  // [4 taps x 64 couts][32 K] fp16, 64B-swizzled K-major rows
 constexpr int kRollWOddBytes = 192 * 64;   // [3 taps x 64 couts][32 K]
 static_assert(kRollWEvenBytes + kRollWOddBytes == kStemWBytes, "stacked weights are a permutation of the canonical pack");
@@ -54,7 +55,8 @@ struct StemRollSmem {
   static constexpr int STRIP_OFF = kStemWBytes;
   static constexpr int ROW_OFF = ((STRIP_OFF + kRollStages * kRollStripBytes + 1023) / 1024) * 1024;
   static constexpr int BAR_OFF = ROW_OFF + kRollRowBufs * kRollRowBytes;
-  static constexpr int BYTES = BAR_OFF + 1024 + 1024;
+  static constexpr int CMD_OFF = BAR_OFF + 1024;                 // issue program of one item: 32 B per input row
+  static constexpr int BYTES = CMD_OFF + kRollMaxInputRows * 32 + 1024;
 };
 
 struct RollItem {
@@ -158,9 +160,18 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer (warp-converged, one lane issues)
+    // Which accumulators an input row feeds, where a run wraps around the TMEM ring, which slot has to be waited for
+    // and which row completes is ~100 dependent scalar instructions per input row; done inline, that arithmetic (not
+    // the tensor pipe) set the pace.  So the 32 lanes first write the whole item's issue program into a smem table,
+    // one input row per lane, and the issue loop only loads a 32-byte command and fires.
     const bool issuer = elect_one();
     mbar_wait(w_bar, 0);
-    const uint32_t w_even = smem_u32(w_smem), w_odd = w_even + kRollWEvenBytes;
+    const uint32_t w_even = (smem_u32(w_smem) & 0x3FFFF) >> 4, w_odd = w_even + (kRollWEvenBytes >> 4);
+    const uint32_t a_lo0 = ((smem_u32(strips) & 0x3FFFF) >> 4) | (1u << 16);  // no-swizzle K-major: LBO = 16 B
+    constexpr uint32_t kADescHi = (128u >> 4) | (1u << 14);                    // SBO = 128 B, descriptor version 1
+    constexpr uint32_t kBDescHi = (512u >> 4) | (1u << 14) | (4u << 29);       // SBO = 512 B, version 1, 64B swizzle
+    constexpr uint32_t kNone = 0xFFFFFFFFu;
+    uint4* cmds = reinterpret_cast<uint4*>(smem + StemRollSmem::CMD_OFF);
     int stage = 0;
     uint32_t phase = 0;
     int G0 = 0;  // conv rows this CTA has started before the current item: row G lives in TMEM slot G & 7
@@ -168,41 +179,54 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
     const long long m_begin = clock64();
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       const RollItem R = roll_decode(p, it);
-      for (int ri = 0; ri < R.n_in; ++ri) {
-        const long long m0 = clock64();
-        mbar_wait(&full_bar[stage], phase);
-        m_full += clock64() - m0;
-        tc_fence_after();
+      for (int ri = lane; ri < R.n_in; ri += 32) {
         const bool even = !(ri & 1);
         const int ly_hi = min(R.n_rows - 1, ri >> 1);
         const int ly_lo = ri >= 6 ? (ri - 5) >> 1 : 0;  // ceil((ri - 6) / 2)
-        if (even && (ri >> 1) < R.n_rows) {  // first tap (ky = 0) of conv row ri/2: its slot must have been zeroed
-          const int G = G0 + (ri >> 1);
+        const int total = ly_hi - ly_lo + 1;            // conv rows this input row feeds (1..4)
+        const int slot = (G0 + ly_lo) & 7;
+        const int cnt1 = min(total, kRollSlots - slot);  // a run may not wrap around the ring
+        const int ky = ri - 2 * ly_lo;                    // tap of the first row; later rows: ky - 2, ...
+        const int g = even ? (6 - ky) >> 1 : (5 - ky) >> 1;  // its 64-row group in the stacked weights
+        const uint32_t wb = (even ? w_even : w_odd) | (1u << 16);
+        uint4 c0, c1;
+        c0.x = static_cast<uint32_t>(slot * 64);                    // run 1: TMEM column offset
+        c0.y = make_idesc_f16(kBlockM, 64 * cnt1, false);
+        c0.z = wb + static_cast<uint32_t>(g * (4096 >> 4));          // low word of the B descriptor
+        c0.w = cnt1 < total ? 0u : kNone;                            // run 2 starts at slot 0
+        c1.x = make_idesc_f16(kBlockM, 64 * (total - cnt1 > 0 ? total - cnt1 : 1), false);
+        c1.y = wb + static_cast<uint32_t>((g + cnt1) * (4096 >> 4));
+        // first tap (ky = 0) of conv row ri/2: its slot must have been drained and zeroed
+        const int Gt = G0 + (ri >> 1);
+        c1.z = (even && (ri >> 1) < R.n_rows) ? static_cast<uint32_t>((Gt & 7) | (((Gt >> 3) & 1) << 8)) : kNone;
+        // last tap (ky = 6) of conv row (ri - 6) / 2: the row is complete
+        c1.w = (even && ri >= 6) ? static_cast<uint32_t>((G0 + ((ri - 6) >> 1)) & 7) : kNone;
+        cmds[2 * ri] = c0;
+        cmds[2 * ri + 1] = c1;
+      }
+      __syncwarp();
+      for (int ri = 0; ri < R.n_in; ++ri) {
+        const uint4 c0 = cmds[2 * ri], c1 = cmds[2 * ri + 1];
+        const long long m0 = clock64();
+        mbar_wait(&full_bar[stage], phase);
+        m_full += clock64() - m0;
+        if (c1.z != kNone) {
           const long long m1 = clock64();
-          mbar_wait(&tmem_empty[G & 7], (G >> 3) & 1);
+          mbar_wait(&tmem_empty[c1.z & 7], (c1.z >> 8) & 1);
           m_empty += clock64() - m1;
-          tc_fence_after();
         }
-        const uint64_t a_desc = make_noswz_desc(smem_u32(strips + stage * kRollStripBytes), 16, 128);
-        for (int ly = ly_lo; ly <= ly_hi;) {
-          const int slot = (G0 + ly) & 7;
-          const int cnt = min(ly_hi - ly + 1, kRollSlots - slot);  // a run may not wrap around the ring
-          const int ky = ri - 2 * ly;                              // tap of the run's first row; later rows: ky - 2, ...
-          const int g = even ? (6 - ky) >> 1 : (5 - ky) >> 1;      // its 64-row group in the stacked weights
-          // B rows are 64 B (one tap row = 32 K) in the 64B-swizzled layout: a no-swizzle B costs ~1.5 cycles per
-          // row and MMA, the swizzled one ~0.5
-          const uint64_t b_desc = make_kmajor_desc<64>((even ? w_even : w_odd) + g * 4096);
-          const uint32_t idesc = make_idesc_f16(kBlockM, 64 * cnt, false);
-          if (issuer) {
-            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(slot * 64);
-            umma_f16(d_tmem, a_desc, b_desc, idesc, 1u);
-            umma_f16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);  // +32 B of A, +32 B along K of B
-          }
-          __syncwarp();
-          ly += cnt;
-        }
+        tc_fence_after();
         if (issuer) {
-          if (even && ri >= 6) umma_commit(&tmem_full[(G0 + ((ri - 6) >> 1)) & 7]);  // last tap (ky = 6) of that row
+          const uint64_t a_desc = (static_cast<uint64_t>(kADescHi) << 32) | (a_lo0 + static_cast<uint32_t>(stage * (kRollStripBytes >> 4)));
+          const uint64_t b1 = (static_cast<uint64_t>(kBDescHi) << 32) | c0.z;
+          umma_f16(tmem_base + c0.x, a_desc, b1, c0.y, 1u);
+          umma_f16(tmem_base + c0.x, a_desc + 2, b1 + 2, c0.y, 1u);  // +32 B of A, +32 B along K of B
+          if (c0.w != kNone) {
+            const uint64_t b2 = (static_cast<uint64_t>(kBDescHi) << 32) | c1.y;
+            umma_f16(tmem_base, a_desc, b2, c1.x, 1u);
+            umma_f16(tmem_base, a_desc + 2, b2 + 2, c1.x, 1u);
+          }
+          if (c1.w != kNone) umma_commit(&tmem_full[c1.w]);
           umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
@@ -211,6 +235,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
           phase ^= 1;
         }
       }
+      __syncwarp();  // the table is rewritten for the next item
       G0 += R.n_rows;
     }
     if (p.dbg != nullptr && lane == 0 && blockIdx.x == 0) {
