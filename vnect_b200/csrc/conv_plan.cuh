@@ -598,11 +598,15 @@ inline cudaError_t launch_stem_pool(const StemPoolLaunch& L, cudaStream_t st) {
   if (L.roll) {
     static bool roll_attr_set = false;
     if (!roll_attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(stem_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemRollSmem::BYTES);
+      cudaError_t e = cudaFuncSetAttribute(stem_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, StemRollSmem::BYTES);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stem_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, StemRollSmem::BYTES);
       if (e != cudaSuccess) return e;
       roll_attr_set = true;
     }
-    return launch_pdl(stem_roll_kernel, dim3(L.grid_roll), dim3(kRollThreads), StemRollSmem::BYTES, st, L.r);
+    if (L.r.dbg != nullptr)
+      return launch_pdl(stem_roll_kernel<true>, dim3(L.grid_roll), dim3(kRollThreads), StemRollSmem::BYTES, st, L.r);
+    return launch_pdl(stem_roll_kernel<false>, dim3(L.grid_roll), dim3(kRollThreads), StemRollSmem::BYTES, st, L.r);
   }
   static bool attr_set = false;
   if (!attr_set) {

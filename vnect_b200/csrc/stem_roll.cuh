@@ -92,6 +92,14 @@ __device__ __forceinline__ void tmem_zero_32x32(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// DBG = true adds cycle counters (selftest only); the shipped instantiation has none in its loops
+template <bool DBG>
+__device__ __forceinline__ long long roll_clock() {
+  if constexpr (DBG) return clock64();
+  else return 0;
+}
+
+template <bool DBG = false>
 __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid_constant__ StemRollParams p) {
   constexpr uint32_t TMEM_COLS = 512;
   extern __shared__ uint8_t smem_raw[];
@@ -176,7 +184,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
     uint32_t phase = 0;
     int G0 = 0;  // conv rows this CTA has started before the current item: row G lives in TMEM slot G & 7
     long long m_full = 0, m_empty = 0;
-    const long long m_begin = clock64();
+    const long long m_begin = roll_clock<DBG>();
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       const RollItem R = roll_decode(p, it);
       for (int ri = lane; ri < R.n_in; ri += 32) {
@@ -207,13 +215,13 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
       __syncwarp();
       for (int ri = 0; ri < R.n_in; ++ri) {
         const uint4 c0 = cmds[2 * ri], c1 = cmds[2 * ri + 1];
-        const long long m0 = clock64();
+        const long long m0 = roll_clock<DBG>();
         mbar_wait(&full_bar[stage], phase);
-        m_full += clock64() - m0;
+        m_full += roll_clock<DBG>() - m0;
         if (c1.z != kNone) {
-          const long long m1 = clock64();
+          const long long m1 = roll_clock<DBG>();
           mbar_wait(&tmem_empty[c1.z & 7], (c1.z >> 8) & 1);
-          m_empty += clock64() - m1;
+          m_empty += roll_clock<DBG>() - m1;
         }
         tc_fence_after();
         if (issuer) {
@@ -238,8 +246,8 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
       __syncwarp();  // the table is rewritten for the next item
       G0 += R.n_rows;
     }
-    if (p.dbg != nullptr && lane == 0 && blockIdx.x == 0) {
-      p.dbg[4] = m_full; p.dbg[5] = m_empty; p.dbg[6] = clock64() - m_begin;
+    if (DBG && p.dbg != nullptr && lane == 0 && blockIdx.x == 0) {
+      p.dbg[4] = m_full; p.dbg[5] = m_empty; p.dbg[6] = roll_clock<DBG>() - m_begin;
     }
   } else if (warp >= 4) {
     // ================================================================ 8 warps: drain + zero a slot, pool every 2nd row
@@ -265,16 +273,16 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
     int G0 = 0;
     uint32_t win = 0;  // pooling windows done by this CTA: column maxima alternate between two smem buffers
     long long t_wait = 0, t_drain = 0, t_pool = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = roll_clock<DBG>();
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       const RollItem R = roll_decode(p, it);
       const int x0 = p.xt_x0[R.xt], pb = p.xt_pb[R.xt], pe = p.xt_pe[R.xt];
       __half2 row_a[16], row_b[16];  // the open window's first (even) and second (odd) conv row, this thread's column
       for (int ly = 0; ly < R.n_rows; ++ly) {
         const int G = G0 + ly;
-        const long long c0 = clock64();
+        const long long c0 = roll_clock<DBG>();
         mbar_wait(&tmem_full[G & 7], (G >> 3) & 1);
-        const long long c1 = clock64();
+        const long long c1 = roll_clock<DBG>();
         t_wait += c1 - c0;
         tc_fence_after();
         uint32_t v[32];
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
           const uint32_t pk = pack_half2_relu(__uint_as_float(v[2 * j]) + bias_r[2 * j], __uint_as_float(v[2 * j + 1]) + bias_r[2 * j + 1]);
           cur[j] = *reinterpret_cast<const __half2*>(&pk);
         }
-        const long long c2 = clock64();
+        const long long c2 = roll_clock<DBG>();
         t_drain += c2 - c1;
         // a pooling window closes on every even row >= 2, and on the last row when the image edge clips it to 2 rows
         const bool full3 = ly >= 2 && !(ly & 1);
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
             __half* o = p.out + ((static_cast<size_t>(R.img) * p.PH + (R.p0 + lpy)) * p.PW + px) * 64 + pc * 8;
             *reinterpret_cast<uint4*>(o) = acc;
           }
-          t_pool += clock64() - c2;
+          t_pool += roll_clock<DBG>() - c2;
         }
         if (ly & 1) {
 #pragma unroll
@@ -350,8 +358,8 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
       }
       G0 += R.n_rows;
     }
-    if (p.dbg != nullptr && et == 0 && blockIdx.x == 0) {
-      p.dbg[0] = t_wait; p.dbg[1] = t_drain; p.dbg[2] = t_pool; p.dbg[3] = clock64() - t_begin;
+    if (DBG && p.dbg != nullptr && et == 0 && blockIdx.x == 0) {
+      p.dbg[0] = t_wait; p.dbg[1] = t_drain; p.dbg[2] = t_pool; p.dbg[3] = roll_clock<DBG>() - t_begin;
     }
   }
   tc_fence_before();
