@@ -127,6 +127,25 @@ def test_forward_is_batch_invariant(engine_w1):
         assert np.array_equal(a[3:4], b)  # bit-identical regardless of batch composition
 
 
+def test_forward_is_plan_invariant(w1):
+    """The small-batch plan (64-column tiles, single CTAs), the CTA-pair plan (cta_group::2, 128/256-column tiles) and a
+    batch whose tile count is odd give bit-identical maps: tiling never changes the order of the K accumulation."""
+    from vnect_b200 import VNectEngine
+    x = np.stack([prepost.gen_input_batch(synth.frame_c2(i), 368, [1.0])[0][0] for i in range(3)])
+    outs = []
+    for max_frames in (1, 4, 16):   # 2, 8 and 32 forwards of capacity
+        eng = VNectEngine(w1, SCALES2, max_frames=max_frames, max_streams=max_frames)
+        try:
+            outs.append([eng.forward(x[i:i + 1]) for i in range(3)] if max_frames == 1 else
+                        [[m[i:i + 1] for m in eng.forward(x)] for i in range(3)])
+        finally:
+            eng.close()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            for ma, mb in zip(a, b):
+                assert np.array_equal(ma, mb)
+
+
 # ------------------------------------------------------------------------------------------------ K8 post-processing
 @pytest.mark.parametrize("case", POST_CASES, ids=[c[0] for c in POST_CASES])
 def test_postprocess_against_reference_golden(case, golden):
