@@ -410,6 +410,35 @@ def test_box448_three_scales(w1):
         eng.close()
 
 
+def test_box512_is_the_maximum_size(w1):
+    """Largest supported box (512 x 512, heat-maps 64 x 64): conv1+pool1 needs three 128-column tiles there, the
+    post-process its full table size; one size up is refused at vnect_create."""
+    from vnect_b200 import VNectEngine
+    scales = [1.0, 0.7]
+    net = OracleNet(w1)
+    eng = VNectEngine(w1, scales, box_size=512, max_frames=1, max_streams=1)
+    try:
+        frame = np.random.default_rng(4000).integers(0, 256, (512, 512, 3), dtype=np.uint8)
+        got, scaler, offs = eng.preprocess(frame)
+        ref, rs, ro = prepost.gen_input_batch(frame, 512, scales)
+        assert np.array_equal(got, ref.astype(np.float16).astype(np.float32))
+        outs = eng.forward(got)
+        refs = net(got)
+        for a, b in zip(outs, refs):
+            assert a.shape == (2, 64, 64, 21)
+            assert rel_l2(a, b) < 3e-3
+        j2, j3 = eng.estimate(frame, [0], [2.0], [2.01])
+        clock = Clock()
+        clock.q = [2.0, 2.01]
+        oracle = prepost.OracleEstimator(net, scales, clock=clock, box_size=512)
+        r2, r3 = oracle(frame)
+        assert _assert_only_near_ties(np.rint(j2[0]).astype(int), oracle) <= 2
+    finally:
+        eng.close()
+    with pytest.raises(ValueError):
+        VNectEngine(w1, scales, box_size=528, max_frames=1, max_streams=1)
+
+
 def test_many_streams_over_time(engine_w0, oracle_net_w0):
     """C4-style: several video streams advanced together for a few frames (filters live per stream) must equal the
     same streams advanced one at a time (per-stream state never mixes, results independent of batch composition)."""
