@@ -84,9 +84,10 @@ struct GemmCfg {
   static constexpr int B_BYTES = (BLOCK_N / CG) * SWZ;
   static constexpr int STAGE_BYTES = BRES ? A_BYTES : A_BYTES + B_BYTES;
   static constexpr int BRES_BYTES = BRES ? kMaxResidentKBlocks * B_BYTES : 0;
-  static constexpr int EPI_BYTES = (EPI == EPI_TMA)       ? kEpiGroups * kOutStages * kEpiChunkBytes
-                                   : (EPI == EPI_TMA_RES) ? (kEpiGroups * kOutStages + kResStages) * kEpiChunkBytes
-                                                          : 0;
+  static constexpr int EPI_BYTES = (EPI == EPI_TMA)          ? kEpiGroups * kOutStages * kEpiChunkBytes
+                                   : (EPI == EPI_TMA_RES)    ? (kEpiGroups * kOutStages + kResStages) * kEpiChunkBytes
+                                   : (EPI == EPI_PLANAR_F32) ? BLOCK_N * kBlockM * 4  // [column][row] fp32 transpose tile
+                                                             : 0;
   static constexpr int THREADS = (EPI == EPI_TMA || EPI == EPI_TMA_RES) ? kGemmThreadsTma : kGemmThreads;
   static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - EPI_BYTES - BRES_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -550,15 +551,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
         }
         if constexpr (EPI == EPI_PLANAR_F32) {
-          if (valid) {
-            float* o = reinterpret_cast<float*>(p.out);
-            const size_t plane = static_cast<size_t>(p.OH) * p.OW;
-            const size_t base = static_cast<size_t>(n) * p.n_valid * plane + static_cast<size_t>(oy) * p.OW + ox;
+          // transpose through smem: one scalar store per (thread, plane) straight to HBM kept a single warp per
+          // scheduler busy with ~1500 dependent instructions per tile; [column][row] staging, then 16-byte stores
+          float* st = reinterpret_cast<float*>(out_stage);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (col0 + j < p.n_valid) o[base + static_cast<size_t>(col0 + j) * plane] = f[j];
-            }
-          }
+          for (int j = 0; j < 32; ++j) st[(c0 + j) * kBlockM + r] = f[j];
         } else {
           if (valid) {
             if (p.residual != nullptr) {
@@ -600,6 +597,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
         }
+      }
+      if constexpr (EPI == EPI_PLANAR_F32) {
+        // flat rows only (1x1 conv, no decimation): row m = n * hw + rem, planes are [n][column][hw]; hw % 4 == 0
+        named_bar_sync(1, 128);
+        const float* st = reinterpret_cast<const float*>(out_stage);
+        float* o = reinterpret_cast<float*>(p.out);
+        const int hw = p.H * p.W;
+        const int m0 = m_tile * kBlockM + 4 * lane;
+        if (m0 < p.M) {
+          const int n0 = m0 / hw;
+          float* obase = o + static_cast<size_t>(n0) * p.n_valid * hw + (m0 - n0 * hw);
+          for (int c = q; c < p.n_valid; c += 4)
+            *reinterpret_cast<float4*>(obase + static_cast<size_t>(c) * hw) =
+                *reinterpret_cast<const float4*>(st + c * kBlockM + 4 * lane);
+        }
+        named_bar_sync(1, 128);  // the staging tile may be overwritten by the next tile
       }
       if constexpr (EPI == EPI_DECONV_HEAD) {
         if (valid) {

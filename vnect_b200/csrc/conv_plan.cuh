@@ -289,6 +289,10 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
                       (uint64_t)s.cin2_pad * 2 * p.M};
     if (!encode_tmap(&L->tmap_a2, s.in2, 5, d2, s2, box, swz, err)) return false;
   }
+  if (s.epi == EPI_PLANAR_F32 && (p.mode != 0 || s.decimate || (s.H * s.W) % 4 != 0)) {
+    if (err) *err = "the planar epilogue needs a flat 1x1 conv whose plane size is a multiple of 4";
+    return false;
+  }
   if (s.epi == EPI_TMA || s.epi == EPI_TMA_RES) {
     // output (and residual) tiles leave / enter through swizzled smem in 64-channel chunks: same row tiling as A
     if (s.decimate || s.kind == CONV_DECONV4 || s.ldc % 8 != 0) {
