@@ -88,7 +88,8 @@ struct GemmCfg {
                                    : (EPI == EPI_TMA_RES)    ? (kEpiGroups * kOutStages + kResStages) * kEpiChunkBytes
                                    : (EPI == EPI_PLANAR_F32) ? BLOCK_N * kBlockM * 4  // [column][row] fp32 transpose tile
                                                              : 0;
-  static constexpr int THREADS = (EPI == EPI_TMA || EPI == EPI_TMA_RES) ? kGemmThreadsTma : kGemmThreads;
+  // two epilogue warpgroups: the TMA epilogues (alternate 64-column chunks) and the deconv head (features / deltas)
+  static constexpr int THREADS = (EPI == EPI_TMA || EPI == EPI_TMA_RES || EPI == EPI_DECONV_HEAD) ? kGemmThreadsTma : kGemmThreads;
   static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - EPI_BYTES - BRES_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
@@ -118,7 +119,7 @@ __device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
 }
 
 template <int BLOCK_N, int SWZ, int EPI, int CG = 1, bool BRES = false>
-__global__ void __launch_bounds__((EPI == EPI_TMA || EPI == EPI_TMA_RES) ? kGemmThreadsTma : kGemmThreads, 1)
+__global__ void __launch_bounds__((EPI == EPI_TMA || EPI == EPI_TMA_RES || EPI == EPI_DECONV_HEAD) ? kGemmThreadsTma : kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ ConvGemmParams p) {
@@ -161,7 +162,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       // one arrive per epilogue warp that reads the accumulator: both groups when a tile has >= 2 chunks
-      mbar_init(&tmem_empty[s], CG * ((kTmaEpi && BLOCK_N >= 128) ? 8 : 4));
+      mbar_init(&tmem_empty[s], CG * (((kTmaEpi && BLOCK_N >= 128) || EPI == EPI_DECONV_HEAD) ? 8 : 4));
     }
     for (int s = 0; s < kResStages; ++s) {
       mbar_init(&res_full[s], 1);
@@ -529,8 +530,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int j = 0; j < 21; ++j) bone[j] = 0.f;
       }
 
+      // deconv head: warps 4-7 take the 128 feature columns, warps 8-11 the 63 deltas + bone lengths
+      [[maybe_unused]] const int head_grp = (warp - 4) >> 2;
 #pragma unroll
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        if constexpr (EPI == EPI_DECONV_HEAD) {
+          if ((c0 >= 128) != (head_grp == 1)) continue;
+        }
         uint32_t v[32];
         tmem_ld_32x32(t_row + c0, v);
         tmem_ld_wait();
@@ -615,7 +621,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         named_bar_sync(1, 128);  // the staging tile may be overwritten by the next tile
       }
       if constexpr (EPI == EPI_DECONV_HEAD) {
-        if (valid) {
+        if (valid && head_grp == 1) {
           __half* o = reinterpret_cast<__half*>(p.out) + pix * p.ldc;
           float b[26];
 #pragma unroll
