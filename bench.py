@@ -7,6 +7,9 @@ A step = one pass of the hot path over one batch of 64 synthetic 368x368 BGR fra
 SURVEY.md section 8d: scales [1.0, 0.7] => 128 CNN forwards), OneEuroFilter state live across steps (each frame slot is
 a video stream).  For N > 1 launch with torchrun (one rank per GPU); streams are sharded, nothing is exchanged on the
 compute path, and the per-step results are all-gathered with NCCL inside the timed region (weak scaling).
+Extra keys of the same line: `sustained` (>= 2 s of back-to-back steps), `c4_strong_scaling` (BASELINE config 4: 256
+streams sharded i mod G for 32 steps, total work fixed, plus the bit-for-bit check of the gathered results against a
+single-GPU run), batch-1 latency.
 
 value  = frames/s with the frames already resident in HBM (device-timed with CUDA events on the launch stream).
 e2e    = frames/s through the public host API (pinned host frames in, host joints out; H2D/D2H inside the timed region).
@@ -44,6 +47,17 @@ WORKLOAD = "C2: 64 synthetic 368x368 BGR frames per GPU per step, scales [1.0, 0
 def frame_c2(i, size=BOX):
     """C2 frame i: uniform-noise BGR image, seed 1000 + i."""
     return np.random.default_rng(1000 + i).integers(0, 256, (size, size, 3), dtype=np.uint8)
+
+
+def stream_frame(stream, k, size=BOX):
+    """C4: frame k of synthetic stream `stream` = a fixed noise image (seed 2000 + stream)
+    circularly shifted by (k, 2k) pixels, so the argmaxes move and the filters see motion."""
+    base = np.random.default_rng(2000 + stream).integers(0, 256, (size, size, 3), dtype=np.uint8)
+    return np.ascontiguousarray(np.roll(base, shift=(k, 2 * k), axis=(0, 1)))
+
+
+C4_STREAMS = 256
+C4_STEPS = 32
 
 
 def measured_peaks():
@@ -148,6 +162,87 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_c4(eng, parallel, dev, stream, rank, world, local, barrier):
+    """BASELINE.json config 4 as specified: 256 synthetic video streams x 32 steps, stream i on rank i mod G, results of
+    every step all-gathered (NCCL).  Total work is fixed, so this is the STRONG-scaling curve.  Outside the timed region
+    rank 0 recomputes all 256 streams alone and asserts the gathered [256, 21, 5] equal it bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from vnect_b200 import VNectEngine
+    from vnect_b200.weights import seeded_init
+    per = parallel.slots_per_rank(C4_STREAMS, world)
+    mine = parallel.owned_streams(C4_STREAMS, rank, world)
+    assert len(mine) == per, "256 streams divide evenly over 1/2/4/8 ranks"
+    ceng = VNectEngine(seeded_init("W0"), SCALES, BOX, max_frames=per, max_streams=per, device=local)
+    ceng.set_cuda_stream(stream.cuda_stream)
+    base = torch.from_numpy(np.stack([np.random.default_rng(2000 + s).integers(0, 256, (BOX, BOX, 3), dtype=np.uint8)
+                                      for s in mine])).to(dev)
+    frames = [torch.roll(base, shifts=(k, 2 * k), dims=(1, 2)).contiguous() for k in range(C4_STEPS)]  # == stream_frame
+    d2 = torch.empty((per, 21, 2), dtype=torch.float64, device=dev)
+    d3 = torch.empty((per, 21, 3), dtype=torch.float32, device=dev)
+    packed = torch.zeros((per, 21, 5), dtype=torch.float64, device=dev)
+    gathered = torch.empty((C4_STEPS, world * per, 21, 5), dtype=torch.float64, device=dev)
+    ceng.set_packed_results(packed.data_ptr())
+    ids = np.arange(per, dtype=np.int32)
+
+    def run(record):
+        ceng.reset()
+        for k in range(C4_STEPS):
+            t = 1000 + k / 30
+            ceng.estimate_device(frames[k].data_ptr(), per, BOX, BOX, d2.data_ptr(), d3.data_ptr(), ids,
+                                 np.full(per, t), np.full(per, t + 0.004))
+            if world > 1:
+                parallel.all_gather_packed(packed, gathered[k] if record else gathered[0])
+            elif record:
+                gathered[k].copy_(packed)
+
+    run(False)  # warm-up: function attributes, CUDA graph capture, NCCL channels
+    run(False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    run(True)
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    out = {"streams": C4_STREAMS, "steps": C4_STEPS, "streams_per_gpu": per, "scaling": "strong",
+           "value": C4_STREAMS * C4_STEPS / (ms * 1e-3), "unit": "frames/s", "ms_total": ms,
+           "data": "synth.stream_frame streams resident in HBM, results all-gathered every step"}
+    ceng.close()
+    # ---- T6: the gathered results equal the single-GPU answer bit for bit (outside the timed region, rank 0 only)
+    if rank == 0:
+        got = gathered.cpu().numpy()[:, parallel.unshard_index(C4_STREAMS, world)]          # [steps, 256, 21, 5]
+        chunk = 64
+        seng = VNectEngine(seeded_init("W0"), SCALES, BOX, max_frames=chunk, max_streams=C4_STREAMS, device=local)
+        seng.set_cuda_stream(stream.cuda_stream)
+        sp = torch.zeros((chunk, 21, 5), dtype=torch.float64, device=dev)
+        s2 = torch.empty((chunk, 21, 2), dtype=torch.float64, device=dev)
+        s3 = torch.empty((chunk, 21, 3), dtype=torch.float32, device=dev)
+        seng.set_packed_results(sp.data_ptr())
+        want = np.empty_like(got)
+        for c0 in range(0, C4_STREAMS, chunk):
+            sb = torch.from_numpy(np.stack([np.random.default_rng(2000 + s).integers(0, 256, (BOX, BOX, 3), dtype=np.uint8)
+                                            for s in range(c0, c0 + chunk)])).to(dev)
+            for k in range(C4_STEPS):
+                fr = torch.roll(sb, shifts=(k, 2 * k), dims=(1, 2)).contiguous()
+                tt = 1000 + k / 30
+                seng.estimate_device(fr.data_ptr(), chunk, BOX, BOX, s2.data_ptr(), s3.data_ptr(),
+                                     np.arange(c0, c0 + chunk, dtype=np.int32), np.full(chunk, tt), np.full(chunk, tt + 0.004))
+                torch.cuda.synchronize()
+                want[k, c0:c0 + chunk] = sp.cpu().numpy()
+        seng.close()
+        same = bool(np.array_equal(got, want))
+        out["bit_identical_to_single_gpu"] = same
+        if not same:
+            bad = np.argwhere(np.any(got != want, axis=(2, 3)))
+            out["first_mismatch_step_stream"] = [int(v) for v in bad[0]]
+        assert same, "C4: gathered multi-GPU results differ from the single-GPU run"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -156,6 +251,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 strong-scaling leg (256 streams x 32 steps)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -174,8 +270,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version there)
+        # stdout carries exactly one JSON line; NCCL's own log (version, "nranks N" of the communicator) goes to
+        # stderr instead of being muted, so the rank count of the gather can be read from the run's log
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     nf = args.frames
     n_streams = nf * world
@@ -196,6 +295,10 @@ def main():
     dev_frames = host_frames.to(dev)
     d_j2 = torch.empty((nf, 21, 2), dtype=torch.float64, device=dev)
     d_j3 = torch.empty((nf, 21, 3), dtype=torch.float32, device=dev)
+    # the exchange buffer of the gather: the post-process kernel itself writes (row, col, x, y, z) float64 here
+    d_packed = torch.zeros((nf, 21, 5), dtype=torch.float64, device=dev)
+    g_all = torch.empty((world * nf, 21, 5), dtype=torch.float64, device=dev)
+    eng.set_packed_results(d_packed.data_ptr())
     ids = np.arange(nf, dtype=np.int32)
     tclock = {"t": 1000.0}
 
@@ -207,9 +310,7 @@ def main():
         t2, t3 = stamps()
         eng.estimate_device(dev_frames.data_ptr(), nf, BOX, BOX, d_j2.data_ptr(), d_j3.data_ptr(), ids, t2, t3)
         if world > 1:
-            packed = torch.cat([d_j2, d_j3.to(torch.float64)], dim=2)
-            out = torch.empty((world * nf, 21, 5), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(out, packed)
+            parallel.all_gather_packed(d_packed, g_all)
 
     def barrier():
         if world > 1:
@@ -259,9 +360,11 @@ def main():
             return
         if g_work[lane] is not None:
             g_work[lane].wait()
+        # the batch of this lane has completed (wait(lane)); d_packed holds a LATER batch by now, so the slots are
+        # refilled from the lane's host results (vnect_b200.parallel layout)
         g_in[lane][:, :, :2].copy_(outs[lane][2], non_blocking=True)
         g_in[lane][:, :, 2:].copy_(outs[lane][3], non_blocking=True)
-        g_work[lane] = dist.all_gather_into_tensor(g_out[lane], g_in[lane], async_op=True)
+        _, g_work[lane] = parallel.all_gather_packed(g_in[lane], g_out[lane], async_op=True)
 
     def e2e_steps(k):
         for i in range(k):
@@ -290,6 +393,24 @@ def main():
     e2e_value = n_streams * args.steps / float(t.item())
     clocks = sampler.stop() if rank == 0 else None  # sampled across both timed regions (value and e2e)
 
+    # ---------------------------------------------------------------- sustained figure (>= 2 s of back-to-back steps)
+    barrier()
+    sus_steps = max(args.steps, int(2.2 / max(ms_max / args.steps * 1e-3, 1e-5)))
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for _ in range(sus_steps):
+        device_step()
+    s1.record(stream)
+    barrier()
+    t = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sustained = {"value": n_streams * sus_steps / (float(t.item()) * 1e-3), "unit": "frames/s", "steps": sus_steps,
+                 "seconds": float(t.item()) * 1e-3}
+
+    # ---------------------------------------------------------------- C4: 256 streams sharded i mod G, strong scaling
+    c4 = run_c4(eng, parallel, dev, stream, rank, world, local, barrier) if not args.no_c4 else None
+
     # ---------------------------------------------------------------- roofline of the conv-GEMM kernel family
     barrier()
     fwd_ms, per = eng.time_forward(nf * len(SCALES), reps=3, per_layer=True)
@@ -302,8 +423,13 @@ def main():
         with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as f:
             tj = json.load(f)
         if tj.get("frames_per_step") == nf:
+            import hashlib
             traffic = tj["conv_family_dram_bytes_per_step"]
-            traffic_note = "dram__bytes_read.sum + dram__bytes_write.sum summed over the family's launches of one step, " + tj["source"]
+            with open(os.path.join(ROOT, "profiles", "conv_traffic.json"), "rb") as fb:
+                digest = hashlib.sha256(fb.read()).hexdigest()[:16]
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the family's launches of one step, "
+                            + tj["source"] + "; NOT measured in this run: read from profiles/conv_traffic.json (sha256 "
+                            + digest + ", captured at commit " + str(tj.get("captured_at_commit")) + ")")
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<*> (implicit-GEMM conv family, %d launches per forward batch)" % (len(per) - 1),
@@ -314,6 +440,7 @@ def main():
                     "achieved_gbs": traffic / (conv_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
                     "frac": traffic / (conv_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                     "note": "the family mixes tensor-bound 3x3 convs with HBM-bound 1x1 expand convs; per-launch numbers in profiles/r01_step_traffic.txt"},
+                "frac_of_burst": achieved / peaks["bf16_tflops"],
                 "conv_ms_per_batch": conv_ms, "forward_ms_per_batch": fwd_ms,
                 "flops_per_forward_executed": EXECUTED_FLOPS_PER_FORWARD, "flops_per_forward_reference": FLOPS_PER_FORWARD}
 
@@ -354,6 +481,8 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "sustained": sustained,
+            "c4_strong_scaling": c4,
             "latency_ms_p50_batch1": statistics.median(lat) if lat else None,
             "latency_ms_p95_batch1": lat[int(0.95 * (len(lat) - 1))] if lat else None,
         }

@@ -5,7 +5,8 @@
  * Each entry point below names the reference interface it replaces.  Plain pointers and sizes only; every buffer
  * passed in or out is owned by the caller, the handle owns device weights, workspaces and per-stream filter state.
  * All functions return 0 on success or a negative VNECT_E_* code; vnect_last_error() gives the message.
- * One handle = one device + one CUDA stream; a handle is not thread-safe (neither is the reference object).
+ * One handle = one device + one CUDA stream; a handle is not thread-safe (neither is the reference object).  A process
+ * may hold handles on several devices: every entry point switches to its handle's device and restores the caller's.
  */
 #ifndef VNECT_B200_H
 #define VNECT_B200_H
@@ -108,12 +109,29 @@ int vnect_postprocess(vnect_t* h, const float* hm, const float* xm, const float*
                       int32_t offset_y, double* joints2d, float* joints3d, int32_t* raw_argmax);
 
 /* replaces VNectEstimator.joint_filter (src/estimator.py:83-95) on explicit values: one step of the 21*dim scalar
- * filters of a stream at clock reading t.  values: host float64 [21*dim], filtered in place (dim 3 values are
- * rounded to float32 like the reference's float32 array). */
-int vnect_filter(vnect_t* h, int32_t stream_id, int32_t dim, double t, double* values);
+ * filters of a stream at clock reading t.  values: host float64 [21*dim], filtered in place.  values_are_f32 = 1 when
+ * the caller's array is float32 (the reference's joints_3d, src/utils.py:186): the raw difference is then taken in
+ * float32 and the results are rounded to float32; 0 for a float64 array (joints_2d).
+ * Errors like the reference: a repeated timestamp is VNECT_E_ZERO_DT (ZeroDivisionError, src/OneEuroFilter.py:66), an
+ * earlier one VNECT_E_INVALID (ValueError "alpha ... should be in (0.0, 1.0]", src/OneEuroFilter.py:21-22); both are
+ * detected before the stream's state is touched.  The same checks guard vnect_estimate / vnect_submit / vnect_track. */
+int vnect_filter(vnect_t* h, int32_t stream_id, int32_t dim, int32_t values_are_f32, double t, double* values);
 
 /* forget the temporal-filter state of one stream (a new VNectEstimator() in the reference); -1 = all streams */
 int vnect_reset_stream(vnect_t* h, int32_t stream_id);
+
+/* Temporal state of one stream as VNECT_STREAM_STATE_DOUBLES plain doubles: the 42 + 63 OneEuroFilter objects of
+ * src/estimator.py:46-53 ({prev, s_x, s_dx, lasttime, freq, has_prev, has_time} each), the two last clock readings and
+ * the tracked crop box.  Lets a caller move a stream to another handle / GPU or keep it across a rebuild of the device
+ * context (the reference keeps one filter set for the lifetime of its estimator object). */
+#define VNECT_STREAM_STATE_DOUBLES (7 * 21 * 5 + 6)
+int vnect_export_stream_state(vnect_t* h, int32_t stream_id, double* state);
+int vnect_import_stream_state(vnect_t* h, int32_t stream_id, const double* state);
+
+/* Multi-GPU gather layout: when dev_packed (DEVICE pointer, float64 [max_frames][21][5]) is set, every later
+ * estimate / submit / track call also writes (row, col, x, y, z) per joint there, straight from the post-process
+ * kernel -- the buffer a caller hands to ncclAllGather.  NULL turns it off. */
+int vnect_set_packed_results(vnect_t* h, void* dev_packed);
 
 /* run on a caller-provided cudaStream_t (e.g. torch's current stream) instead of the handle's own */
 int vnect_set_stream(vnect_t* h, void* cuda_stream);
@@ -122,6 +140,10 @@ int vnect_synchronize(vnect_t* h);
 /* introspection for tests and benchmarks */
 int vnect_get_tap(vnect_t* h, const char* name, int32_t n, float* out_nhwc, int64_t capacity_elems,
                   int32_t* dims4 /* n, H, W, C */);
+/* unfiltered (row, col) argmax in box pixels of the frames of the most recent estimate / submit / track call
+ * (what utils.extract_2d_joints returns, src/utils.py:153-175, before joint_filter): int32 [n_frames][21][2].
+ * Waits for that call to complete.  Parity tests use it to prove that an argmax difference is a near-tie. */
+int vnect_get_raw_argmax(vnect_t* h, int32_t n_frames, int32_t* raw_argmax);
 int64_t vnect_launch_count(vnect_t* h);      /* kernels launched by this handle so far */
 double vnect_info(vnect_t* h, const char* key); /* "flops_per_forward", "num_sms", "conv_launches_per_forward", ... */
 /* device time of `reps` back-to-back forwards of n images already in device memory (CUDA events on the handle's

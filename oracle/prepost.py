@@ -90,6 +90,27 @@ def resize_f32_np(img, fx, fy):
     return t[y0] * b0 + t[y1] * b1
 
 
+def area2x_u8(img):
+    """cv2.resize(u8, fx=fy=0.5, INTER_LINEAR) == INTER_AREA with scale 2 (resizeAreaFast): full 2x2 blocks are
+    (sum + 2) >> 2; a partial last block (odd source side, dsize = cvRound(side / 2)) averages its in-range pixels as
+    saturate_cast<uchar>(float(sum) / count).  Restated for squarify_kernel mode 1; pinned against cv2 by
+    tests/test_oracle_prepost.py."""
+    h, w = img.shape[:2]
+    dw, dh = cv_round(w * 0.5), cv_round(h * 0.5)
+    s = img.astype(np.int32)
+    out = np.zeros((dh, dw, img.shape[2]), np.uint8)
+    for dy in range(dh):
+        ys = [y for y in (2 * dy, 2 * dy + 1) if y < h]
+        for dx in range(dw):
+            xs = [x for x in (2 * dx, 2 * dx + 1) if x < w]
+            tot = sum(s[y, x] for y in ys for x in xs)
+            if len(ys) == 2 and len(xs) == 2:
+                out[dy, dx] = (tot + 2) >> 2
+            else:
+                out[dy, dx] = np.rint(tot.astype(np.float32) / np.float32(len(ys) * len(xs))).astype(np.uint8)
+    return out
+
+
 def _fma(a, b, c):
     return float(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
 

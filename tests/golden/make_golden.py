@@ -14,6 +14,11 @@ Fixtures (all small):
   filter.npz  OneEuroFilter on a seeded noisy signal (float64), irregular timestamps
   e2e.npz     VNectEstimator.__call__ with the CNN restatement (W0) on test_pic + synthetic frames
   test_pic.npz  decoded pixels of pic/test_pic.jpg (C1 input; the GPU box has no reference tree)
+  filter_joint.npz  VNectEstimator.joint_filter (estimator.py:83-95) called directly: dim 2 (float64) and dim 3 (float32)
+  video.npz   first 12 decoded frames of pic/test_video.mp4 (C3 input) + the reference's video loop on them
+              (run_estimator.py:98-119 executed verbatim around the reference estimator, CNN restatement W0)
+
+`python tests/golden/make_golden.py filter_joint video` regenerates only the named fixtures.
 """
 import hashlib
 import os
@@ -67,9 +72,100 @@ def post_frame_maps(seed, k, scales):
     return synth.synthetic_maps(seed * 100 + k, len(scales), border_joints=(k % 2 == 0))
 
 
+JF_STEPS = 7
+VIDEO_FRAMES = 12
+VIDEO_SCALES = [1.0, 0.7]
+
+
+def joint_filter_inputs(dim):
+    """Seeded joint trajectories for the standalone joint_filter fixture: [JF_STEPS, 21, dim] + irregular timestamps."""
+    rng = np.random.default_rng(300 + dim)
+    base = rng.uniform(20, 340, (21, dim)) if dim == 2 else rng.uniform(-600, 600, (21, dim))
+    x = base[None] + np.cumsum(rng.standard_normal((JF_STEPS, 21, dim)) * 4, axis=0)
+    t = 2000 + np.cumsum(rng.uniform(0.012, 0.07, JF_STEPS))
+    if dim == 2:
+        x = np.rint(x)  # argmax output is integer valued
+    return (x.astype(np.float64) if dim == 2 else x.astype(np.float32)), t
+
+
+def video_timestamps(n):
+    return 1000 + np.arange(n) / 25.0  # SURVEY.md section 8d C3: t_k = 1000 + k/25 for both filter groups
+
+
+def reference_tracker_lines():
+    """run_estimator.py:110-119 (the bounding-box update), as source text to be exec'd verbatim."""
+    import textwrap
+    src = open(os.path.join(ref_shim.REFERENCE_ROOT, "run_estimator.py")).read().splitlines()
+    first = next(i for i, line in enumerate(src) if "y_min = (np.min(joints_2d[:, 0]))" in line)
+    body = textwrap.dedent("\n".join(src[first:first + 10]))
+    assert "H_img - y" in body
+    return body
+
+
+def make_filter_joint(est_mod):
+    out = dict(versions=str(VERSIONS))
+    for dim in (2, 3):
+        est, em = ref_shim.make_reference_estimator(lambda b: None, [1.0])
+        x, t = joint_filter_inputs(dim)
+        ys = []
+        real_time = em.time
+        try:
+            for k in range(JF_STEPS):
+                em.time = ref_shim.ScriptedClock([float(t[k])])
+                j = x[k].copy()
+                r = est.joint_filter(j, dim=dim)
+                assert r is j  # in place, like the reference's callers rely on
+                ys.append(j.copy())
+        finally:
+            em.time = real_time
+        out[f"d{dim}/x"], out[f"d{dim}/t"], out[f"d{dim}/y"] = x, t, np.array(ys)
+    np.savez_compressed(os.path.join(OUT, "filter_joint.npz"), **out)
+
+
+def make_video():
+    cap = cv2.VideoCapture(os.path.join(ref_shim.REFERENCE_ROOT, "pic", "test_video.mp4"))
+    assert cap.isOpened()
+    frames = []
+    for _ in range(VIDEO_FRAMES):
+        ok, f = cap.read()
+        assert ok
+        frames.append(f)
+    frames = np.stack(frames)
+    H_img, W_img = frames.shape[1:3]
+    net = OracleNet(make_weights("W0"))
+    est, em = ref_shim.make_reference_estimator(net, VIDEO_SCALES)
+    body = reference_tracker_lines()
+    t = video_timestamps(VIDEO_FRAMES)
+    x, y, w, h = 0, 0, W_img, H_img  # run_estimator.py:68, no HOG click (C3: fixed initial crop = full frame)
+    j2s, j3s, boxes = [], [], []
+    for k in range(VIDEO_FRAMES):
+        frame = frames[k]
+        boxes.append((x, y, w, h))
+        frame_cropped = frame[y: y + h, x: x + w, :]            # run_estimator.py:100
+        joints_2d, joints_3d = ref_shim.run_reference(est, em, frame_cropped, float(t[k]), float(t[k]))
+        joints_2d[:, 0] += y                                    # :104-105
+        joints_2d[:, 1] += x
+        ns = dict(np=np, joints_2d=joints_2d, W_img=W_img, H_img=H_img)
+        exec(body, ns)                                          # :110-119 verbatim
+        x, y, w, h = ns["x"], ns["y"], ns["w"], ns["h"]
+        j2s.append(joints_2d.copy())
+        j3s.append(joints_3d.copy())
+    np.savez_compressed(os.path.join(OUT, "video.npz"), frames=frames, t=t, j2=np.array(j2s), j3=np.array(j3s),
+                        boxes=np.array(boxes, np.int32), versions=str(VERSIONS))
+
+
 def main():
     assert ref_shim.reference_available(), "run in the dev container (needs /root/reference)"
     utils, oef, est_mod = ref_shim.load_reference_modules()
+    only = set(sys.argv[1:])
+    if only:
+        if "filter_joint" in only:
+            make_filter_joint(est_mod)
+        if "video" in only:
+            make_video()
+        return
+    make_filter_joint(est_mod)
+    make_video()
 
     # ---- pre.npz
     pre = dict(versions=str(VERSIONS))

@@ -23,7 +23,9 @@ def test_variable_inventory():
     assert shapes["res5c_branch2a/kernel"] == (4, 4, 128, 256)
     assert shapes["res5c_branch2c/kernel"] == (1, 1, 128, 84)
     assert shapes["res5c_branch2b/weights"] == (3, 3, 212, 128)
-    assert sum(int(np.prod(s)) for n, s in shapes.items() if n.endswith(("weights", "kernel"))) == 14_578_880 + 0 or True
+    # "~14.6 M weights + ~22 k biases"; exact counts of the 55 kernels and of all 109 variables
+    assert sum(int(np.prod(s)) for n, s in shapes.items() if n.endswith(("weights", "kernel"))) == 14_596_288
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 14_615_936
 
 
 def test_weights_are_deterministic():

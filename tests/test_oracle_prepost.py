@@ -203,3 +203,55 @@ def test_tracker_update_known_values():
     j2[:, 0] = np.linspace(100.0, 400.0, 21)   # rows
     j2[:, 1] = np.linspace(300.5, 420.25, 21)  # cols
     assert prepost.tracker_update(j2, 960, 540) == (252, 69, 216, 360)
+
+
+# ------------------------------------------------------------------------------------------------ round-2 fixtures
+def test_joint_filter_golden(golden):
+    """tests/golden/filter_joint.npz: the reference's VNectEstimator.joint_filter (estimator.py:83-95) called directly,
+    dim 2 on a float64 array and dim 3 on a float32 one, irregular timestamps."""
+    from tests.golden.make_golden import JF_STEPS, joint_filter_inputs
+    g = golden("filter_joint.npz")
+    for dim in (2, 3):
+        x, t = joint_filter_inputs(dim)
+        assert np.array_equal(x, g[f"d{dim}/x"]) and np.array_equal(t, g[f"d{dim}/t"])  # inputs are reproducible
+        clock = _Clock()
+        est = prepost.OracleEstimator(None, [1.0], clock=clock, promotion="numpy")
+        legacy = prepost.OracleEstimator(None, [1.0], clock=_Clock(), promotion="legacy")
+        for k in range(JF_STEPS):
+            clock.q = [float(t[k])]
+            legacy.clock.q = [float(t[k])]
+            y = est.joint_filter(x[k].copy(), dim)
+            assert y.dtype == g[f"d{dim}/y"].dtype and np.array_equal(y, g[f"d{dim}/y"][k]), (dim, k)
+            yl = legacy.joint_filter(x[k].copy(), dim)
+            if dim == 2:
+                assert np.array_equal(yl, y)
+            else:  # numpy-1.x promotion (what the CUDA path implements) vs numpy >= 2: float32 rounding noise only
+                assert np.abs(yl.astype(np.float64) - y).max() < 1e-2
+
+
+def test_video_golden_tracked_loop(golden, oracle_net_w0):
+    """tests/golden/video.npz: the first frames of pic/test_video.mp4 through the reference's estimator + the verbatim
+    bounding-box lines of run_estimator.py:98-119 (C3).  OracleTracker + OracleEstimator must walk the same boxes."""
+    g = golden("video.npz")
+    frames, t = g["frames"], g["t"]
+    assert frames.shape[1:] == (540, 960, 3) and frames.dtype == np.uint8
+    clock = _Clock()
+    trk = prepost.OracleTracker(prepost.OracleEstimator(oracle_net_w0, [1.0, 0.7], clock=clock, promotion="numpy"),
+                                (0, 0, 960, 540))
+    for k in range(6):
+        clock.q = [float(t[k]), float(t[k])]
+        j2, j3, used = trk(frames[k])
+        assert used == tuple(int(v) for v in g["boxes"][k]), k
+        assert np.max(np.abs(j2 - g["j2"][k])) < 1e-6
+        assert np.max(np.abs(j3 - g["j3"][k])) < 0.05
+
+
+def test_area2x_partial_blocks_match_cv2():
+    """Exact 2x decimation of an odd-sided image (OpenCV switches INTER_LINEAR to INTER_AREA, and the last partial
+    block averages only its in-range pixels): the arithmetic squarify_kernel mode 1 implements."""
+    import cv2
+    rng = np.random.default_rng(3)
+    for h, w in ((36, 35), (35, 36), (35, 35), (7, 8)):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = cv2.resize(img, (0, 0), fx=0.5, fy=0.5, interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(prepost.area2x_u8(img), ref), (h, w)

@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libvnect_b200.so")
 
 OK, E_INVALID, E_CUDA, E_WEIGHT, E_ZERO_DT, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 MAX_SCALES = 4
+STREAM_STATE_DOUBLES = 7 * 21 * 5 + 6
 
 
 class Config(C.Structure):
@@ -42,9 +43,13 @@ SIGNATURES = {
     "vnect_estimate_device": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
     "vnect_preprocess": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "vnect_postprocess": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, _P, _P, _P, C.c_double, C.c_int32, C.c_int32, _P, _P, _P]),
-    "vnect_filter": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_double, _P]),
+    "vnect_filter": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_double, _P]),
+    "vnect_export_stream_state": (C.c_int, [_P, C.c_int32, _P]),
+    "vnect_import_stream_state": (C.c_int, [_P, C.c_int32, _P]),
+    "vnect_get_raw_argmax": (C.c_int, [_P, C.c_int32, _P]),
     "vnect_reset_stream": (C.c_int, [_P, C.c_int32]),
     "vnect_set_stream": (C.c_int, [_P, _P]),
+    "vnect_set_packed_results": (C.c_int, [_P, _P]),
     "vnect_synchronize": (C.c_int, [_P]),
     "vnect_get_tap": (C.c_int, [_P, C.c_char_p, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int32)]),
     "vnect_launch_count": (C.c_int64, [_P]),

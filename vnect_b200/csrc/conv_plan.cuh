@@ -8,8 +8,6 @@
 #include <string>
 
 #include "conv_gemm.cuh"
-#include "stem_gemm.cuh"
-#include "stem_pool.cuh"
 #include "stem_roll.cuh"
 
 namespace vnect {
@@ -358,16 +356,27 @@ inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cud
   return launch_pdl_cluster(kern, grid, block, smem, st, 1, args...);
 }
 
+// cudaFuncSetAttribute is per device (context): remember, per kernel instantiation, which devices of this process
+// already carry the opt-in.  One bit per device ordinal; a process holds at most one handle per GPU of an 8-GPU box.
+template <typename Kern>
+inline cudaError_t ensure_dyn_smem(Kern kern, int bytes, unsigned long long* done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(done_mask, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  __atomic_fetch_or(done_mask, bit, __ATOMIC_RELEASE);
+  return cudaSuccess;
+}
+
 template <int BLOCK_N, int SWZ, int EPI, int CG = 1>
 inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
   using Cfg = GemmCfg<BLOCK_N, SWZ, EPI, CG>;
-  static bool attr_set = false;
+  static unsigned long long done = 0;
   auto kern = conv_gemm_kernel<BLOCK_N, SWZ, EPI, CG>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = ensure_dyn_smem(kern, Cfg::SMEM_BYTES, &done); e != cudaSuccess) return e;
   return launch_pdl_cluster(kern, dim3(L.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, CG, L.tmap_a, L.tmap_b,
                             L.tmap_out, L.tmap_res, L.tmap_a2, L.p);
 }
@@ -375,13 +384,9 @@ inline cudaError_t launch_one(const ConvLaunch& L, cudaStream_t st) {
 template <int BLOCK_N, int SWZ, int EPI>
 inline cudaError_t launch_one_bres(const ConvLaunch& L, cudaStream_t st) {
   using Cfg = GemmCfg<BLOCK_N, SWZ, EPI, 1, true>;
-  static bool attr_set = false;
+  static unsigned long long done = 0;
   auto kern = conv_gemm_kernel<BLOCK_N, SWZ, EPI, 1, true>;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  if (cudaError_t e = ensure_dyn_smem(kern, Cfg::SMEM_BYTES, &done); e != cudaSuccess) return e;
   return launch_pdl(kern, dim3(L.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, L.tmap_a, L.tmap_b, L.tmap_out,
                     L.tmap_res, L.tmap_a2, L.p);
 }
@@ -428,70 +433,10 @@ inline cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// conv1 through stem_gemm_kernel (raw-strip A operand).  Output buffer: [NB][tiles_per_image*128 virtual px][64].
-struct StemLaunch {
-  CUtensorMap tmap_out;
-  StemParams p;
-  int grid = 0;
-  int out_h = 0, out_w = 0;   // S/2
-  int vw = 0;                 // virtual row pitch in pixels (S/2 + 3)
-  int64_t img_px = 0;         // virtual pixels per image (tiles_per_image * 128)
-};
-
-// [64][224] K-major (k = ky*32 + kx*4 + c) -> canonical no-swizzle layout [k/8][n][k%8]
-inline void pack_stem_canonical(const __half* kmajor, __half* out) {
-  for (int n = 0; n < 64; ++n)
-    for (int k = 0; k < 224; ++k) out[((k / 8) * 64 + n) * 8 + (k % 8)] = kmajor[n * 224 + k];
-}
-
-inline bool build_stem(const __half* x1, int S, int rows_per_parity, int row_pitch, const __half* w_canonical,
-                       const float* bias, __half* out, int nb_capacity, int num_sms, StemLaunch* L, std::string* err) {
-  memset(L, 0, sizeof(*L));
-  L->out_h = L->out_w = S / 2;
-  L->vw = S / 2 + 3;
-  if (row_pitch * 2 != L->vw * 16) {
-    if (err) *err = "stem row pitch must be (S/2+3)*16 bytes";
-    return false;
-  }
-  const int tpi = (L->out_h * L->vw + kBlockM - 1) / kBlockM;
-  L->img_px = (int64_t)tpi * kBlockM;
-  L->p.x1 = reinterpret_cast<const uint8_t*>(x1);
-  L->p.plane_bytes = (int64_t)rows_per_parity * row_pitch * 2;
-  L->p.w = reinterpret_cast<const uint8_t*>(w_canonical);
-  L->p.bias = bias;
-  L->p.vw = L->vw;
-  L->p.tiles_per_image = tpi;
-  L->p.num_tiles = nb_capacity * tpi;
-  L->grid = L->p.num_tiles < num_sms ? L->p.num_tiles : num_sms;
-  uint64_t od[5] = {64, (uint64_t)nb_capacity * tpi * kBlockM, 1, 1, 1};
-  uint64_t os[4] = {128, 128ull * od[1], 128ull * od[1], 128ull * od[1]};
-  uint32_t ob[5] = {64, kBlockM, 1, 1, 1};
-  return encode_tmap(&L->tmap_out, out, 5, od, os, ob, 128, err);
-}
-
-inline void stem_set_batch(StemLaunch& L, int nb, int num_sms, int img0 = 0) {
-  L.p.img0 = img0;
-  L.p.num_tiles = nb * L.p.tiles_per_image;
-  L.grid = L.p.num_tiles < num_sms ? L.p.num_tiles : num_sms;
-}
-
-inline cudaError_t launch_stem(const StemLaunch& L, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(stem_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  stem_gemm_kernel<<<L.grid, kGemmThreads, StemSmem::BYTES, st>>>(L.tmap_out, L.p);
-  return cudaGetLastError();
-}
-
-// conv1 + pool1 fused (stem_pool.cuh)
+// conv1 + pool1 fused (stem_roll.cuh)
 struct StemPoolLaunch {
-  StemPoolParams p;   // band kernel (stem_pool.cuh), kept as the A/B baseline
-  StemRollParams r;   // rolling kernel (stem_roll.cuh), used when stacked weights are supplied
-  bool roll = false;
-  int grid = 0, grid_roll = 0;
+  StemRollParams r;
+  int grid = 0;
 };
 
 // [64][224] K-major (k = ky*32 + kx*4 + c) -> the rolling kernel's stacked weights: rows (ky = 6, 4, 2, 0) x 64 couts for
@@ -535,90 +480,54 @@ inline void stem_roll_set_batch(StemRollParams& r, int nb, int num_sms, int* gri
   *grid = r.num_items < num_sms ? r.num_items : num_sms;
 }
 
-inline bool build_stem_pool(const __half* x1, int S, int rows_per_parity, int row_pitch, const __half* w_canonical,
+inline bool build_stem_pool(const __half* x1, int S, int rows_per_parity, int row_pitch, const __half* w_stacked,
                             const float* bias, __half* pooled_out, int nb, int num_sms, StemPoolLaunch* L,
-                            std::string* err, const __half* w_stacked = nullptr) {
+                            std::string* err) {
   memset(L, 0, sizeof(*L));
-  if (w_stacked) {
-    StemRollParams& r = L->r;
-    r.x1 = reinterpret_cast<const uint8_t*>(x1);
-    r.plane_bytes = (int64_t)rows_per_parity * row_pitch * 2;
-    r.w = reinterpret_cast<const uint8_t*>(w_stacked);
-    r.bias = bias;
-    r.out = pooled_out;
-    r.vw = S / 2 + 3;
-    r.CH = r.CW = S / 2;
-    r.PH = r.PW = S / 4;
-    int pb = 0;
-    while (pb < r.PW) {  // x tiles: 128 conv columns each, pooled columns split where a 3-wide window would cross
-      if (r.n_xt == kMaxXTiles) {
-        if (err) *err = "box size too large for the rolling stem";
-        return false;
-      }
-      int x0 = 2 * pb < r.CW - kBlockM ? 2 * pb : r.CW - kBlockM;
-      if (x0 < 0) x0 = 0;
-      const int pe = x0 + kBlockM >= r.CW ? r.PW : (x0 + kBlockM - 3) / 2 + 1;
-      r.xt_x0[r.n_xt] = x0;
-      r.xt_pb[r.n_xt] = pb;
-      r.xt_pe[r.n_xt] = pe;
-      ++r.n_xt;
-      pb = pe;
-    }
-    stem_roll_set_batch(r, nb, num_sms, &L->grid_roll);
-    L->roll = true;
-  }
-  StemPoolParams& p = L->p;
-  p.vw = S / 2 + 3;
-  if (row_pitch * 2 != p.vw * 16 || S % 16 != 0) {
+  StemRollParams& r = L->r;
+  r.vw = S / 2 + 3;
+  if (row_pitch * 2 != r.vw * 16 || S % 16 != 0) {
     if (err) *err = "stem row pitch must be (S/2+3)*16 bytes and S a multiple of 16";
     return false;
   }
-  p.x1 = reinterpret_cast<const uint8_t*>(x1);
-  p.plane_bytes = (int64_t)rows_per_parity * row_pitch * 2;
-  p.w = reinterpret_cast<const uint8_t*>(w_canonical);
-  p.bias = bias;
-  p.out = pooled_out;
-  p.CH = p.CW = S / 2;
-  p.PH = p.PW = S / 4;
-  p.ppb = (5 * p.vw <= kBandTiles * kBlockM) ? 2 : 1;
-  p.band_tiles = ((2 * p.ppb + 1) * p.vw + kBlockM - 1) / kBlockM;
-  if (p.band_tiles > kBandTiles) {
-    if (err) *err = "box size too large for the fused stem";
-    return false;
+  r.x1 = reinterpret_cast<const uint8_t*>(x1);
+  r.plane_bytes = (int64_t)rows_per_parity * row_pitch * 2;
+  r.w = reinterpret_cast<const uint8_t*>(w_stacked);
+  r.bias = bias;
+  r.out = pooled_out;
+  r.CH = r.CW = S / 2;
+  r.PH = r.PW = S / 4;
+  int pb = 0;
+  while (pb < r.PW) {  // x tiles: 128 conv columns each, pooled columns split where a 3-wide window would cross
+    if (r.n_xt == kMaxXTiles) {
+      if (err) *err = "box size too large for the rolling stem";
+      return false;
+    }
+    int x0 = 2 * pb < r.CW - kBlockM ? 2 * pb : r.CW - kBlockM;
+    if (x0 < 0) x0 = 0;
+    const int pe = x0 + kBlockM >= r.CW ? r.PW : (x0 + kBlockM - 3) / 2 + 1;
+    r.xt_x0[r.n_xt] = x0;
+    r.xt_pb[r.n_xt] = pb;
+    r.xt_pe[r.n_xt] = pe;
+    ++r.n_xt;
+    pb = pe;
   }
-  p.bands_per_image = p.PH / p.ppb;
-  p.num_items = nb * p.bands_per_image;
-  L->grid = p.num_items < num_sms ? p.num_items : num_sms;
+  stem_roll_set_batch(r, nb, num_sms, &L->grid);
   return true;
 }
 
-inline void stem_pool_set_batch(StemPoolLaunch& L, int nb, int num_sms) {
-  L.p.num_items = nb * L.p.bands_per_image;
-  L.grid = L.p.num_items < num_sms ? L.p.num_items : num_sms;
-  if (L.roll) stem_roll_set_batch(L.r, nb, num_sms, &L.grid_roll);
-}
+inline void stem_pool_set_batch(StemPoolLaunch& L, int nb, int num_sms) { stem_roll_set_batch(L.r, nb, num_sms, &L.grid); }
 
 inline cudaError_t launch_stem_pool(const StemPoolLaunch& L, cudaStream_t st) {
-  if (L.roll) {
-    static bool roll_attr_set = false;
-    if (!roll_attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(stem_roll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, StemRollSmem::BYTES);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(stem_roll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, StemRollSmem::BYTES);
-      if (e != cudaSuccess) return e;
-      roll_attr_set = true;
-    }
-    if (L.r.dbg != nullptr)
-      return launch_pdl(stem_roll_kernel<true>, dim3(L.grid_roll), dim3(kRollThreads), StemRollSmem::BYTES, st, L.r);
-    return launch_pdl(stem_roll_kernel<false>, dim3(L.grid_roll), dim3(kRollThreads), StemRollSmem::BYTES, st, L.r);
+  static unsigned long long done = 0;
+  cudaError_t e = ensure_dyn_smem(stem_roll_kernel<false>, StemRollSmem::BYTES, &done);
+  if (e != cudaSuccess) return e;
+  if (L.r.dbg != nullptr) {
+    static unsigned long long done_dbg = 0;
+    if ((e = ensure_dyn_smem(stem_roll_kernel<true>, StemRollSmem::BYTES, &done_dbg)) != cudaSuccess) return e;
+    return launch_pdl(stem_roll_kernel<true>, dim3(L.grid), dim3(kRollThreads), StemRollSmem::BYTES, st, L.r);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(stem_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemPoolSmem::BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  return launch_pdl(stem_pool_kernel, dim3(L.grid), dim3(kStemPoolThreads), StemPoolSmem::BYTES, st, L.p);
+  return launch_pdl(stem_roll_kernel<false>, dim3(L.grid), dim3(kRollThreads), StemRollSmem::BYTES, st, L.r);
 }
 
 }  // namespace vnect

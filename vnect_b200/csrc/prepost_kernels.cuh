@@ -134,10 +134,26 @@ __global__ void squarify_kernel(const uint8_t* __restrict__ in, uint8_t* __restr
       if (mode == 0) {
         cv_resize_u8_px(src, p.pitch, H, W, sy, sx, inv_scale, v);
       } else {
+        // OpenCV resizeAreaFast (exact 2x): full 2x2 blocks are (sum + 2) >> 2; where an odd source side leaves a
+        // partial block (e.g. 736x735 -> dw = cvRound(367.5) = 368), only the in-range pixels are averaged:
+        // saturate_cast<uchar>((float)sum / count), i.e. float division then round-half-even.
         const uint8_t* r0 = src + (int64_t)(2 * sy) * p.pitch + (int64_t)(2 * sx) * 3;
-        const uint8_t* r1 = r0 + p.pitch;
+        const bool col2 = 2 * sx + 1 < W, row2 = 2 * sy + 1 < H;
+        const uint8_t* r1 = r0 + (row2 ? p.pitch : 0);
+        const int dxo = col2 ? 3 : 0;
+        if (col2 && row2) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = (r0[c] + r0[3 + c] + r1[c] + r1[3 + c] + 2) >> 2;
+          for (int c = 0; c < 3; ++c) v[c] = (r0[c] + r0[3 + c] + r1[c] + r1[3 + c] + 2) >> 2;
+        } else {
+          const int count = (col2 ? 2 : 1) * (row2 ? 2 : 1);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            int sum = r0[c];
+            if (col2) sum += r0[dxo + c];
+            if (row2) sum += r1[c];
+            v[c] = __float2int_rn(__fdiv_rn((float)sum, (float)count));
+          }
+        }
       }
     }
     uint8_t* o = out + i * 3;
@@ -289,6 +305,8 @@ __device__ __forceinline__ double oef_alpha(double freq, double cutoff) {
 }
 
 // x_is_f32: numpy-1.x ("legacy") promotion for the float32 3D joints -- the raw difference is float32.
+// The host validates t > lasttime before anything is launched (a repeated timestamp is the reference's
+// ZeroDivisionError, an earlier one its LowPassFilter ValueError: alpha leaves (0, 1]), so freq stays positive here.
 __device__ __forceinline__ double oef_step(FilterState& st, const FilterCfg& cfg, double x, double t, bool x_is_f32) {
   if (st.has_time && st.lasttime != 0.0 && t != 0.0) st.freq = __ddiv_rn(1.0, __dsub_rn(t, st.lasttime));
   st.lasttime = t;
@@ -330,6 +348,7 @@ struct PostParams {
   unsigned int* frame_counter;    // [n_frames], zeroed before launch
   double* out2d;                  // [n_frames][21][2]
   float* out3d;                   // [n_frames][21][3]
+  double* packed;                 // optional [n_frames][21][5] = (row, col, x, y, z): the layout the multi-GPU gather moves
 };
 
 constexpr int kPostThreads = 128;
@@ -583,6 +602,7 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
       p.st3d[((size_t)p.stream_ids[frame] * kJoints + j) * 3 + c] = st;
     }
     p.out3d[(frame * kJoints + j) * 3 + c] = v;
+    if (p.packed != nullptr) p.packed[(frame * kJoints + j) * 5 + 2 + c] = (double)v;
   }
   if (tid < kJoints * 2) {
     const int j = tid >> 1, c = tid & 1;
@@ -599,6 +619,7 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
       v2 = __ddiv_rn(__dsub_rn(jb[j * 2 + c], off), scaler);
     }
     p.out2d[(frame * kJoints + j) * 2 + c] = v2;
+    if (p.packed != nullptr) p.packed[(frame * kJoints + j) * 5 + c] = v2;
   }
 }
 
@@ -635,12 +656,13 @@ __global__ void track_update_kernel(const double* __restrict__ joints2d, const i
 }
 
 // VNectEstimator.joint_filter (estimator.py:83-95) on explicit values: 21*dim scalar filters of one stream.
-__global__ void joint_filter_kernel(FilterState* st, FilterCfg cfg, double* values, double t, int dim) {
+// is_f32: the caller's array is float32 (the reference's joints_3d), so the raw difference and the stored result are.
+__global__ void joint_filter_kernel(FilterState* st, FilterCfg cfg, double* values, double t, int dim, int is_f32) {
   const int i = threadIdx.x;
   if (i >= kJoints * dim) return;
   FilterState s = st[i];
-  const double v = oef_step(s, cfg, values[i], t, dim == 3);
-  values[i] = dim == 3 ? (double)__double2float_rn(v) : v;
+  const double v = oef_step(s, cfg, values[i], t, is_f32 != 0);
+  values[i] = is_f32 ? (double)__double2float_rn(v) : v;
   st[i] = s;
 }
 

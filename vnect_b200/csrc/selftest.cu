@@ -270,126 +270,39 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   return bad == 0 ? 0 : 1;
 }
 
-// conv1 through stem_gemm_kernel (strip loads, resident weights) against the same naive reference
-static int run_stem2(int NB, int S, int num_sms) {
-  const int OH = S / 2, vw = OH + 3, rpp = OH + 3, pitch = vw * 8;
-  const size_t in_elems = (size_t)NB * 2 * rpp * pitch + 4096;
-  std::vector<__half> h_in(in_elems), h_w((size_t)64 * 224), h_wc((size_t)64 * 224);
-  for (auto& v : h_in) v = __float2half(frand());
-  for (auto& v : h_w) v = __float2half(frand() * 0.15f);
-  pack_stem_canonical(h_w.data(), h_wc.data());
-  std::vector<float> h_bias(64);
-  for (auto& v : h_bias) v = frand() * 0.5f;
-  __half *d_in, *d_w, *d_wc, *d_out;
-  float *d_bias, *d_acc;
-  CK(cudaMalloc(&d_in, in_elems * 2));
-  CK(cudaMalloc(&d_w, h_w.size() * 2));
-  CK(cudaMalloc(&d_wc, h_wc.size() * 2));
-  CK(cudaMalloc(&d_bias, 64 * 4));
-  CK(cudaMemcpy(d_in, h_in.data(), in_elems * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_w, h_w.data(), h_w.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_wc, h_wc.data(), h_wc.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_bias, h_bias.data(), 64 * 4, cudaMemcpyHostToDevice));
-  StemLaunch L;
-  std::string err;
-  const int tpi = (OH * vw + 127) / 128;
-  const size_t out_elems = (size_t)NB * tpi * 128 * 64;
-  CK(cudaMalloc(&d_out, out_elems * 2));
-  CK(cudaMemset(d_out, 0, out_elems * 2));
-  if (!build_stem(d_in, S, rpp, pitch, d_wc, d_bias, d_out, NB, num_sms, &L, &err)) {
-    printf("[stem2] build FAILED: %s\n", err.c_str());
-    return 1;
-  }
-  CK(launch_stem(L, 0));
-  cudaError_t se = cudaDeviceSynchronize();
-  if (se != cudaSuccess) {
-    printf("[stem2] kernel FAILED: %s\n", cudaGetErrorString(se));
-    exit(3);
-  }
-  NaiveGeom g;
-  memset(&g, 0, sizeof g);
-  g.kind = CONV_STEM7; g.NB = NB; g.H = OH; g.W = OH; g.cin_pad = 0; g.n_pad = 64; g.taps = 7; g.phases = 1;
-  g.k_total = 224; g.stem_rpp = rpp; g.stem_pitch = pitch; g.in_stride = 1;
-  for (int ky = 0; ky < 7; ++ky) { g.dy[ky] = (signed char)(ky >> 1); g.dx[ky] = 0; g.dp[ky] = (signed char)(ky & 1); }
-  const size_t acc_elems = (size_t)NB * OH * OH * 64;
-  CK(cudaMalloc(&d_acc, acc_elems * 4));
-  naive_acc_kernel<<<1184, 256>>>(d_in, d_w, d_acc, g);
-  CK(cudaDeviceSynchronize());
-  std::vector<float> h_acc(acc_elems);
-  std::vector<__half> h_out(out_elems);
-  CK(cudaMemcpy(h_acc.data(), d_acc, acc_elems * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(h_out.data(), d_out, out_elems * 2, cudaMemcpyDeviceToHost));
-  long long bad = 0, checked = 0;
-  double max_err = 0;
-  for (int n = 0; n < NB; ++n)
-    for (int y = 0; y < OH; ++y)
-      for (int x = 0; x < OH; ++x)
-        for (int c = 0; c < 64; ++c) {
-          const float exp = fmaxf(h_acc[(((size_t)n * OH + y) * OH + x) * 64 + c] + h_bias[c], 0.f);
-          const float got = __half2float(h_out[((size_t)n * L.img_px + (size_t)y * vw + x) * 64 + c]);
-          const float e = fabsf(got - exp);
-          if (!(e <= 3e-3f * fabsf(exp) + 3e-3f)) {
-            if (bad < 5) printf("   mismatch n%d y%d x%d c%d got %f exp %f\n", n, y, x, c, got, exp);
-            ++bad;
-          }
-          if (e > max_err) max_err = e;
-          ++checked;
-        }
-  printf("[stem2 strip-load conv1 S=%d nb=%d] tiles=%d grid=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n", S, NB,
-         L.p.num_tiles, L.grid, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
-  if (bad == 0) {
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) CK(launch_stem(L, 0));
-    CK(cudaEventRecord(e0));
-    for (int i = 0; i < 20; ++i) CK(launch_stem(L, 0));
-    CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
-    float ms;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    printf("   timing: %.2f us/launch\n", ms * 1000.0 / 20);
-  }
-  cudaFree(d_in); cudaFree(d_w); cudaFree(d_wc); cudaFree(d_bias); cudaFree(d_out); cudaFree(d_acc);
-  return bad == 0 ? 0 : 1;
-}
-
 // fused conv1 + pool1 against naive conv + host max-pool
-static int run_stem_pool(int NB, int S, int num_sms, bool roll = false) {
+static int run_stem_pool(int NB, int S, int num_sms) {
+  const bool roll = true;
   const int OH = S / 2, PH = S / 4, vw = OH + 3, rpp = OH + 3, pitch = vw * 8;
   const size_t in_elems = (size_t)NB * 2 * rpp * pitch + 8192;
-  std::vector<__half> h_in(in_elems), h_w((size_t)64 * 224), h_wc((size_t)64 * 224), h_ws((size_t)64 * 224);
+  std::vector<__half> h_in(in_elems), h_w((size_t)64 * 224), h_ws((size_t)64 * 224);
   for (auto& v : h_in) v = __float2half(frand());
   for (auto& v : h_w) v = __float2half(frand() * 0.15f);
-  pack_stem_canonical(h_w.data(), h_wc.data());
   pack_stem_stacked(h_w.data(), h_ws.data());
   std::vector<float> h_bias(64);
   for (auto& v : h_bias) v = frand() * 0.5f;
-  __half *d_in, *d_w, *d_wc, *d_ws, *d_out;
+  __half *d_in, *d_w, *d_ws, *d_out;
   CK(cudaMalloc(&d_ws, h_ws.size() * 2));
   CK(cudaMemcpy(d_ws, h_ws.data(), h_ws.size() * 2, cudaMemcpyHostToDevice));
   float *d_bias, *d_acc;
   CK(cudaMalloc(&d_in, in_elems * 2));
   CK(cudaMalloc(&d_w, h_w.size() * 2));
-  CK(cudaMalloc(&d_wc, h_wc.size() * 2));
   CK(cudaMalloc(&d_bias, 64 * 4));
   CK(cudaMemcpy(d_in, h_in.data(), in_elems * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_w, h_w.data(), h_w.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(d_wc, h_wc.data(), h_wc.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_bias, h_bias.data(), 64 * 4, cudaMemcpyHostToDevice));
   const size_t out_elems = (size_t)NB * PH * PH * 64;
   CK(cudaMalloc(&d_out, out_elems * 2));
   CK(cudaMemset(d_out, 0xff, out_elems * 2));
   StemPoolLaunch L;
   std::string err;
-  if (!build_stem_pool(d_in, S, rpp, pitch, d_wc, d_bias, d_out, NB, num_sms, &L, &err, roll ? d_ws : nullptr)) {
+  if (!build_stem_pool(d_in, S, rpp, pitch, d_ws, d_bias, d_out, NB, num_sms, &L, &err)) {
     printf("[stem_pool] build FAILED: %s\n", err.c_str());
     return 1;
   }
   unsigned long long* d_dbg;
   CK(cudaMalloc(&d_dbg, 8 * sizeof(unsigned long long)));
   CK(cudaMemset(d_dbg, 0, 8 * sizeof(unsigned long long)));
-  L.p.dbg = d_dbg;
   L.r.dbg = d_dbg;
   CK(launch_stem_pool(L, 0));
   cudaError_t se = cudaDeviceSynchronize();
@@ -435,20 +348,15 @@ static int run_stem_pool(int NB, int S, int num_sms, bool roll = false) {
   {
     unsigned long long h_dbg[8];
     CK(cudaMemcpy(h_dbg, d_dbg, sizeof h_dbg, cudaMemcpyDeviceToHost));
-    const double items0 = (double)((L.p.num_items + L.grid - 1) / L.grid);
+    const double items0 = (double)((L.r.num_items + L.grid - 1) / L.grid);
     if (!roll) printf("   CTA0 epilogue cycles per band: wait-MMA %.0f, drain %.0f, barrier %.0f, pool %.0f\n", h_dbg[0] / items0,
            h_dbg[1] / items0, h_dbg[2] / items0, h_dbg[3] / items0);
     if (roll) printf("   CTA0 epilogue cycles: wait-MMA %llu, drain %llu, pool %llu, total %llu\n", h_dbg[0], h_dbg[1], h_dbg[2], h_dbg[3]);
     if (roll) printf("   CTA0 MMA warp cycles: wait-strips %llu, wait-slot %llu, total %llu\n", h_dbg[4], h_dbg[5], h_dbg[6]);
-    L.p.dbg = nullptr;
     L.r.dbg = nullptr;
   }
-  if (roll)
-    printf("[stem_roll rolling conv1+pool1 S=%d nb=%d] items=%d grid=%d x-tiles=%d seg_rows=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n",
-           S, NB, L.r.num_items, L.grid_roll, L.r.n_xt, L.r.seg_rows, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
-  else
-    printf("[stem_pool fused conv1+pool1 S=%d nb=%d] items=%d grid=%d ppb=%d tiles/band=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n",
-           S, NB, L.p.num_items, L.grid, L.p.ppb, L.p.band_tiles, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
+  printf("[stem_roll rolling conv1+pool1 S=%d nb=%d] items=%d grid=%d x-tiles=%d seg_rows=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n",
+         S, NB, L.r.num_items, L.grid, L.r.n_xt, L.r.seg_rows, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
   if (bad == 0) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -462,8 +370,120 @@ static int run_stem_pool(int NB, int S, int num_sms, bool roll = false) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     printf("   timing: %.2f us/launch\n", ms * 1000.0 / 20);
   }
-  cudaFree(d_in); cudaFree(d_w); cudaFree(d_wc); cudaFree(d_bias); cudaFree(d_out); cudaFree(d_acc);
+  cudaFree(d_in); cudaFree(d_w); cudaFree(d_ws); cudaFree(d_bias); cudaFree(d_out); cudaFree(d_acc);
   return bad == 0 ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Descriptor probe: how does tcgen05.mma address a 128B-swizzled K-major A operand whose start address is NOT aligned
+// to the 1024-byte swizzle atom and whose 8-row groups are `pitch` rows apart?  (The halo-patch 3x3 convolution reads
+// its nine filter taps from ONE shared-memory patch by shifting the descriptor's start address by whole pixels.)
+// Rows are written exactly as the TMA unit writes a dense box: 16-byte chunk c of row r lands at
+// r*128 + ((c ^ (r & 7)) << 4) from a 1024-aligned base.  Logical A row m of the MMA is patch row
+// shift + (m / 8) * pitch + (m % 8).  bo = 1 sets the descriptor's base-offset field to (start >> 7) & 7.
+__global__ void __launch_bounds__(128, 1) desc_probe_kernel(const __half* __restrict__ a_rows, int n_rows,
+                                                             const __half* __restrict__ b_rows, float* __restrict__ d,
+                                                             int shift, int pitch, int bo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                                   // n_rows x 128 B
+  uint8_t* sb = smem + ((n_rows * 128 + 1023) / 1024) * 1024;  // 64 x 128 B
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n_rows * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(sa + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(a_rows + r * 64 + c * 8);
+  }
+  for (int i = tid; i < 64 * 8; i += 128) {
+    const int r = i >> 3, c = i & 7;
+    *reinterpret_cast<uint4*>(sb + r * 128 + ((c ^ (r & 7)) << 4)) = *reinterpret_cast<const uint4*>(b_rows + r * 64 + c * 8);
+  }
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (tid < 32) tmem_alloc<64>(&tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t a_addr = smem_u32(sa) + shift * 128;
+    uint64_t a_desc = 0;
+    a_desc |= static_cast<uint64_t>((a_addr & 0x3FFFF) >> 4);
+    a_desc |= static_cast<uint64_t>(1) << 16;
+    a_desc |= static_cast<uint64_t>((pitch * 128) >> 4) << 32;
+    a_desc |= 1ull << 46;
+    if (bo) a_desc |= static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
+    a_desc |= 2ull << 61;
+    const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(sb));
+    constexpr uint32_t IDESC = make_idesc_f16(128, 64, false);
+    for (int k = 0; k < 4; ++k) umma_f16(tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, k ? 1u : 0u);
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  {
+    const int warp = tid >> 5;
+    uint32_t v[32];
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) d[tid * 64 + c0 + j] = __uint_as_float(v[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc<64>(tmem);
+}
+
+static void run_desc_probe() {
+  const int n_rows = 288;
+  std::vector<__half> h_a((size_t)n_rows * 64), h_b((size_t)64 * 64);
+  for (auto& v : h_a) v = __float2half(frand());
+  for (auto& v : h_b) v = __float2half(frand());
+  __half *d_a, *d_b;
+  float* d_d;
+  CK(cudaMalloc(&d_a, h_a.size() * 2));
+  CK(cudaMalloc(&d_b, h_b.size() * 2));
+  CK(cudaMalloc(&d_d, 128 * 64 * 4));
+  CK(cudaMemcpy(d_a, h_a.data(), h_a.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_b, h_b.data(), h_b.size() * 2, cudaMemcpyHostToDevice));
+  const int smem = n_rows * 128 + 64 * 128 + 3072;
+  CK(cudaFuncSetAttribute(desc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  printf("[desc probe] SW128 K-major A operand read at a shifted start; rows = patch[shift + (m/8)*pitch + m%%8]\n");
+  const int shifts[] = {0, 1, 3, 8, 11, 21};
+  const int pitches[] = {8, 10, 16};
+  for (int pitch : pitches)
+    for (int shift : shifts)
+      for (int bo = 0; bo < 2; ++bo) {
+        if (shift + 15 * pitch + 8 > n_rows) continue;
+        CK(cudaMemset(d_d, 0, 128 * 64 * 4));
+        desc_probe_kernel<<<1, 128, smem>>>(d_a, n_rows, d_b, d_d, shift, pitch, bo);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+          printf("   pitch %2d shift %2d base_offset %d: kernel error %s\n", pitch, shift, bo, cudaGetErrorString(e));
+          exit(4);
+        }
+        std::vector<float> h_d(128 * 64);
+        CK(cudaMemcpy(h_d.data(), d_d, h_d.size() * 4, cudaMemcpyDeviceToHost));
+        int bad = 0;
+        double max_err = 0;
+        for (int m = 0; m < 128; ++m) {
+          const int row = shift + (m / 8) * pitch + (m % 8);
+          for (int n = 0; n < 64; ++n) {
+            double acc = 0;
+            for (int k = 0; k < 64; ++k) acc += (double)__half2float(h_a[(size_t)row * 64 + k]) * __half2float(h_b[(size_t)n * 64 + k]);
+            const double err = fabs(acc - h_d[m * 64 + n]);
+            if (err > max_err) max_err = err;
+            if (err > 2e-3) ++bad;
+          }
+        }
+        printf("   pitch %2d shift %2d base_offset %d: %s (bad %d, max_err %.3e)\n", pitch, shift, bo, bad ? "MISMATCH" : "match", bad, max_err);
+      }
+  cudaFree(d_a); cudaFree(d_b); cudaFree(d_d);
 }
 
 int main(int argc, char** argv) {
@@ -473,6 +493,10 @@ int main(int argc, char** argv) {
   printf("device: %s, SMs %d, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
   const int sms = prop.multiProcessorCount;
   const bool big = argc > 1 && atoi(argv[1]) > 0;
+  if (argc > 1 && strcmp(argv[1], "probe") == 0) {
+    run_desc_probe();
+    return 0;
+  }
   std::vector<Case> cases = {
       {"1x1 64->64 relu 92x92", CONV_1x1, 2, 92, 92, 64, 64, 64, 64, EPI_NHWC_F16, true, false, 64, 0},
       {"1x1 256->512 +res relu 46x46", CONV_1x1, 4, 46, 46, 256, 512, 512, 256, EPI_NHWC_F16, true, true, 512, 0},
@@ -524,21 +548,13 @@ int main(int argc, char** argv) {
     fails += run_case(r2, sms, true);
     fails += run_case(r3, sms, true);
   }
-  fails += run_stem2(2, 368, sms);
-  fails += run_stem2(1, 448, sms);
   fails += run_stem_pool(2, 368, sms);
   fails += run_stem_pool(2, 448, sms);
   fails += run_stem_pool(1, 64, sms);
-  fails += run_stem_pool(2, 368, sms, true);
-  fails += run_stem_pool(2, 448, sms, true);
-  fails += run_stem_pool(1, 64, sms, true);
-  fails += run_stem_pool(1, 512, sms, true);
+  fails += run_stem_pool(1, 512, sms);
   if (big) {
-    fails += run_stem2(32, 368, sms);
     fails += run_stem_pool(32, 368, sms);
     fails += run_stem_pool(128, 368, sms);
-    fails += run_stem_pool(32, 368, sms, true);
-    fails += run_stem_pool(128, 368, sms, true);
     std::vector<Case> bigc = {
         {"BIG 1x1 1024->1024 23x23 nb128", CONV_1x1, 128, 23, 23, 1024, 1024, 1024, 256, EPI_NHWC_F16, true, false,
          1024, 0},

@@ -9,16 +9,32 @@
 // consecutive conv rows: TMEM is an 8-slot ring indexed by conv row.  Per conv row that is ~870 cycles of tensor
 // pipe instead of 14 x 107, and nothing is computed twice between neighbouring pooled rows.
 //
-// A CTA's unit of work: (forward, x tile of 128 conv columns, segment of pooled rows).  Strips are the same raw
-// no-swizzle K-major windows as in stem_gemm.cuh (consecutive conv columns are 16 bytes apart), 2112 bytes per input
-// row, fetched with one bulk copy each.  Accumulators are only ever accumulated into: the epilogue warps zero a slot
+// Input ("stem layout", written by pyramid_kernel): [forward][row parity][rpp rows][row pitch] fp16, NHWC padded to
+// 4 channels; the row pitch is (S+6)*4 halves = (S/2+3)*16 bytes, so with VW = S/2+3 "virtual" conv columns per row the
+// 8-pixel x 4-channel window of virtual conv pixel v = oy*VW + ox for row tap ky starts at byte
+//     plane(ky & 1) + 16 * (v + VW * (ky >> 1))
+// i.e. consecutive GEMM rows are exactly 16 bytes apart.  That is the canonical no-swizzle K-major UMMA layout (8-row
+// core matrices of 16-byte rows, SBO = 128 B between row groups) with overlapping K chunks (LBO = 16 B), so a
+// contiguous strip of 128*16+48 bytes is a valid 128 x 32 A tile: the A operand is read IN PLACE, no im2col.
+//
+// A CTA's unit of work: (forward, x tile of 128 conv columns, segment of pooled rows).  Strips are raw 2112-byte
+// windows of one padded input row, fetched with one bulk copy each.  Accumulators are only ever accumulated into: the epilogue warps zero a slot
 // (tcgen05.st) right after draining it.  Each epilogue thread drains the same conv column of every row (bias, ReLU,
 // fp16), keeps the vertical 3-max of the open pooling window in registers, and every second row the 8 epilogue
 // warps exchange the column maxima through smem for the horizontal 3-max and write one pooled row straight to HBM.
 #pragma once
-#include "stem_gemm.cuh"
+#include "conv_gemm.cuh"
 
 namespace vnect {
+
+constexpr int kStemWBytes = 28 * 64 * 16;  // 7 row taps x 32 K values x 64 couts, fp16
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 constexpr int kRollThreads = 128 + 256;      // 4 control warps + 8 epilogue / pooling warps
 constexpr int kRollStripLoad = kBlockM * 16 + 64;
@@ -31,7 +47,7 @@ constexpr int kMaxXTiles = 4;
 constexpr int kRollMaxInputRows = 4 * 128 + 8;  // a segment of up to 128 pooled rows (box size 512)
 constexpr int kRollWEvenBytes = 256 * 64;  // [4 taps x 64 couts][32 K] fp16, 64B-swizzled K-major rows
 constexpr int kRollWOddBytes = 192 * 64;   // [3 taps x 64 couts][32 K]
-static_assert(kRollWEvenBytes + kRollWOddBytes == kStemWBytes, "stacked weights are a permutation of the canonical pack");
+static_assert(kRollWEvenBytes + kRollWOddBytes == kStemWBytes, "the two stacks hold all 7 row taps");
 
 struct StemRollParams {
   const uint8_t* x1;

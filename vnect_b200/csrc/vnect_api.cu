@@ -25,7 +25,7 @@ struct Act {
 };
 
 struct Step {
-  int kind = 0;  // 0 = implicit-GEMM conv (conv_gemm_kernel), 3 = fused conv1 + pool1 (stem_pool_kernel)
+  int kind = 0;  // 0 = implicit-GEMM conv (conv_gemm_kernel), 3 = fused conv1 + pool1 (stem_roll_kernel)
   std::string name;
   ConvLaunch launch;
   StemPoolLaunch stem_pool;
@@ -95,12 +95,30 @@ struct vnect_handle {
     cudaGraphExec_t exec = nullptr;
     long long launches = 0;
     bool unusable = false;
+    unsigned long long last_use = 0;
   };
+  static constexpr size_t kMaxGraphs = 16;  // a video loop changes its crop size every frame: bound the cache (LRU)
+  unsigned long long graph_clock = 0;
   std::map<GraphKey, GraphEntry> graphs;
   bool use_graphs = true;
   std::vector<double> last_t2d, last_t3d;  // host mirror of the filters' last timestamps (NaN = none yet)
   PyramidParams pyr{};
+  double* d_packed = nullptr;  // caller-owned device buffer [max_frames][21][5] (vnect_set_packed_results) or null
 };
+
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it: function
+// attributes, streams and allocations are per device, and a process may hold one handle per GPU.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+#define ON_DEVICE(h) DeviceGuard device_guard_((h)->cfg.device)
 
 static int fail(vnect_t* h, int code, const char* fmt, ...) {
   char buf[512];
@@ -138,19 +156,14 @@ static inline int grid_for(int64_t total, int threads, int sms) {
 static const char* kBnVars[4] = {"gamma", "beta", "moving_mean", "moving_variance"};
 
 struct ConvDef {
-  const char* scope;
+  std::string scope;
   int k, cin, cout;
 };
 
 static std::vector<ConvDef> conv_defs() {
   std::vector<ConvDef> d;
-  static std::vector<std::string> names;  // keeps c_str() alive
-  names.clear();
-  names.reserve(128);
-  auto add = [&](const std::string& s, int k, int ci, int co) {
-    names.push_back(s);
-    d.push_back({names.back().c_str(), k, ci, co});
-  };
+  d.reserve(64);
+  auto add = [&](const std::string& s, int k, int ci, int co) { d.push_back({s, k, ci, co}); };
   auto block = [&](const std::string& pre, int cin, int mid, int cout, bool proj, const std::string& suf) {
     if (proj) add(pre + "_branch1" + suf, 1, cin, cout);
     add(pre + "_branch2a" + suf, 1, cin, mid);
@@ -463,7 +476,7 @@ static int alloc_prepost(vnect_t* h) {
   // stem input: parity-split, zero-padded NHWC4 (zeros are written once here and never touched again)
   h->stem_rpp = S / 2 + 3;
   h->stem_pitch = (S + 6) * 4;
-  // + slack: the last strip of the last image reads a few KB past its parity plane (stem_gemm.cuh)
+  // + slack: the last strip of the last image reads a few KB past its parity plane (stem_roll.cuh)
   if ((rc = dev_alloc(h, &h->x1, (size_t)nb * 2 * h->stem_rpp * h->stem_pitch + 16384, true))) return rc;
   if ((rc = dev_alloc(h, &h->maps, (size_t)nb * 84 * h->hs * h->hs, true))) return rc;
   const int mf = h->cfg.max_frames, ms = h->cfg.max_streams;
@@ -556,7 +569,8 @@ int vnect_create(vnect_t** out, const vnect_config* cfg) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(h, VNECT_E_CUDA, "no CUDA device: this library has no CPU path");
-  CU(h, cudaSetDevice(cfg->device));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(h, VNECT_E_INVALID, "device %d not in [0, %d)", cfg->device, ndev);
+  ON_DEVICE(h);  // the caller's current device is restored on return
   cudaDeviceProp prop;
   CU(h, cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) return fail(h, VNECT_E_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
@@ -589,10 +603,11 @@ int vnect_set_weight(vnect_t* h, const char* tf_name, const float* data, const i
 int vnect_finalize(vnect_t* h) {
   if (!h) return VNECT_E_INVALID;
   if (h->finalized) return fail(h, VNECT_E_INVALID, "already finalized");
+  ON_DEVICE(h);
   // every variable of the graph must be present (the reference restores all 109 from the checkpoint)
   for (const ConvDef& c : conv_defs())
     for (const char* leaf : {"/weights", "/biases"})
-      if (!h->vars.count(std::string(c.scope) + leaf)) return fail(h, VNECT_E_WEIGHT, "missing variable %s%s", c.scope, leaf);
+      if (!h->vars.count(c.scope + leaf)) return fail(h, VNECT_E_WEIGHT, "missing variable %s%s", c.scope.c_str(), leaf);
   for (const char* k : {"res5c_branch1a/kernel", "res5c_branch2a/kernel", "res5c_branch2c/kernel"})
     if (!h->vars.count(k)) return fail(h, VNECT_E_WEIGHT, "missing variable %s", k);
   for (const char* v : kBnVars)
@@ -600,23 +615,18 @@ int vnect_finalize(vnect_t* h) {
 
   const int S = h->S, nb = h->cap_fw;
   int rc;
-  {  // conv1 + pool1 (vnect_model.py:27-29) fused: rolling raw-strip implicit GEMM + max-pool (stem_roll.cuh);
-     // VNECT_B200_STEM=band selects the older band kernel (stem_pool.cuh) for A/B runs
-    std::vector<__half> wk = to_half(pack_stem(h->vars.at("conv1/weights"))), wc(wk.size()), ws(wk.size());
-    pack_stem_canonical(wk.data(), wc.data());
+  {  // conv1 + pool1 (vnect_model.py:27-29) fused: rolling raw-strip implicit GEMM + max-pool (stem_roll.cuh)
+    std::vector<__half> wk = to_half(pack_stem(h->vars.at("conv1/weights"))), ws(wk.size());
     pack_stem_stacked(wk.data(), ws.data());
-    __half* dw = nullptr;
     __half* dws = nullptr;
     float* db = nullptr;
-    if ((rc = upload(h, wc, &dw))) return rc;
-    const char* stem_env = getenv("VNECT_B200_STEM");
-    if (!(stem_env && strcmp(stem_env, "band") == 0) && (rc = upload(h, ws, &dws))) return rc;
+    if ((rc = upload(h, ws, &dws))) return rc;
     if ((rc = upload(h, h->vars.at("conv1/biases").data, &db))) return rc;
     if ((rc = new_act(h, "pool1", S / 4, S / 4, 64))) return rc;
     Step st;
     st.kind = 3; st.name = "conv1+pool1";
     std::string err;
-    if (!build_stem_pool(h->x1, S, h->stem_rpp, h->stem_pitch, dw, db, h->acts.at("pool1").p, nb, h->num_sms, &st.stem_pool, &err, dws))
+    if (!build_stem_pool(h->x1, S, h->stem_rpp, h->stem_pitch, dws, db, h->acts.at("pool1").p, nb, h->num_sms, &st.stem_pool, &err))
       return fail(h, VNECT_E_CUDA, "conv1+pool1: %s", err.c_str());
     h->steps.push_back(st);
   }
@@ -696,7 +706,7 @@ int vnect_finalize(vnect_t* h) {
   for (size_t i = 0; i < h->steps.size(); ++i) {
     const int rev = (pingpong && i % 2 == 0) ? 1 : 0;
     if (h->steps[i].kind == 0) h->steps[i].launch.p.reverse = rev;
-    else h->steps[i].stem_pool.p.reverse = h->steps[i].stem_pool.r.reverse = rev;
+    else h->steps[i].stem_pool.r.reverse = rev;
   }
 
   h->vars.clear();  // host copies no longer needed
@@ -801,6 +811,12 @@ static int stage_frame_meta(vnect_t* h, int n_frames, const int32_t* stream_ids,
         return fail(h, VNECT_E_ZERO_DT, "float division by zero (stream %d: repeated 2D timestamp %.17g)", sid, t2d[i]);
       if (h->last_t3d[sid] == h->last_t3d[sid] && h->last_t3d[sid] != 0.0 && t3d[i] != 0.0 && t3d[i] == h->last_t3d[sid])
         return fail(h, VNECT_E_ZERO_DT, "float division by zero (stream %d: repeated 3D timestamp %.17g)", sid, t3d[i]);
+      // an EARLIER timestamp makes freq negative and every alpha leave (0, 1]: LowPassFilter raises ValueError
+      // (OneEuroFilter.py:21-22).  Refused here, before any filter state is touched.
+      if (h->last_t2d[sid] == h->last_t2d[sid] && h->last_t2d[sid] != 0.0 && t2d[i] != 0.0 && t2d[i] < h->last_t2d[sid])
+        return fail(h, VNECT_E_INVALID, "alpha should be in (0.0, 1.0] (stream %d: 2D timestamp %.17g earlier than the previous %.17g)", sid, t2d[i], h->last_t2d[sid]);
+      if (h->last_t3d[sid] == h->last_t3d[sid] && h->last_t3d[sid] != 0.0 && t3d[i] != 0.0 && t3d[i] < h->last_t3d[sid])
+        return fail(h, VNECT_E_INVALID, "alpha should be in (0.0, 1.0] (stream %d: 3D timestamp %.17g earlier than the previous %.17g)", sid, t3d[i], h->last_t3d[sid]);
     }
   }
   for (int i = 0; i < n_frames; ++i) {
@@ -834,6 +850,7 @@ static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, i
   p.j2_box = h->d_j2_box; p.j3_raw = h->d_j3_raw; p.raw_argmax = h->d_raw_argmax;
   p.frame_counter = h->d_counter;
   p.out2d = dev_out2d; p.out3d = dev_out3d;
+  p.packed = h->d_packed;
   CU(h, cudaMemsetAsync(h->d_counter, 0, n_frames * sizeof(unsigned int), h->stream));
   // averaged plane (float64) + the raw plane of every scale (float32)
   const size_t smem = (size_t)h->hs * h->hs * (sizeof(double) + h->n_scales * sizeof(float));
@@ -851,6 +868,7 @@ extern "C" {
 
 int vnect_forward(vnect_t* h, const float* nhwc, int32_t n, float* hm, float* xm, float* ym, float* zm) {
   if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  ON_DEVICE(h);
   if (!nhwc || !hm || !xm || !ym || !zm) return fail(h, VNECT_E_INVALID, "null buffer");
   if (n < 1 || n > h->cap_fw) return fail(h, VNECT_E_INVALID, "n %d not in [1, %d]", n, h->cap_fw);
   const int S = h->S, hs = h->hs;
@@ -896,10 +914,18 @@ static int run_pipeline(vnect_t* h, int lane, const uint8_t* dev_bgr, int n_fram
   const vnect_handle::GraphKey key(lane + (tracked ? 2 : 0), n_frames, H, W, (long long)pitch, (long long)frame_stride, dev_bgr, out2d, out3d);
   auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
-    h->graphs[key] = vnect_handle::GraphEntry();
+    if (h->graphs.size() >= vnect_handle::kMaxGraphs) {  // evict the least recently used entry
+      auto victim = h->graphs.begin();
+      for (auto g = h->graphs.begin(); g != h->graphs.end(); ++g)
+        if (g->second.last_use < victim->second.last_use) victim = g;
+      if (victim->second.exec) cudaGraphExecDestroy(victim->second.exec);
+      h->graphs.erase(victim);
+    }
+    h->graphs[key].last_use = ++h->graph_clock;
     return direct();  // warm-up run: sets function attributes, exercises every launch configuration
   }
   vnect_handle::GraphEntry& e = it->second;
+  e.last_use = ++h->graph_clock;
   if (e.unusable) return direct();
   if (!e.exec) {
     const long long before = h->launches;
@@ -937,6 +963,7 @@ int vnect_estimate_device(vnect_t* h, const uint8_t* dev_bgr, int32_t n_frames, 
                           int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d,
                           double* dev_joints2d, float* dev_joints3d) {
   if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  ON_DEVICE(h);
   if (!dev_bgr || !dev_joints2d || !dev_joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
   if (H < 2 || W < 2 || pitch < (int64_t)W * 3) return fail(h, VNECT_E_INVALID, "bad frame geometry %dx%d pitch %lld", H, W, (long long)pitch);
   // alternate lanes for the per-call meta so the host can run one call ahead of the GPU
@@ -954,6 +981,7 @@ int vnect_submit(vnect_t* h, int32_t lane, const uint8_t* bgr, int32_t n_frames,
                  int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d, double* joints2d,
                  float* joints3d) {
   if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  ON_DEVICE(h);
   if (lane < 0 || lane > 1) return fail(h, VNECT_E_INVALID, "lane must be 0 or 1");
   if (!bgr || !joints2d || !joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
   if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames %d not in [1, %d]", n_frames, h->cfg.max_frames);
@@ -983,6 +1011,7 @@ int vnect_submit(vnect_t* h, int32_t lane, const uint8_t* bgr, int32_t n_frames,
 
 int vnect_track_set_box(vnect_t* h, int32_t stream_id, int32_t x, int32_t y, int32_t w, int32_t hh) {
   if (!h || !h->d_boxes) return fail(h, VNECT_E_INVALID, "handle not created");
+  ON_DEVICE(h);
   if (stream_id < 0 || stream_id >= h->cfg.max_streams) return fail(h, VNECT_E_INVALID, "stream id out of range");
   if (x < 0 || y < 0 || w < 2 || hh < 2) return fail(h, VNECT_E_INVALID, "box must have x, y >= 0 and w, h >= 2");
   const int4 b = make_int4(x, y, w, hh);
@@ -993,6 +1022,7 @@ int vnect_track_set_box(vnect_t* h, int32_t stream_id, int32_t x, int32_t y, int
 
 int vnect_track_get_box(vnect_t* h, int32_t stream_id, int32_t* xywh) {
   if (!h || !h->d_boxes || !xywh) return fail(h, VNECT_E_INVALID, "handle not created / null buffer");
+  ON_DEVICE(h);
   if (stream_id < 0 || stream_id >= h->cfg.max_streams) return fail(h, VNECT_E_INVALID, "stream id out of range");
   CU(h, cudaStreamSynchronize(h->stream));
   int4 b;
@@ -1005,6 +1035,7 @@ int vnect_track(vnect_t* h, const uint8_t* frames, int32_t n_frames, int32_t FH,
                 int64_t frame_stride, const int32_t* stream_ids, const double* t2d, const double* t3d, double* joints2d,
                 float* joints3d, int32_t* boxes_used) {
   if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  ON_DEVICE(h);
   if (!frames || !joints2d || !joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
   if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames %d not in [1, %d]", n_frames, h->cfg.max_frames);
   if (FH < 2 || FW < 2 || FH > h->cfg.max_input_h || FW > h->cfg.max_input_w)
@@ -1029,6 +1060,7 @@ int vnect_track(vnect_t* h, const uint8_t* frames, int32_t n_frames, int32_t FH,
 
 int vnect_wait(vnect_t* h, int32_t lane) {
   if (!h || lane < 0 || lane > 1) return fail(h, VNECT_E_INVALID, "bad handle or lane");
+  ON_DEVICE(h);
   return lane_acquire(h, lane);
 }
 
@@ -1043,6 +1075,7 @@ int vnect_estimate(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H, 
 int vnect_preprocess(vnect_t* h, const uint8_t* bgr, int32_t n_frames, int32_t H, int32_t W, int64_t pitch,
                      int64_t frame_stride, float* out_nhwc, double* scaler_offsets) {
   if (!h || !h->x1) return fail(h, VNECT_E_INVALID, "handle not created");
+  ON_DEVICE(h);
   if (!bgr || !out_nhwc) return fail(h, VNECT_E_INVALID, "null buffer");
   if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames out of range");
   if (H < 2 || W < 2 || H > h->cfg.max_input_h || W > h->cfg.max_input_w) return fail(h, VNECT_E_INVALID, "frame size outside max_input");
@@ -1071,6 +1104,7 @@ int vnect_postprocess(vnect_t* h, const float* hm, const float* xm, const float*
                       const int32_t* stream_ids, const double* t2d, const double* t3d, double scaler, int32_t offset_x,
                       int32_t offset_y, double* joints2d, float* joints3d, int32_t* raw_argmax) {
   if (!h || !h->x1) return fail(h, VNECT_E_INVALID, "handle not created");
+  ON_DEVICE(h);
   if (!hm || !xm || !ym || !zm || !joints2d || !joints3d) return fail(h, VNECT_E_INVALID, "null buffer");
   int rc = lane_acquire(h, 0);
   if (rc) return rc;
@@ -1098,6 +1132,7 @@ int vnect_postprocess(vnect_t* h, const float* hm, const float* xm, const float*
 
 int vnect_reset_stream(vnect_t* h, int32_t stream_id) {
   if (!h || !h->d_st2d) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  ON_DEVICE(h);
   const int ms = h->cfg.max_streams;
   if (stream_id < -1 || stream_id >= ms) return fail(h, VNECT_E_INVALID, "stream id out of range");
   const int lo = stream_id < 0 ? 0 : stream_id, hi = stream_id < 0 ? ms : stream_id + 1;
@@ -1111,21 +1146,30 @@ int vnect_reset_stream(vnect_t* h, int32_t stream_id) {
   CU(h, cudaMemcpy(h->d_st2d + (size_t)lo * kJoints * 2, s2.data(), s2.size() * sizeof(FilterState), cudaMemcpyHostToDevice));
   CU(h, cudaMemcpy(h->d_st3d + (size_t)lo * kJoints * 3, s3.data(), s3.size() * sizeof(FilterState), cudaMemcpyHostToDevice));
   for (int i = lo; i < hi; ++i) h->last_t2d[i] = h->last_t3d[i] = NAN;
+  // the tracked crop box restarts as the whole frame (run_estimator.py:68: rect = 0, 0, W_img, H_img); the geometry
+  // kernel clips it to the actual frame size
+  std::vector<int4> full((size_t)(hi - lo), make_int4(0, 0, 1 << 30, 1 << 30));
+  CU(h, cudaMemcpy(h->d_boxes + lo, full.data(), full.size() * sizeof(int4), cudaMemcpyHostToDevice));
   return VNECT_OK;
 }
 
-int vnect_filter(vnect_t* h, int32_t stream_id, int32_t dim, double t, double* values) {
+int vnect_filter(vnect_t* h, int32_t stream_id, int32_t dim, int32_t values_are_f32, double t, double* values) {
   if (!h || !h->x1 || !values) return fail(h, VNECT_E_INVALID, "handle not created / null buffer");
+  ON_DEVICE(h);
   if (stream_id < 0 || stream_id >= h->cfg.max_streams || (dim != 2 && dim != 3)) return fail(h, VNECT_E_INVALID, "bad stream id or dim");
   std::vector<double>& last = dim == 2 ? h->last_t2d : h->last_t3d;
-  if (last[stream_id] == last[stream_id] && last[stream_id] != 0.0 && t != 0.0 && t == last[stream_id])
-    return fail(h, VNECT_E_ZERO_DT, "float division by zero (stream %d: repeated timestamp %.17g)", stream_id, t);
+  if (last[stream_id] == last[stream_id] && last[stream_id] != 0.0 && t != 0.0) {
+    if (t == last[stream_id])
+      return fail(h, VNECT_E_ZERO_DT, "float division by zero (stream %d: repeated timestamp %.17g)", stream_id, t);
+    if (t < last[stream_id])
+      return fail(h, VNECT_E_INVALID, "alpha should be in (0.0, 1.0] (stream %d: timestamp %.17g earlier than the previous %.17g)", stream_id, t, last[stream_id]);
+  }
   last[stream_id] = t;
   const int n = kJoints * dim;
   CU(h, cudaMemcpyAsync(h->d_filter_scratch, values, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   FilterState* st = dim == 2 ? h->d_st2d + (size_t)stream_id * kJoints * 2 : h->d_st3d + (size_t)stream_id * kJoints * 3;
   const FilterCfg cfg = dim == 2 ? FilterCfg{30.0, 1.7, 0.3, 0.4} : FilterCfg{30.0, 0.8, 0.4, 0.4};
-  joint_filter_kernel<<<1, 64, 0, h->stream>>>(st, cfg, h->d_filter_scratch, t, dim);
+  joint_filter_kernel<<<1, 64, 0, h->stream>>>(st, cfg, h->d_filter_scratch, t, dim, values_are_f32 ? 1 : 0);
   CU(h, cudaGetLastError());
   ++h->launches;
   CU(h, cudaMemcpyAsync(values, h->d_filter_scratch, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1133,8 +1177,75 @@ int vnect_filter(vnect_t* h, int32_t stream_id, int32_t dim, double t, double* v
   return VNECT_OK;
 }
 
+// waits for every submitted batch: the per-call scratch (raw argmax) and the per-stream state are then at rest
+static int quiesce(vnect_t* h) {
+  for (auto& L : h->lanes)
+    if (L.pending) {
+      CU(h, cudaEventSynchronize(L.done));
+      L.pending = false;
+    }
+  CU(h, cudaStreamSynchronize(h->stream));
+  return VNECT_OK;
+}
+
+int vnect_get_raw_argmax(vnect_t* h, int32_t n_frames, int32_t* raw_argmax) {
+  if (!h || !h->d_raw_argmax || !raw_argmax) return fail(h, VNECT_E_INVALID, "handle not created / null buffer");
+  ON_DEVICE(h);
+  if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames out of range");
+  if (int rc = quiesce(h)) return rc;
+  CU(h, cudaMemcpy(raw_argmax, h->d_raw_argmax, (size_t)n_frames * kJoints * 2 * sizeof(int), cudaMemcpyDeviceToHost));
+  return VNECT_OK;
+}
+
+// Per-stream temporal state as plain doubles (VNECT_STREAM_STATE_DOUBLES of them): 105 filters x {prev, s_x, s_dx,
+// lasttime, freq, has_prev, has_time} (2D filters first, [21][2], then 3D, [21][3]), then the host-side last timestamps
+// (2D, 3D; NaN = none) and the tracked box (x, y, w, h).
+int vnect_export_stream_state(vnect_t* h, int32_t stream_id, double* state) {
+  if (!h || !h->d_st2d || !state) return fail(h, VNECT_E_INVALID, "handle not created / null buffer");
+  ON_DEVICE(h);
+  if (stream_id < 0 || stream_id >= h->cfg.max_streams) return fail(h, VNECT_E_INVALID, "stream id out of range");
+  if (int rc = quiesce(h)) return rc;
+  std::vector<FilterState> st(kJoints * 5);
+  CU(h, cudaMemcpy(st.data(), h->d_st2d + (size_t)stream_id * kJoints * 2, kJoints * 2 * sizeof(FilterState), cudaMemcpyDeviceToHost));
+  CU(h, cudaMemcpy(st.data() + kJoints * 2, h->d_st3d + (size_t)stream_id * kJoints * 3, kJoints * 3 * sizeof(FilterState), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < kJoints * 5; ++i) {
+    double* o = state + 7 * i;
+    o[0] = st[i].prev; o[1] = st[i].s_x; o[2] = st[i].s_dx; o[3] = st[i].lasttime; o[4] = st[i].freq;
+    o[5] = st[i].has_prev; o[6] = st[i].has_time;
+  }
+  int4 b;
+  CU(h, cudaMemcpy(&b, h->d_boxes + stream_id, sizeof b, cudaMemcpyDeviceToHost));
+  double* tail = state + 7 * kJoints * 5;
+  tail[0] = h->last_t2d[stream_id]; tail[1] = h->last_t3d[stream_id];
+  tail[2] = b.x; tail[3] = b.y; tail[4] = b.z; tail[5] = b.w;
+  return VNECT_OK;
+}
+
+int vnect_import_stream_state(vnect_t* h, int32_t stream_id, const double* state) {
+  if (!h || !h->d_st2d || !state) return fail(h, VNECT_E_INVALID, "handle not created / null buffer");
+  ON_DEVICE(h);
+  if (stream_id < 0 || stream_id >= h->cfg.max_streams) return fail(h, VNECT_E_INVALID, "stream id out of range");
+  std::vector<FilterState> st(kJoints * 5);
+  for (int i = 0; i < kJoints * 5; ++i) {
+    const double* o = state + 7 * i;
+    memset(&st[i], 0, sizeof(FilterState));
+    st[i].prev = o[0]; st[i].s_x = o[1]; st[i].s_dx = o[2]; st[i].lasttime = o[3]; st[i].freq = o[4];
+    st[i].has_prev = o[5] != 0.0; st[i].has_time = o[6] != 0.0;
+  }
+  if (int rc = quiesce(h)) return rc;
+  CU(h, cudaMemcpy(h->d_st2d + (size_t)stream_id * kJoints * 2, st.data(), kJoints * 2 * sizeof(FilterState), cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(h->d_st3d + (size_t)stream_id * kJoints * 3, st.data() + kJoints * 2, kJoints * 3 * sizeof(FilterState), cudaMemcpyHostToDevice));
+  const double* tail = state + 7 * kJoints * 5;
+  h->last_t2d[stream_id] = tail[0];
+  h->last_t3d[stream_id] = tail[1];
+  const int4 b = make_int4((int)tail[2], (int)tail[3], (int)tail[4], (int)tail[5]);
+  CU(h, cudaMemcpy(h->d_boxes + stream_id, &b, sizeof b, cudaMemcpyHostToDevice));
+  return VNECT_OK;
+}
+
 int vnect_set_stream(vnect_t* h, void* cuda_stream) {
   if (!h) return VNECT_E_INVALID;
+  ON_DEVICE(h);
   if (h->own_stream && h->stream) {
     cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);
@@ -1144,14 +1255,27 @@ int vnect_set_stream(vnect_t* h, void* cuda_stream) {
   return VNECT_OK;
 }
 
+int vnect_set_packed_results(vnect_t* h, void* dev_packed) {
+  if (!h) return VNECT_E_INVALID;
+  ON_DEVICE(h);
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (auto& kv : h->graphs)  // the pointer is baked into the captured post-process launch
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  h->graphs.clear();
+  h->d_packed = reinterpret_cast<double*>(dev_packed);
+  return VNECT_OK;
+}
+
 int vnect_synchronize(vnect_t* h) {
   if (!h) return VNECT_E_INVALID;
+  ON_DEVICE(h);
   CU(h, cudaStreamSynchronize(h->stream));
   return VNECT_OK;
 }
 
 int vnect_get_tap(vnect_t* h, const char* name, int32_t n, float* out_nhwc, int64_t capacity_elems, int32_t* dims4) {
   if (!h || !h->finalized || !name) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  ON_DEVICE(h);
   auto it = h->acts.find(name);
   if (it == h->acts.end()) return fail(h, VNECT_E_INVALID, "no activation named '%s'", name);
   const Act& a = it->second;
@@ -1190,7 +1314,7 @@ double vnect_info(vnect_t* h, const char* key) {
     double f = 0;
     for (const Step& st : h->steps)
       if (st.kind == 0) f += st.launch.flops / h->cap_fw;
-      else f += 2.0 * st.stem_pool.p.bands_per_image * st.stem_pool.p.band_tiles * kBlockM * 64 * 224;
+      else f += 2.0 * (h->S / 2) * (h->S / 2) * 64 * 224;  // conv1 with its K padded to 7 rows x 8 px x 4 ch
     return f;
   }
   if (k == "hm_size") return h->hs;
@@ -1200,6 +1324,7 @@ double vnect_info(vnect_t* h, const char* key) {
 
 int vnect_time_forward(vnect_t* h, int32_t n, int32_t reps, float* total_ms, float* per_layer_ms) {
   if (!h || !h->finalized) return fail(h, VNECT_E_INVALID, "handle not finalized");
+  ON_DEVICE(h);
   if (n < 1 || n > h->cap_fw || reps < 1) return fail(h, VNECT_E_INVALID, "bad n/reps");
   const int ns = (int)h->steps.size();
   std::vector<cudaEvent_t> ev(ns + 1);
@@ -1238,6 +1363,7 @@ int vnect_time_forward(vnect_t* h, int32_t n, int32_t reps, float* total_ms, flo
 
 void vnect_destroy(vnect_t* h) {
   if (!h) return;
+  ON_DEVICE(h);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& kv : h->graphs)

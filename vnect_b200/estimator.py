@@ -208,11 +208,34 @@ class VNectEngine:
                                                 _ptr(raw)))
         return j2, j3, raw
 
-    def filter(self, values, dim, t, stream_id=0):
-        """One joint_filter step (src/estimator.py:83-95) on explicit values [21, dim]."""
-        v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1)
-        self._check(self._lib.vnect_filter(self._h, int(stream_id), int(dim), float(t), _ptr(v)))
+    def filter(self, values, dim, t, stream_id=0, is_f32=None):
+        """One joint_filter step (src/estimator.py:83-95) on explicit values [21, dim].  ``is_f32`` says whether the
+        caller's array is float32 like the reference's joints_3d (default: dim == 3); the result is float64-typed
+        either way and float32-valued when it is."""
+        is_f32 = (dim == 3) if is_f32 is None else bool(is_f32)
+        v = np.ascontiguousarray(values, dtype=np.float64).reshape(-1).copy()
+        if v.size != JOINTS * dim:
+            raise ValueError(f"expected [21, {dim}] values")
+        self._check(self._lib.vnect_filter(self._h, int(stream_id), int(dim), 1 if is_f32 else 0, float(t), _ptr(v)))
         return v.reshape(JOINTS, dim)
+
+    def raw_argmax(self, n=1):
+        """Unfiltered (row, col) argmax in box pixels of the last estimate / submit / track call, int32 [n,21,2]."""
+        out = np.empty((n, JOINTS, 2), np.int32)
+        self._check(self._lib.vnect_get_raw_argmax(self._h, int(n), _ptr(out)))
+        return out
+
+    def export_stream_state(self, stream_id=0):
+        """Temporal state of a stream (filters, last clock readings, tracked box) as a float64 vector."""
+        out = np.empty(_capi.STREAM_STATE_DOUBLES, np.float64)
+        self._check(self._lib.vnect_export_stream_state(self._h, int(stream_id), _ptr(out)))
+        return out
+
+    def import_stream_state(self, state, stream_id=0):
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        if state.shape != (_capi.STREAM_STATE_DOUBLES,):
+            raise ValueError("stream state has the wrong size")
+        self._check(self._lib.vnect_import_stream_state(self._h, int(stream_id), _ptr(state)))
 
     def tap(self, name, n=1):
         """Intermediate activation `name` of the last forward as float32 NHWC (fp16 on the device)."""
@@ -227,6 +250,10 @@ class VNectEngine:
 
     def set_cuda_stream(self, stream_ptr):
         self._check(self._lib.vnect_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def set_packed_results(self, dev_ptr):
+        """Device pointer to float64 [max_frames,21,5]: later calls also write (row, col, x, y, z) there (0 = off)."""
+        self._check(self._lib.vnect_set_packed_results(self._h, C.c_void_p(dev_ptr) if dev_ptr else None))
 
     def synchronize(self):
         self._check(self._lib.vnect_synchronize(self._h))
@@ -268,7 +295,11 @@ class VNectEstimator:
     joints_sum = 21  # :23
     joint_parents = [16, 15, 1, 2, 3, 1, 5, 6, 14, 8, 9, 14, 11, 12, 14, 14, 1, 4, 7, 10, 13]  # :25
 
-    def __init__(self, weights=None, scales=None, box_size=None, device=0, clock=None, verbose=True):
+    # Largest frame the device context is sized for up front.  The reference's video loop hands in a crop whose size
+    # changes every frame (run_estimator.py:100, 110-119), so sizing by the first frame would rebuild mid-video.
+    default_max_input = (1080, 1920)
+
+    def __init__(self, weights=None, scales=None, box_size=None, device=0, clock=None, verbose=True, max_input=None):
         self._verbose = verbose
         if verbose:
             print('Initializing VNect Estimator...')
@@ -280,26 +311,32 @@ class VNectEstimator:
         self._clock = clock or time.time
         self._engine = None
         self._engine_key = None
+        self._max_input = tuple(max_input) if max_input else self.default_max_input
         self._ensure_engine((self.box_size, self.box_size))
         if verbose:
             print('VNect Estimator initialized.')
 
     def _ensure_engine(self, hw):
         """(Re)build the device context when `scales` was changed by the caller (the reference reads self.scales on
-        every call, src/estimator.py:99) or a larger frame arrives.  Filter state restarts, as it would for a new
-        reference object."""
-        need_h = max(hw[0], self.box_size)
-        need_w = max(hw[1], self.box_size)
+        every call, src/estimator.py:99) or a frame larger than `max_input` arrives.  The OneEuroFilter state belongs
+        to the estimator object in the reference (src/estimator.py:46-53) and survives both: it is carried over."""
+        need_h = max(hw[0], self.box_size, self._max_input[0])
+        need_w = max(hw[1], self.box_size, self._max_input[1])
         key = (tuple(float(s) for s in self.scales), self.box_size)
         if self._engine is not None and key == self._engine_key and need_h <= self._engine.max_input[0] \
                 and need_w <= self._engine.max_input[1]:
             return
+        state = None
         if self._engine is not None:
             need_h = max(need_h, self._engine.max_input[0])
             need_w = max(need_w, self._engine.max_input[1])
+            state = self._engine.export_stream_state(0)
             self._engine.close()
+        self._max_input = (need_h, need_w)
         self._engine = VNectEngine(self._weights, self.scales, self.box_size, max_frames=1, max_streams=1,
                                    max_input=(need_h, need_w), device=self._device, filters=True)
+        if state is not None:
+            self._engine.import_stream_state(state, 0)
         self._engine_key = key
 
     @staticmethod
@@ -314,15 +351,22 @@ class VNectEstimator:
             eng.close()
 
     def joint_filter(self, joints, dim=2):
-        """src/estimator.py:83-95: in-place one-euro filtering of [21, dim] joints at the current clock reading."""
-        joints[...] = self._engine.filter(joints, dim, self._clock())
+        """src/estimator.py:83-95: in-place one-euro filtering of [21, dim] joints at the current clock reading.  A
+        float32 array (the reference's joints_3d) is filtered with float32 raw differences and float32 results, a
+        float64 one (joints_2d) in float64."""
+        is_f32 = getattr(joints, "dtype", None) == np.float32
+        joints[...] = self._engine.filter(joints, dim, self._clock(), is_f32=is_f32)
         return joints
 
     def __call__(self, img_input):
         t0 = time.time()
         img = np.asarray(img_input)
         self._ensure_engine(img.shape[:2])
-        t2d = self._clock()  # the reference reads the clock once per filter group (src/estimator.py:84)
+        # The reference reads the clock once per filter group, AFTER its sess.run (src/estimator.py:84, 132-135).  Here
+        # pre-processing, CNN and post-processing are one device submission, so both readings are taken just before
+        # it: every reading is earlier by about the CNN latency, the differences between frames -- all the filters
+        # use -- are unchanged.
+        t2d = self._clock()
         t3d = self._clock()
         j2, j3 = self._engine.estimate(img, stream_ids=[0], t2d=[t2d], t3d=[t3d])
         joints_2d, joints_3d = j2[0].copy(), j3[0].copy()
