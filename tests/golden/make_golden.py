@@ -18,7 +18,11 @@ Fixtures (all small):
   video.npz   first 12 decoded frames of pic/test_video.mp4 (C3 input) + the reference's video loop on them
               (run_estimator.py:98-119 executed verbatim around the reference estimator, CNN restatement W0)
 
-`python tests/golden/make_golden.py filter_joint video` regenerates only the named fixtures.
+  ref_scripts.npz  the text of the reference's CALLER scripts run_pic.py and run_estimator.py (bytes + sha256): test
+              vectors for SURVEY.md T5 -- the scripts are executed unchanged against the drop-in on the GPU box, which
+              has no reference tree.  Not product code; nothing under vnect_b200/ reads it.
+
+`python tests/golden/make_golden.py filter_joint video ref_scripts` regenerates only the named fixtures.
 """
 import hashlib
 import os
@@ -154,6 +158,18 @@ def make_video():
                         boxes=np.array(boxes, np.int32), versions=str(VERSIONS))
 
 
+REF_SCRIPTS = ("run_pic.py", "run_estimator.py")
+
+
+def make_ref_scripts():
+    out = dict(versions=str(VERSIONS))
+    for name in REF_SCRIPTS:
+        data = open(os.path.join(ref_shim.REFERENCE_ROOT, name), "rb").read()
+        out[name] = np.frombuffer(data, dtype=np.uint8)
+        out[name + "/sha256"] = hashlib.sha256(data).hexdigest()
+    np.savez_compressed(os.path.join(OUT, "ref_scripts.npz"), **out)
+
+
 def main():
     assert ref_shim.reference_available(), "run in the dev container (needs /root/reference)"
     utils, oef, est_mod = ref_shim.load_reference_modules()
@@ -163,9 +179,12 @@ def main():
             make_filter_joint(est_mod)
         if "video" in only:
             make_video()
+        if "ref_scripts" in only:
+            make_ref_scripts()
         return
     make_filter_joint(est_mod)
     make_video()
+    make_ref_scripts()
 
     # ---- pre.npz
     pre = dict(versions=str(VERSIONS))

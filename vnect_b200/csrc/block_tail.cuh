@@ -1,0 +1,474 @@
+// Tail of a bottleneck block fused with the head of the next one (reference: src/vnect_model.py:38-51 + 44, 58-66,
+// 70-76, ... -- `resNx_branch2c` [+ `branch1`] + add + ReLU, then `resN(x+1)_branch2a` + ReLU):
+//
+//     X[m, :]  = relu( A[m, :K1] * W^T + bias (+ R[m, :]) )        fp16, written to HBM (the block output)
+//     Y[m, :]  = relu( fp16(X[m, :]) * W2^T + bias2 )              fp16, written to HBM (the next block's 1x1 reduce)
+//
+// Unfused, the reduce conv re-reads X from HBM right after it was written (0.6 ms of a 3.6 ms forward batch, all of it
+// HBM-bound at res2 / res3).  Here every 64-channel chunk of X that the epilogue stages in shared memory for its TMA
+// store -- a 128B-swizzled [128 px x 64 ch] tile, i.e. exactly one K block of a K-major A operand -- is also fed to
+// the tensor cores as the A operand of the second GEMM; W2 streams through its own small ring.  X is read back by
+// nobody but the residual / projection path of the next block.
+//
+// One CTA pair (tcgen05 cta_group::2) owns 256 GEMM rows and walks ALL output-channel tiles of those rows (256 columns
+// each), so the second accumulator sees the whole K = Cout.  TMEM: columns [0, 256) main accumulator (single
+// buffered), [256, 256 + N2) second accumulator.  K order of the second GEMM is channel order, the same as the
+// stand-alone reduce conv, so both plans give bit-identical results.
+//
+// Warp roles (384 threads): 0 = TMA producer of the main GEMM (A rows + half of the W tile), 1 = MMA issuer (leader
+// CTA), 2 = TMEM allocator, then producer of the W2 tiles, 3 = residual prefetcher, 4-7 / 8-11 = two epilogue
+// warpgroups on alternate 64-column chunks (each owns one staging tile).
+#pragma once
+#include "conv_gemm.cuh"
+
+namespace vnect {
+
+constexpr int kTailBlockN = 256;
+constexpr int kTailW2Stages = 2;
+
+struct BlockTailParams {
+  ConvGemmParams g;      // rows / tiling / main epilogue (mode, M, tiles, cblocks, cblocks2, bias, relu_cols, strides)
+  const float* bias2;    // [N2]
+  int n2_k_chunks;       // Cout / 64: K blocks of the second GEMM (= 4 * g.num_n_tiles)
+};
+
+template <int N2, bool RES>
+struct TailCfg {
+  static constexpr int A_BYTES = kBlockM * 128;
+  static constexpr int B_BYTES = (kTailBlockN / 2) * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int W2_BYTES = (N2 / 2) * 128;
+  static constexpr int OUT_BYTES = kEpiGroups * kEpiChunkBytes;
+  static constexpr int RES_BYTES = RES ? kResStages * kEpiChunkBytes : 0;
+  static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - OUT_BYTES - RES_BYTES - kTailW2Stages * W2_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kTailW2Stages * W2_BYTES + OUT_BYTES + RES_BYTES + 1024 + 512;
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static_assert(N2 == 64 || N2 == 128 || N2 == 256, "second GEMM width");
+};
+
+// cluster-scope release / acquire for barriers that order one CTA's generic-proxy smem writes before tensor-core reads
+// triggered from the other CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (globaltimer_ns() - t0 > 4000000000ull) {
+      printf("vnect: mbarrier (cluster) wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int N2, bool RES>
+__global__ void __launch_bounds__(kGemmThreadsTma, 1)
+block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_w2,
+                  const __grid_constant__ CUtensorMap tmap_out2, const __grid_constant__ BlockTailParams bp) {
+  using Cfg = TailCfg<N2, RES>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BLOCK_N = kTailBlockN;
+  constexpr int BLOCK_K = 64;
+  constexpr int CH = BLOCK_N / 64;   // main chunks per output-channel tile
+  constexpr int CH2 = N2 / 64;       // chunks of the second accumulator
+  constexpr uint32_t IDESC = make_idesc_f16(2 * kBlockM, BLOCK_N, false);
+  constexpr uint32_t IDESC2 = make_idesc_f16(2 * kBlockM, N2, false);
+  const ConvGemmParams& p = bp.g;
+  const int cta_rank = static_cast<int>(cluster_ctarank());
+  const int worker = blockIdx.x / 2, n_workers = gridDim.x / 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w2_ring = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* out_stage = w2_ring + kTailW2Stages * Cfg::W2_BYTES;
+  uint8_t* res_stage = out_stage + Cfg::OUT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + Cfg::RES_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = full_bar + STAGES;         // [STAGES]
+  uint64_t* tmem_full = empty_bar + STAGES;        // main accumulator complete
+  uint64_t* tmem_empty = tmem_full + 1;            // main accumulator drained (8 epilogue warps x 2 CTAs)
+  uint64_t* acc2_full = tmem_empty + 1;
+  uint64_t* acc2_empty = acc2_full + 1;
+  uint64_t* res_full = acc2_empty + 1;             // [kResStages]
+  uint64_t* res_empty = res_full + kResStages;     // [kResStages]
+  uint64_t* w2_full = res_empty + kResStages;      // [kTailW2Stages]
+  uint64_t* w2_empty = w2_full + kTailW2Stages;    // [kTailW2Stages]
+  uint64_t* chunk_ready = w2_empty + kTailW2Stages;  // [2]: staging tile of group g holds a finished chunk of X (both CTAs)
+  uint64_t* chunk_free = chunk_ready + 2;            // [2]: the second GEMM has read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
+    tma_prefetch_desc(&tmap_w2);
+    tma_prefetch_desc(&tmap_out2);
+    if (p.cblocks2 > 0) tma_prefetch_desc(&tmap_a2);
+    if constexpr (RES) tma_prefetch_desc(&tmap_res);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 2 * 8);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 2 * (CH2 >= 2 ? 8 : 4));
+    for (int s = 0; s < kResStages; ++s) {
+      mbar_init(&res_full[s], 1);
+      mbar_init(&res_empty[s], 1);
+    }
+    for (int s = 0; s < kTailW2Stages; ++s) {
+      mbar_init(&w2_full[s], 1);
+      mbar_init(&w2_empty[s], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&chunk_ready[g], 2);  // one arrive per CTA of the pair
+      mbar_init(&chunk_free[g], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const int m_units = (p.num_m_tiles + 1) / 2;
+  const int NT = p.num_n_tiles;
+  const int k_iters = p.cblocks + p.cblocks2;
+
+  auto tile_coords = [&](int unit, int* cx, int* cy, int* cn) {
+    const int m_tile = unit * 2 + cta_rank;
+    if (p.mode == 0) {
+      *cx = m_tile * kBlockM; *cy = 0; *cn = 0;
+    } else {
+      const int per_img = p.tiles_x * p.tiles_y;
+      *cn = m_tile / per_img;
+      const int t2 = m_tile - *cn * per_img;
+      *cy = (t2 / p.tiles_x) * p.th;
+      *cx = (t2 % p.tiles_x) * p.tw;
+    }
+  };
+
+  if (warp == 0) {
+    // ================================================================ main-GEMM producer
+    const bool issuer = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int it = worker; it < m_units; it += n_workers) {
+      const int unit = p.reverse ? m_units - 1 - it : it;
+      int cx, cy, cn;
+      tile_coords(unit, &cx, &cy, &cn);
+      for (int nt = 0; nt < NT; ++nt) {
+        const int b_row = nt * BLOCK_N + cta_rank * (BLOCK_N / 2);
+        for (int kb = 0; kb < k_iters; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (issuer) {
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * p.stage_tx_bytes);
+            if (kb < p.cblocks) tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, cx * p.in_stride, cy * p.in_stride, 0, cn);
+            else tma_load_5d_pair(sa, &tmap_a2, &full_bar[stage], (kb - p.cblocks) * BLOCK_K, cx, cy, 0, cn);
+            tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], kb * BLOCK_K, b_row);
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    for (int s2 = 0; s2 < STAGES; ++s2) {  // drain: the leader's multicast commits still arrive on our empty barriers
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (++stage == STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (leader CTA)
+    const bool issuer = elect_one();
+    if (cta_rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t main_tiles = 0;       // main accumulator uses so far
+      uint32_t units_done = 0;       // second accumulator uses so far
+      int ws = 0;
+      uint32_t wphase = 0;
+      uint32_t chained[2] = {0, 0};  // chunks of group g fed to the second GEMM so far
+      const uint32_t d_main = tmem_base, d_acc2 = tmem_base + BLOCK_N;
+      // second GEMM on chunk j of the unit (j = nt * CH + c): A = staging tile of group j & 1, B = next W2 tile
+      auto chain = [&](int j) {
+        const int g = j & 1;
+        mbar_wait(&w2_full[ws], wphase);
+        mbar_wait_cluster(&chunk_ready[g], chained[g] & 1u);
+        if (j == 0) mbar_wait(acc2_empty, (units_done & 1u) ^ 1u);
+        tc_fence_after();
+        const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(out_stage + g * kEpiChunkBytes));
+        const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(w2_ring + ws * Cfg::W2_BYTES));
+        if (issuer) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_pair(d_acc2, a_desc + 2 * k, b_desc + 2 * k, IDESC2, (j | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&w2_empty[ws]);
+          umma_commit_pair(&chunk_free[g]);
+        }
+        __syncwarp();
+        ++chained[g];
+        if (++ws == kTailW2Stages) {
+          ws = 0;
+          wphase ^= 1;
+        }
+      };
+      for (int it = worker; it < m_units; it += n_workers) {
+        for (int nt = 0; nt < NT; ++nt) {
+          mbar_wait(tmem_empty, (main_tiles & 1u) ^ 1u);
+          tc_fence_after();
+          for (int kb = 0; kb < k_iters; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint64_t a_desc = make_kmajor_desc<128>(a_addr);
+            const uint64_t b_desc = make_kmajor_desc<128>(a_addr + Cfg::A_BYTES);
+            if (issuer) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16_pair(d_main, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+              umma_commit_pair(&empty_bar[stage]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (issuer) umma_commit_pair(tmem_full);
+          __syncwarp();
+          ++main_tiles;
+          // software pipeline: the last two chunks of the previous tile are chained AFTER this tile's main MMAs, so
+          // the main accumulator is refilled while the epilogue still works on them
+          if (nt > 0) {
+            chain((nt - 1) * CH + 2);
+            chain((nt - 1) * CH + 3);
+          }
+          chain(nt * CH + 0);
+          chain(nt * CH + 1);
+        }
+        chain((NT - 1) * CH + 2);
+        chain((NT - 1) * CH + 3);
+        if (issuer) umma_commit_pair(acc2_full);
+        __syncwarp();
+        ++units_done;
+      }
+    }
+  } else if (warp == 2) {
+    // ================================================================ W2 producer ([N2/2 rows of this CTA] x 64 K per chunk)
+    const bool issuer = elect_one();
+    int ws = 0;
+    uint32_t wphase = 0;
+    for (int it = worker; it < m_units; it += n_workers) {
+      for (int j = 0; j < bp.n2_k_chunks; ++j) {
+        mbar_wait(&w2_empty[ws], wphase ^ 1);
+        if (issuer) {
+          if (cta_rank == 0) mbar_arrive_expect_tx(&w2_full[ws], 2 * Cfg::W2_BYTES);
+          tma_load_2d_pair(w2_ring + ws * Cfg::W2_BYTES, &tmap_w2, &w2_full[ws], j * BLOCK_K, cta_rank * (N2 / 2));
+        }
+        __syncwarp();
+        if (++ws == kTailW2Stages) {
+          ws = 0;
+          wphase ^= 1;
+        }
+      }
+    }
+    for (int s2 = 0; s2 < kTailW2Stages; ++s2) {  // drain
+      mbar_wait(&w2_empty[ws], wphase ^ 1);
+      if (++ws == kTailW2Stages) {
+        ws = 0;
+        wphase ^= 1;
+      }
+    }
+  } else if (warp == 3) {
+    // ================================================================ residual prefetcher
+    if constexpr (RES) {
+      const bool issuer = elect_one();
+      uint32_t ctr = 0;
+      for (int it = worker; it < m_units; it += n_workers) {
+        const int unit = p.reverse ? m_units - 1 - it : it;
+        int cx, cy, cn;
+        tile_coords(unit, &cx, &cy, &cn);
+        for (int nt = 0; nt < NT; ++nt)
+          for (int c0 = 0; c0 < BLOCK_N; c0 += 64, ++ctr) {
+            const int rb = ctr % kResStages;
+            mbar_wait(&res_empty[rb], ((ctr / kResStages) & 1) ^ 1);
+            if (issuer) {
+              mbar_arrive_expect_tx(&res_full[rb], p.res_tx_bytes);
+              tma_load_5d(res_stage + rb * kEpiChunkBytes, &tmap_res, &res_full[rb], nt * BLOCK_N + c0,
+                          cx * p.res_stride, cy * p.res_stride, 0, cn);
+            }
+            __syncwarp();
+          }
+      }
+    }
+  } else {
+    // ================================================================ epilogue: two warpgroups on alternate chunks
+    const int grp = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const bool leader = (threadIdx.x == 128 + grp * 128);
+    const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(r & 7);
+    uint8_t* ostage = out_stage + grp * kEpiChunkBytes;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t main_tiles = 0, units_done = 0, res_ctr = 0;
+    uint32_t fed = 0;           // chunks of this group handed to the second GEMM so far
+    bool free_pending = false;  // the staging tile's last content was handed to the second GEMM: wait before rewriting
+
+    // fp32 x 64 (+ bias, + residual) -> relu? -> fp16 into the swizzled staging tile
+    auto stage_chunk = [&](const uint32_t (&v)[64], const float* bias, bool relu, const uint8_t* rstage) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+        if (bias != nullptr) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j + 4));
+          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+        }
+        const uint32_t off = row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);
+        if (rstage != nullptr) {
+          const uint4 rv = *reinterpret_cast<const uint4*>(rstage + off);
+          const __half2* h = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 t = __half22float2(h[e]);
+            f[2 * e] += t.x;
+            f[2 * e + 1] += t.y;
+          }
+        }
+        uint4 o;
+        if (relu) {
+          o.x = pack_half2_relu(f[0], f[1]); o.y = pack_half2_relu(f[2], f[3]);
+          o.z = pack_half2_relu(f[4], f[5]); o.w = pack_half2_relu(f[6], f[7]);
+        } else {
+          o.x = pack_half2(f[0], f[1]); o.y = pack_half2(f[2], f[3]);
+          o.z = pack_half2(f[4], f[5]); o.w = pack_half2(f[6], f[7]);
+        }
+        *reinterpret_cast<uint4*>(ostage + off) = o;
+      }
+    };
+    // the staging tile may be rewritten once its TMA store has read it and (if it was chained) the second GEMM has
+    auto wait_stage_free = [&]() {
+      if (free_pending) {
+        mbar_wait(&chunk_free[grp], (fed - 1) & 1u);
+        free_pending = false;
+      }
+      if (leader) bulk_wait_group_read<0>();
+      named_bar_sync(1 + grp, 128);
+    };
+
+    for (int it = worker; it < m_units; it += n_workers) {
+      const int unit = p.reverse ? m_units - 1 - it : it;
+      int cx, cy, cn;
+      tile_coords(unit, &cx, &cy, &cn);
+      for (int nt = 0; nt < NT; ++nt) {
+        mbar_wait(tmem_full, main_tiles & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = grp; c < CH; c += 2) {
+          const int c0 = c * 64;
+          uint32_t v[64];
+          tmem_ld_32x32(t_lane + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32(t_lane + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+          if (c + 2 >= CH) {  // this group's share of the main accumulator has been read
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tmem_empty);
+          }
+          const int col0 = nt * BLOCK_N + c0;
+          const uint8_t* rstage = nullptr;
+          uint32_t rb = 0;
+          if constexpr (RES) {
+            const uint32_t ctr = res_ctr + static_cast<uint32_t>(c);
+            rb = ctr % kResStages;
+            mbar_wait(&res_full[rb], (ctr / kResStages) & 1);
+            rstage = res_stage + rb * kEpiChunkBytes;
+          }
+          wait_stage_free();
+          stage_chunk(v, p.bias != nullptr ? p.bias + col0 : nullptr, col0 < p.relu_cols, rstage);
+          fence_proxy_async_all();  // generic-proxy smem writes -> visible to the TMA store and to the tensor cores
+          named_bar_sync(1 + grp, 128);
+          if (leader) {
+            tma_store_5d(&tmap_out, ostage, col0, cx, cy, 0, cn);
+            bulk_commit_group();
+            if constexpr (RES) mbar_arrive(&res_empty[rb]);
+            mbar_arrive_leader_release(&chunk_ready[grp]);  // this CTA's half of the chunk is in place
+          }
+          ++fed;
+          free_pending = true;
+        }
+        res_ctr += CH;
+        ++main_tiles;
+      }
+      // ---- second accumulator -> Y (bias2, ReLU), written through the same staging tile
+      if (grp < CH2) {
+        mbar_wait(acc2_full, units_done & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int e = grp; e < CH2; e += 2) {
+          uint32_t v[64];
+          tmem_ld_32x32(t_lane + BLOCK_N + e * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32(t_lane + BLOCK_N + e * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+          tmem_ld_wait();
+          if (e + 2 >= CH2) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(acc2_empty);
+          }
+          wait_stage_free();
+          stage_chunk(v, bp.bias2 + e * 64, true, nullptr);
+          fence_proxy_async_all();
+          named_bar_sync(1 + grp, 128);
+          if (leader) {
+            tma_store_5d(&tmap_out2, ostage, e * 64, cx, cy, 0, cn);
+            bulk_commit_group();
+          }
+        }
+      }
+      ++units_done;
+    }
+    if (leader) bulk_wait_group<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
+}  // namespace vnect

@@ -77,28 +77,48 @@ struct ConvGemmParams {
 // per CTA and stays there; the pipeline stages then carry activations only.  For the 64-channel 3x3 convs this cuts
 // the L2->SM traffic per tile from 9 x 24 KB to 9 x 16 KB, and those layers are bound by exactly that traffic.
 constexpr int kMaxResidentKBlocks = 9;
-template <int BLOCK_N, int SWZ, int EPI, int CG = 1, bool BRES = false>
+// HALO (3x3 stride-1 convs at 92x92 / 46x46): instead of one TMA box per filter tap (nine boxes that fetch the same
+// pixels nine times: measured 9.5x the input bytes in L2->SM traffic, and as many smem writes competing with the
+// MMA's operand reads for the 128 B/clk shared-memory port), ONE (8+2) x (16+2) pixel patch per 64-channel block is
+// loaded and all nine taps read it in place: the A descriptor of tap (ky, kx) starts (ky * 10 + kx) pixels = that
+// many 128-byte rows into the patch, its 8-row groups are one patch row (10 px = 1280 B) apart.  tcgen05 applies the
+// 128B swizzle to absolute smem address bits, so a start that is not 1024-byte aligned and a stride that is not a
+// multiple of 1024 read exactly what the TMA wrote (measured: selftest `probe`, base_offset 0, every shift / pitch).
+// The weight tiles have their own ring (filled by warp 3) or are resident (BRES); the patch ring reuses the
+// residual-prefetch barriers, which a 3x3 conv never needs.
+constexpr int kHaloTW = 8, kHaloTH = 16;                  // output tile: 8 x 16 pixels = 128 GEMM rows, m = ly * 8 + lx
+constexpr int kHaloPW = kHaloTW + 2, kHaloPH = kHaloTH + 2;
+constexpr int kHaloPatchTx = kHaloPW * kHaloPH * 128;      // bytes one patch load delivers (OOB pixels are zero-filled)
+constexpr int kHaloABytes = ((kHaloPatchTx + 1023) / 1024) * 1024;
+template <int BLOCK_N, int SWZ, int EPI, int CG = 1, bool BRES = false, bool HALO = false>
 struct GemmCfg {
   static constexpr int BLOCK_K = SWZ / 2;  // fp16 elements per smem row
   static constexpr int A_BYTES = kBlockM * SWZ;
   static constexpr int B_BYTES = (BLOCK_N / CG) * SWZ;
-  static constexpr int STAGE_BYTES = BRES ? A_BYTES : A_BYTES + B_BYTES;
+  // ring stage: A + B tiles; activations only with resident weights; weight tiles only in HALO mode (the patches have
+  // their own ring); HALO + BRES streams nothing through it (one dummy stage keeps the barrier arrays non-empty)
+  static constexpr int STAGE_BYTES = HALO ? (BRES ? 1024 : B_BYTES) : (BRES ? A_BYTES : A_BYTES + B_BYTES);
   static constexpr int BRES_BYTES = BRES ? kMaxResidentKBlocks * B_BYTES : 0;
+  static constexpr int HALO_STAGES = HALO ? (BRES ? 4 : 3) : 0;  // <= kResStages (shares those barriers)
+  static constexpr int HALO_BYTES = HALO_STAGES * kHaloABytes;
   static constexpr int EPI_BYTES = (EPI == EPI_TMA)          ? kEpiGroups * kOutStages * kEpiChunkBytes
                                    : (EPI == EPI_TMA_RES)    ? (kEpiGroups * kOutStages + kResStages) * kEpiChunkBytes
                                    : (EPI == EPI_PLANAR_F32) ? BLOCK_N * kBlockM * 4  // [column][row] fp32 transpose tile
                                                              : 0;
   // two epilogue warpgroups: the TMA epilogues (alternate 64-column chunks) and the deconv head (features / deltas)
   static constexpr int THREADS = (EPI == EPI_TMA || EPI == EPI_TMA_RES || EPI == EPI_DECONV_HEAD) ? kGemmThreadsTma : kGemmThreads;
-  static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - EPI_BYTES - BRES_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - EPI_BYTES - BRES_BYTES - HALO_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_MAX = HALO ? (BRES ? 1 : 16) : 8;
+  static constexpr int STAGES = STAGES_RAW > STAGES_MAX ? STAGES_MAX : STAGES_RAW;
   static constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                         : (2 * BLOCK_N <= 64)  ? 64
                                         : (2 * BLOCK_N <= 128) ? 128
                                         : (2 * BLOCK_N <= 256) ? 256
                                                                : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
-  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + HALO_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+  static_assert(STAGES >= 2 || (HALO && BRES), "pipeline needs at least two stages");
+  static_assert(!HALO || (EPI == EPI_TMA && SWZ == 128), "the halo-patch path is the plain 3x3 conv: EPI_TMA, 128B swizzle");
+  static_assert(2 * STAGES + 5 + 2 * kResStages + 2 <= 64, "barriers must fit their 512-byte region");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "epilogue walks 32-column chunks");
   static_assert(CG == 1 || CG == 2, "a CTA pair at most");
@@ -118,12 +138,12 @@ __device__ __forceinline__ uint32_t pack_half2_relu(float a, float b) {
   return d;
 }
 
-template <int BLOCK_N, int SWZ, int EPI, int CG = 1, bool BRES = false>
+template <int BLOCK_N, int SWZ, int EPI, int CG = 1, bool BRES = false, bool HALO = false>
 __global__ void __launch_bounds__((EPI == EPI_TMA || EPI == EPI_TMA_RES || EPI == EPI_DECONV_HEAD) ? kGemmThreadsTma : kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ ConvGemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI, CG, BRES>;
+  using Cfg = GemmCfg<BLOCK_N, SWZ, EPI, CG, BRES, HALO>;
   static_assert(!BRES || CG == 1, "resident weights are a single-CTA variant");
   constexpr bool kTmaEpi = (EPI == EPI_TMA || EPI == EPI_TMA_RES);
   constexpr int BLOCK_K = Cfg::BLOCK_K;
@@ -136,9 +156,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_res = smem + STAGES * Cfg::STAGE_BYTES;                            // BRES: k_iters x B_BYTES, resident
-  uint8_t* out_stage = b_res + Cfg::BRES_BYTES;                                 // 2 groups x kOutStages x 16 KB
+  uint8_t* halo = b_res + Cfg::BRES_BYTES;                                      // HALO: patch ring, HALO_STAGES x 23 KB
+  uint8_t* out_stage = halo + Cfg::HALO_BYTES;                                  // 2 groups x kOutStages x 16 KB
   uint8_t* res_stage = out_stage + kEpiGroups * kOutStages * kEpiChunkBytes;    // kResStages x 16 KB (EPI_TMA_RES)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BRES_BYTES + Cfg::EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::BRES_BYTES + Cfg::HALO_BYTES + Cfg::EPI_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -228,6 +249,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           cy = (t2 / p.tiles_x) * p.th;
           cx = (t2 % p.tiles_x) * p.tw;
         }
+        if constexpr (HALO) {
+          // one (8+2) x (16+2) pixel patch per 64-channel block; `stage` / `phase` walk the PATCH ring here
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(&res_empty[stage], phase ^ 1);
+            if (issuer) {
+              uint8_t* sa = halo + stage * kHaloABytes;
+              if constexpr (CG == 2) {
+                if (cta_rank == 0) mbar_arrive_expect_tx(&res_full[stage], 2 * kHaloPatchTx);
+                tma_load_5d_pair(sa, &tmap_a, &res_full[stage], cb * BLOCK_K, cx - 1, cy - 1, 0, cn);
+              } else {
+                mbar_arrive_expect_tx(&res_full[stage], kHaloPatchTx);
+                tma_load_5d(sa, &tmap_a, &res_full[stage], cb * BLOCK_K, cx - 1, cy - 1, 0, cn);
+              }
+            }
+            __syncwarp();
+            if (++stage == Cfg::HALO_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          continue;
+        }
         const int b_row = ph * p.b_rows_per_phase + n_tile * BLOCK_N + cta_rank * (BLOCK_N / CG);
         for (int t = 0; t < p.taps; ++t) {
           const int ti = ph * p.taps + t;
@@ -278,9 +321,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if constexpr (CG == 2) {
         // drain: the leader's multicast commits still arrive on this CTA's empty barriers after the last load was
         // issued; do not let the CTA retire (and its smem be reused) before every slot has been released
-        for (int s2 = 0; s2 < STAGES; ++s2) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (++stage == STAGES) {
+        constexpr int kRing = HALO ? Cfg::HALO_STAGES : STAGES;
+        uint64_t* ring_empty = HALO ? res_empty : empty_bar;
+        for (int s2 = 0; s2 < kRing; ++s2) {
+          mbar_wait(&ring_empty[stage], phase ^ 1);
+          if (++stage == kRing) {
             stage = 0;
             phase ^= 1;
           }
@@ -295,6 +340,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      [[maybe_unused]] int astage = 0;        // HALO: patch ring position
+      [[maybe_unused]] uint32_t aphase = 0;
       if constexpr (BRES) {
         if (worker < total_tiles) mbar_wait(bres_full, 0);
       }
@@ -302,6 +349,55 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        if constexpr (HALO) {
+          // K order: channel block outermost, then the nine taps of the resident patch (all plans of a layer use this
+          // same order, so results do not depend on the plan)
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            mbar_wait(&res_full[astage], aphase);
+            tc_fence_after();
+            const uint32_t patch = smem_u32(halo + astage * kHaloABytes);
+#pragma unroll 1
+            for (int t = 0; t < 9; ++t) {
+              const int ky = t / 3, kx = t - 3 * ky;
+              const uint64_t a_desc = make_kmajor_desc_sbo(patch + static_cast<uint32_t>((ky * kHaloPW + kx) * 128), kHaloPW * 128);
+              uint64_t b_desc;
+              if constexpr (BRES) {
+                b_desc = make_kmajor_desc<SWZ>(smem_u32(b_res + (t * p.cblocks + cb) * Cfg::B_BYTES));
+              } else {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                b_desc = make_kmajor_desc<SWZ>(smem_u32(smem + stage * Cfg::STAGE_BYTES));
+              }
+              if (issuer) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                  if constexpr (CG == 2) umma_f16_pair(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (cb | t | k) != 0 ? 1u : 0u);
+                  else umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, IDESC, (cb | t | k) != 0 ? 1u : 0u);
+                }
+                if constexpr (!BRES) {
+                  if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage]);
+                  else umma_commit(&empty_bar[stage]);
+                }
+              }
+              __syncwarp();
+              if constexpr (!BRES) {
+                if (++stage == STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+            if (issuer) {  // the patch may be overwritten once these MMAs have read it
+              if constexpr (CG == 2) umma_commit_pair(&res_empty[astage]);
+              else umma_commit(&res_empty[astage]);
+            }
+            __syncwarp();
+            if (++astage == Cfg::HALO_STAGES) {
+              astage = 0;
+              aphase ^= 1;
+            }
+          }
+        } else
         for (int kb = 0; kb < k_iters; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -335,6 +431,46 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp == 3) {
+    // ================================================================ HALO: weight-tile producer (its own ring, so the
+    // next patch never queues behind nine weight tiles in one warp's program order)
+    if constexpr (HALO && !BRES) {
+      const bool issuer = elect_one();
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = worker; it < total_tiles; it += n_workers) {
+        const int tile = p.reverse ? total_tiles - 1 - it : it;
+        const int n_tile = tile % p.num_n_tiles;
+        const int b_row = n_tile * BLOCK_N + cta_rank * (BLOCK_N / CG);
+        for (int cb = 0; cb < p.cblocks; ++cb)
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (issuer) {
+              uint8_t* sb = smem + stage * Cfg::STAGE_BYTES;
+              if constexpr (CG == 2) {
+                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::B_BYTES);
+                tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_BYTES);
+                tma_load_2d(sb, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
+              }
+            }
+            __syncwarp();
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+      }
+      if constexpr (CG == 2) {
+        for (int s2 = 0; s2 < STAGES; ++s2) {  // drain, as in the patch producer
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
     // ================================================================ residual prefetcher (EPI_TMA_RES only)
     if constexpr (EPI == EPI_TMA_RES) {
       const bool issuer = elect_one();

@@ -8,6 +8,7 @@
 #include <string>
 
 #include "conv_gemm.cuh"
+#include "block_tail.cuh"
 #include "stem_roll.cuh"
 
 namespace vnect {
@@ -100,12 +101,23 @@ struct ConvSpec {
   int cg = 1;
   // 1: keep the layer's whole weight matrix resident in smem (single N tile, <= kMaxResidentKBlocks K blocks, no pairs)
   int b_resident = 0;
+  // 1: 3x3 stride-1 conv through one halo patch per channel block (8 x 16 pixel tiles, conv_gemm.cuh HALO)
+  int halo = 0;
+  // fused block tail (block_tail.cuh): this 1x1 conv (+ residual / folded shortcut) also feeds a second 1x1 conv
+  // Y = relu(out * W2^T + bias2) of n2 output channels; w2 is [n2][n_pad] fp16 K-major, out2 NHWC [.., n2] on the
+  // same pixel grid as `out`.  Needs block_n = 256 on CTA pairs and a TMA epilogue.
+  const __half* w2 = nullptr;
+  const float* bias2 = nullptr;
+  void* out2 = nullptr;
+  int n2 = 0;
 };
 
 struct ConvLaunch {
-  CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res, tmap_a2;
+  CUtensorMap tmap_a, tmap_b, tmap_out, tmap_res, tmap_a2, tmap_w2, tmap_out2;
   ConvGemmParams p;
-  int block_n = 0, swz = 128, epi = 0, grid = 0, cg = 1, b_resident = 0;
+  const float* bias2 = nullptr;
+  int n2 = 0;  // > 0: fused block tail (block_tail_kernel)
+  int block_n = 0, swz = 128, epi = 0, grid = 0, cg = 1, b_resident = 0, halo = 0;
   size_t smem = 0;
   double flops = 0;  // algorithmic: 2 * valid rows * n_valid * taps * real Cin is tracked by the caller; this is GEMM work
 };
@@ -115,6 +127,13 @@ inline int conv_grid(const ConvGemmParams& p, int cg, int num_sms) {
   const int units = p.phases * ((p.num_m_tiles + cg - 1) / cg) * p.num_n_tiles;
   const int workers = num_sms / cg;
   return cg * (units < workers ? units : workers);
+}
+
+// fused block tail: one CTA pair per 256-row unit, walking all output-channel tiles of its rows
+inline int tail_grid(const ConvGemmParams& p, int num_sms) {
+  const int units = (p.num_m_tiles + 1) / 2;
+  const int workers = num_sms / 2;
+  return 2 * (units < workers ? units : workers);
 }
 
 inline void choose_tile(int H, int W, int* tw_out, int* th_out) {
@@ -134,6 +153,16 @@ inline void choose_tile(int H, int W, int* tw_out, int* th_out) {
   *th_out = bth;
 }
 
+// The halo-patch kernel works on fixed 8 x 16 pixel tiles; use it where that tiling wastes at most ~10 % more GEMM rows
+// than the free-form tile (92x92, 46x46, 56x56, 64x64 grids: yes; 23x23 and 28x28: no, those layers are tensor-bound)
+inline bool halo_tiling_ok(int H, int W) {
+  int tw, th;
+  choose_tile(H, W, &tw, &th);
+  const int free_tiles = ((W + tw - 1) / tw) * ((H + th - 1) / th);
+  const int halo_tiles = ((W + kHaloTW - 1) / kHaloTW) * ((H + kHaloTH - 1) / kHaloTH);
+  return halo_tiles * 10 <= free_tiles * 11;
+}
+
 inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::string* err) {
   memset(L, 0, sizeof(*L));
   ConvGemmParams& p = L->p;
@@ -144,6 +173,12 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
   L->epi = s.epi;
   L->cg = s.cg;
   L->b_resident = s.b_resident;
+  L->halo = s.halo;
+  if (s.halo && (s.kind != CONV_3x3 || s.in_stride != 1 || s.epi != EPI_TMA || (s.block_n != 64 && s.block_n != 128) ||
+                 (s.cg == 2 && s.block_n != 128) || (s.b_resident && s.block_n != 64))) {
+    if (err) *err = "the halo-patch path needs a stride-1 3x3 conv with an EPI_TMA output and a 64- or 128-column tile";
+    return false;
+  }
   if (s.cg != 1 && (s.cg != 2 || s.kind == CONV_STEM7 || (s.block_n / 2) % 8 != 0)) {
     if (err) *err = "unsupported CTA-pair configuration";
     return false;
@@ -194,7 +229,12 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     p.cblocks2 = s.cin2_pad / block_k;
   } else if (s.kind == CONV_3x3 || s.kind == CONV_DECONV4 || spatial1) {
     p.mode = 1;
-    choose_tile(s.H, s.W, &p.tw, &p.th);
+    if (s.halo) {
+      p.tw = kHaloTW;
+      p.th = kHaloTH;
+    } else {
+      choose_tile(s.H, s.W, &p.tw, &p.th);
+    }
     p.tiles_x = (s.W + p.tw - 1) / p.tw;
     p.tiles_y = (s.H + p.th - 1) / p.th;
     p.num_m_tiles = s.NB * p.tiles_x * p.tiles_y;
@@ -237,6 +277,10 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     strides[2] = strides[1] * dims[2];
     strides[3] = strides[2];
     box[0] = block_k; box[1] = p.tw * s.in_stride; box[2] = p.th * s.in_stride; box[3] = 1; box[4] = 1;
+    if (s.halo) {  // the A box is the whole patch: tile + one pixel of halo on every side
+      box[1] = kHaloPW;
+      box[2] = kHaloPH;
+    }
     k_total = p.taps * s.cin_pad;
   } else {  // CONV_STEM7
     p.mode = 1;
@@ -264,6 +308,7 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
   // per CTA: its A rows plus its share of the B tile (half of it in a CTA pair; nothing when the weights are resident)
   p.stage_tx_bytes = (uint32_t)(box[0] * (box[1] / a_stride) * (box[2] / a_stride) * 2 +
                                 (s.b_resident ? 0u : (uint32_t)(s.block_n / s.cg) * block_k * 2));
+  if (s.halo) p.stage_tx_bytes = 0;  // patch / weight-tile byte counts are compile-time constants of the HALO kernel
   if (s.b_resident && (s.cg != 1 || p.num_n_tiles != 1 || p.phases != 1 || s.in2 || k_total / block_k > kMaxResidentKBlocks ||
                        s.block_n != 64 || s.epi != EPI_TMA || swz != 128)) {
     if (err) *err = "resident weights need a single-tile 64-column EPI_TMA layer of at most 9 K blocks";
@@ -313,6 +358,22 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
       return encode_tmap(m, ptr, 5, od, os, ob, 128, err, stride != 1 ? es : nullptr);
     };
     if (!act_map(s.out, s.ldc, &L->tmap_out, 1)) return false;
+    L->tmap_out2 = L->tmap_out;
+    L->tmap_w2 = L->tmap_b;
+    if (s.out2 != nullptr) {
+      if (s.block_n != kTailBlockN || s.cg != 2 || s.kind != CONV_1x1 || (s.n2 != 64 && s.n2 != 128 && s.n2 != 256) ||
+          !s.w2 || !s.bias2 || s.n_pad % kTailBlockN != 0 || s.b_resident || s.halo) {
+        if (err) *err = "a fused block tail needs a 1x1 conv on CTA pairs with 256-column tiles and a 64/128/256-wide second conv";
+        return false;
+      }
+      if (!act_map(s.out2, s.n2, &L->tmap_out2, 1)) return false;
+      uint64_t wd[2] = {(uint64_t)s.n_pad, (uint64_t)s.n2};
+      uint64_t ws[1] = {(uint64_t)s.n_pad * 2};
+      uint32_t wb[2] = {64, (uint32_t)(s.n2 / 2)};
+      if (!encode_tmap(&L->tmap_w2, s.w2, 2, wd, ws, wb, 128, err)) return false;
+      L->n2 = s.n2;
+      L->bias2 = s.bias2;
+    }
     if (s.epi == EPI_TMA_RES) {
       if (!s.residual) {
         if (err) *err = "EPI_TMA_RES without a residual";
@@ -322,8 +383,12 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
       p.res_tx_bytes = (ob[1] / s.res_stride) * (ob[2] / s.res_stride) * 128;
     }
   }
-  L->grid = conv_grid(p, s.cg, num_sms);
-  L->flops = 2.0 * p.phases * (double)p.M * s.n_pad * k_total;
+  if (s.out2 != nullptr && L->n2 == 0) {
+    if (err) *err = "a fused block tail needs a TMA epilogue";
+    return false;
+  }
+  L->grid = L->n2 ? tail_grid(p, num_sms) : conv_grid(p, s.cg, num_sms);
+  L->flops = 2.0 * p.phases * (double)p.M * s.n_pad * k_total + 2.0 * (double)p.M * s.n_pad * L->n2;
   return true;
 }
 
@@ -391,7 +456,45 @@ inline cudaError_t launch_one_bres(const ConvLaunch& L, cudaStream_t st) {
                     L.tmap_res, L.tmap_a2, L.p);
 }
 
+template <int BLOCK_N, int CG, bool BRES>
+inline cudaError_t launch_one_halo(const ConvLaunch& L, cudaStream_t st) {
+  using Cfg = GemmCfg<BLOCK_N, 128, EPI_TMA, CG, BRES, true>;
+  static unsigned long long done = 0;
+  auto kern = conv_gemm_kernel<BLOCK_N, 128, EPI_TMA, CG, BRES, true>;
+  if (cudaError_t e = ensure_dyn_smem(kern, Cfg::SMEM_BYTES, &done); e != cudaSuccess) return e;
+  return launch_pdl_cluster(kern, dim3(L.grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, CG, L.tmap_a, L.tmap_b,
+                            L.tmap_out, L.tmap_res, L.tmap_a2, L.p);
+}
+
+template <int N2, bool RES>
+inline cudaError_t launch_one_tail(const ConvLaunch& L, cudaStream_t st) {
+  using Cfg = TailCfg<N2, RES>;
+  static unsigned long long done = 0;
+  auto kern = block_tail_kernel<N2, RES>;
+  if (cudaError_t e = ensure_dyn_smem(kern, Cfg::SMEM_BYTES, &done); e != cudaSuccess) return e;
+  BlockTailParams bp;
+  bp.g = L.p;
+  bp.bias2 = L.bias2;
+  bp.n2_k_chunks = L.p.num_n_tiles * (kTailBlockN / 64);
+  return launch_pdl_cluster(kern, dim3(L.grid), dim3(kGemmThreadsTma), Cfg::SMEM_BYTES, st, 2, L.tmap_a, L.tmap_b,
+                            L.tmap_out, L.tmap_res, L.tmap_a2, L.tmap_w2, L.tmap_out2, bp);
+}
+
 inline cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
+  if (L.n2) {
+    const bool res = L.epi == EPI_TMA_RES;
+    if (L.n2 == 64) return res ? launch_one_tail<64, true>(L, st) : launch_one_tail<64, false>(L, st);
+    if (L.n2 == 128) return res ? launch_one_tail<128, true>(L, st) : launch_one_tail<128, false>(L, st);
+    if (L.n2 == 256) return res ? launch_one_tail<256, true>(L, st) : launch_one_tail<256, false>(L, st);
+    return cudaErrorInvalidConfiguration;
+  }
+  if (L.halo) {
+    if (L.b_resident) return launch_one_halo<64, 1, true>(L, st);
+    if (L.block_n == 128 && L.cg == 2) return launch_one_halo<128, 2, false>(L, st);
+    if (L.block_n == 128 && L.cg == 1) return launch_one_halo<128, 1, false>(L, st);
+    if (L.block_n == 64 && L.cg == 1) return launch_one_halo<64, 1, false>(L, st);
+    return cudaErrorInvalidConfiguration;
+  }
   if (L.b_resident) return launch_one_bres<64, 128, EPI_TMA>(L, st);
   if (L.cg == 2) {  // CTA pairs: the production epilogues only
     if (L.swz != 128) return cudaErrorInvalidConfiguration;

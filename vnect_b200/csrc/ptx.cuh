@@ -251,6 +251,19 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Same, with an explicit byte stride between 8-row groups (the halo-patch convolution: one patch row apart) and a
+// start address that only needs 128-byte alignment.  The swizzle is a function of absolute smem address bits
+// (base-offset field 0), which is what makes a descriptor shifted by whole 128-byte rows read a TMA-written patch.
+__device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;  // 128B swizzle
+  return d;
+}
+
 // Instruction descriptor, kind::f16: fp32 accumulate, A/B both K-major, no negate / sparsity / saturate.
 //   bits 4-5 D format (1 = f32), bits 7-9 A format, bits 10-12 B format (0 = f16, 1 = bf16),
 //   bit 15 / 16 A / B major (0 = K), bits 17-22 N >> 3, bits 24-28 M >> 4.

@@ -80,7 +80,24 @@ struct Case {
   int cin2 = 0;  // folded shortcut: second input tensor with cin2 channels (1x1 only)
   int cg = 1;    // 2: CTA pairs (tcgen05 cta_group::2)
   int bres = 0;  // 1: weights resident in smem
+  int halo = 0;  // 1: 3x3 conv through halo patches (8 x 16 pixel tiles, nine taps read one smem patch)
+  int n2 = 0;    // > 0: fused block tail, second 1x1 conv of n2 channels on this conv's output (block_tail.cuh)
 };
+
+// reference of the chained conv, from the fp16 X the kernel under test wrote: y[m][col] = relu(sum_c X[m][c] * W2[col][c] + b2[col])
+__global__ void naive_chain_kernel(const __half* __restrict__ x, const __half* __restrict__ w2, const float* __restrict__ b2,
+                                   float* __restrict__ y, long long rows, int cout, int n2) {
+  const long long total = rows * n2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % n2);
+    const long long m = i / n2;
+    const __half* xr = x + m * cout;
+    const __half* wr = w2 + (size_t)col * cout;
+    float s = 0.f;
+    for (int c = 0; c < cout; ++c) s += __half2float(xr[c]) * __half2float(wr[c]);
+    y[i] = fmaxf(s + b2[col], 0.f);
+  }
+}
 
 static int run_case(const Case& c, int num_sms, bool timing) {
   ConvSpec s;
@@ -99,6 +116,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   s.res_stride = c.res_stride;
   s.cg = c.cg;
   s.b_resident = c.bres;
+  s.halo = c.halo;
   const int phases = c.kind == CONV_DECONV4 ? 4 : 1;
   const int taps = c.kind == CONV_1x1 ? 1 : c.kind == CONV_3x3 ? 9 : c.kind == CONV_DECONV4 ? 4 : 7;
   const int k_total = c.kind == CONV_STEM7 ? 7 * 32 : taps * c.cin_pad + c.cin2;
@@ -157,6 +175,22 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   if (c.residual) {
     CK(cudaMalloc(&d_res, h_res.size() * 2));
     CK(cudaMemcpy(d_res, h_res.data(), h_res.size() * 2, cudaMemcpyHostToDevice));
+  }
+  __half *d_w2 = nullptr, *d_out2 = nullptr;
+  float* d_bias2 = nullptr;
+  if (c.n2) {
+    std::vector<__half> h_w2((size_t)c.n2 * c.n_pad);
+    std::vector<float> h_b2(c.n2);
+    const float w2s = 2.0f / sqrtf((float)c.n_pad);
+    for (auto& v : h_w2) v = __float2half(frand() * w2s);
+    for (auto& v : h_b2) v = frand() * 0.5f;
+    CK(cudaMalloc(&d_w2, h_w2.size() * 2));
+    CK(cudaMalloc(&d_bias2, c.n2 * 4));
+    CK(cudaMalloc(&d_out2, (size_t)c.NB * c.H * c.W * c.n2 * 2));
+    CK(cudaMemset(d_out2, 0xff, (size_t)c.NB * c.H * c.W * c.n2 * 2));
+    CK(cudaMemcpy(d_w2, h_w2.data(), h_w2.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_bias2, h_b2.data(), c.n2 * 4, cudaMemcpyHostToDevice));
+    s.w2 = d_w2; s.bias2 = d_bias2; s.out2 = d_out2; s.n2 = c.n2;
   }
   s.in = d_in;
   s.in2 = d_in2;
@@ -245,6 +279,19 @@ static int run_case(const Case& c, int num_sms, bool timing) {
             for (int j = 212; j < 216; ++j) check(__half2float(o16[pix * ldc + j]), 0.f);
           }
         }
+  if (c.n2) {  // the chained conv against a naive evaluation on the X this kernel wrote
+    const long long rows = (long long)c.NB * c.H * c.W;
+    float* d_y;
+    CK(cudaMalloc(&d_y, rows * c.n2 * 4));
+    naive_chain_kernel<<<1184, 256>>>(reinterpret_cast<const __half*>(d_out), d_w2, d_bias2, d_y, rows, c.n_pad, c.n2);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> h_y((size_t)rows * c.n2);
+    std::vector<__half> h_o2((size_t)rows * c.n2);
+    CK(cudaMemcpy(h_y.data(), d_y, h_y.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_o2.data(), d_out2, h_o2.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h_y.size(); ++i) check(__half2float(h_o2[i]), h_y[i]);
+    cudaFree(d_y);
+  }
   printf("[%s] tiles=%d grid=%d tile=%dx%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n", c.name,
          L.p.phases * L.p.num_m_tiles * L.p.num_n_tiles, L.grid, L.p.tw, L.p.th, checked, bad, max_err,
          bad == 0 ? "PASS" : "FAIL");
@@ -267,6 +314,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   cudaFree(d_in); cudaFree(d_w); cudaFree(d_bias); cudaFree(d_out); cudaFree(d_acc);
   if (d_res) cudaFree(d_res);
   if (d_in2) cudaFree(d_in2);
+  if (d_w2) { cudaFree(d_w2); cudaFree(d_bias2); cudaFree(d_out2); }
   return bad == 0 ? 0 : 1;
 }
 
@@ -548,6 +596,39 @@ int main(int argc, char** argv) {
     fails += run_case(r2, sms, true);
     fails += run_case(r3, sms, true);
   }
+  {  // halo-patch 3x3 convs: every instantiation, image sizes that are / are not multiples of the 8 x 16 tile
+    Case h1 = {"HALO BRES 3x3 64->64 relu 92x92", CONV_3x3, 2, 92, 92, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0};
+    Case h2 = {"HALO 3x3 64->64 relu 92x92 (streamed B)", CONV_3x3, 2, 92, 92, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0};
+    Case h3 = {"HALO PAIR 3x3 128->128 relu 46x46", CONV_3x3, 3, 46, 46, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0};
+    Case h4 = {"HALO 3x3 128->128 relu 46x46 bn128 single", CONV_3x3, 3, 46, 46, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0};
+    Case h5 = {"HALO 3x3 128->128 relu 46x46 bn64", CONV_3x3, 1, 46, 46, 128, 128, 128, 64, EPI_TMA, true, false, 128, 0};
+    Case h6 = {"HALO PAIR 3x3 256->128 relu 46x46 (head)", CONV_3x3, 2, 46, 46, 256, 128, 128, 128, EPI_TMA, true, false, 128, 0};
+    Case h7 = {"HALO PAIR 3x3 128->128 lin 56x56", CONV_3x3, 1, 56, 56, 128, 128, 128, 128, EPI_TMA, true, false, 0, 0};
+    Case h8 = {"HALO BRES 3x3 64->64 relu 17x9", CONV_3x3, 3, 17, 9, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0};
+    h1.bres = h8.bres = 1;
+    h3.cg = h6.cg = h7.cg = 2;
+    for (Case* c : {&h1, &h2, &h3, &h4, &h5, &h6, &h7, &h8}) {
+      c->halo = 1;
+      fails += run_case(*c, sms, true);
+    }
+  }
+  {  // fused block tails: every (N2, residual) instantiation, flat and spatial rows, folded shortcut, odd unit counts
+    Case t1 = {"TAIL 1x1 64->256 +res relu 92x92 > 64", CONV_1x1, 2, 92, 92, 64, 256, 256, 256, EPI_TMA_RES, true, true, 256, 0};
+    Case t2 = {"TAIL FOLD 1x1 64(+64)->256 relu 92x92 > 64", CONV_1x1, 2, 92, 92, 64, 256, 256, 256, EPI_TMA, true, false, 256, 0, 1, 1, 64};
+    Case t3 = {"TAIL 1x1 128->512 +res relu 46x46 > 128", CONV_1x1, 3, 46, 46, 128, 512, 512, 256, EPI_TMA_RES, true, true, 512, 0};
+    Case t4 = {"TAIL FOLD 1x1 128(+256)->512 relu 46x46 > 128", CONV_1x1, 3, 46, 46, 128, 512, 512, 256, EPI_TMA, true, false, 512, 0, 1, 1, 256};
+    Case t5 = {"TAIL 1x1 256->1024 +res relu 23x23 > 256", CONV_1x1, 7, 23, 23, 256, 1024, 1024, 256, EPI_TMA_RES, true, true, 1024, 0};
+    Case t6 = {"TAIL FOLD 1x1 512(+1024)->1024 relu 23x23 > 256", CONV_1x1, 5, 23, 23, 512, 1024, 1024, 256, EPI_TMA, true, false, 1024, 0, 1, 1, 1024};
+    Case t7 = {"TAIL S2RES 1x1 64->256 +res(92) relu 46x46 > 128", CONV_1x1, 2, 46, 46, 64, 256, 256, 256, EPI_TMA_RES, true, true, 256, 0, 1, 2};
+    Case t8 = {"TAIL S2RES 1x1 128->512 +res(46) relu 23x23 > 256", CONV_1x1, 3, 23, 23, 128, 512, 512, 256, EPI_TMA_RES, true, true, 512, 0, 1, 2};
+    t1.n2 = t2.n2 = 64;
+    t3.n2 = t4.n2 = t7.n2 = 128;
+    t5.n2 = t6.n2 = t8.n2 = 256;
+    for (Case* c : {&t1, &t2, &t3, &t4, &t5, &t6, &t7, &t8}) {
+      c->cg = 2;
+      fails += run_case(*c, sms, true);
+    }
+  }
   fails += run_stem_pool(2, 368, sms);
   fails += run_stem_pool(2, 448, sms);
   fails += run_stem_pool(1, 64, sms);
@@ -588,6 +669,31 @@ int main(int argc, char** argv) {
       fails += run_case(b1, sms, true);
       fails += run_case(b2, sms, true);
       fails += run_case(b3, sms, true);
+    }
+    {  // fused block tails at full batch (compare: the unfused 2c kernels above + the stand-alone reduce convs)
+      Case a = {"BIG TAIL 1x1 64->256 +res 92x92 nb128 > 64", CONV_1x1, 128, 92, 92, 64, 256, 256, 256, EPI_TMA_RES, true, true, 256, 0};
+      Case b = {"BIG TAIL 1x1 128->512 +res 46x46 nb128 > 128", CONV_1x1, 128, 46, 46, 128, 512, 512, 256, EPI_TMA_RES, true, true, 512, 0};
+      Case c = {"BIG TAIL 1x1 256->1024 +res 23x23 nb128 > 256", CONV_1x1, 128, 23, 23, 256, 1024, 1024, 256, EPI_TMA_RES, true, true, 1024, 0};
+      Case d = {"BIG TAIL FOLD 1x1 64(+64)->256 92x92 nb128 > 64", CONV_1x1, 128, 92, 92, 64, 256, 256, 256, EPI_TMA, true, false, 256, 0, 1, 1, 64};
+      a.n2 = d.n2 = 64; b.n2 = 128; c.n2 = 256;
+      a.cg = b.cg = c.cg = d.cg = 2;
+      fails += run_case(a, sms, true);
+      fails += run_case(b, sms, true);
+      fails += run_case(c, sms, true);
+      fails += run_case(d, sms, true);
+    }
+    {  // halo patches against the nine-box path, full batch
+      Case a = {"BIG HALO BRES 3x3 64->64 92x92 nb128", CONV_3x3, 128, 92, 92, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0};
+      Case b = {"BIG HALO PAIR 3x3 128->128 46x46 nb128", CONV_3x3, 128, 46, 46, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0};
+      Case c = {"BIG HALO PAIR 3x3 256->128 46x46 nb128 (head)", CONV_3x3, 128, 46, 46, 256, 128, 128, 128, EPI_TMA, true, false, 128, 0};
+      Case d = {"BIG PAIR 3x3 256->128 46x46 nb128 (head, nine boxes)", CONV_3x3, 128, 46, 46, 256, 128, 128, 128, EPI_TMA, true, false, 128, 0};
+      a.bres = 1;
+      b.cg = c.cg = d.cg = 2;
+      a.halo = b.halo = c.halo = 1;
+      fails += run_case(a, sms, true);
+      fails += run_case(b, sms, true);
+      fails += run_case(c, sms, true);
+      fails += run_case(d, sms, true);
     }
     for (const auto& c : pairc) {  // same layer on single CTAs and on CTA pairs, timings side by side
       fails += run_case(c, sms, true);

@@ -287,7 +287,40 @@ struct ConvOpts {
   std::string residual;  // act name or empty
   int in_stride = 1;     // 2: compute the conv at even input pixels only (output grid is half-size)
   int res_stride = 1;    // 2: the residual is a full-size tensor read at even pixels
+  // fused block tail (block_tail.cuh): scope of the NEXT block's 1x1 reduce conv, computed from this conv's output
+  // while it is still in shared memory; its output activation is created under that scope's name
+  std::string chain_scope;
+  int chain_cout = 0;
 };
+
+// The block tail is fused with the next block's reduce conv on the throughput plans (256-column tiles on CTA pairs);
+// VNECT_B200_CHAIN=0 turns it off (A/B measurement)
+static bool chain_enabled() {
+  static const bool on = [] { const char* e = getenv("VNECT_B200_CHAIN"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+
+// uploads the chained conv's weights ([n2][cout] K-major fp16) and bias, creates its output activation
+static int attach_chain(vnect_t* h, ConvSpec& s, const ConvOpts& o, int cout, int OH, int OW) {
+  const HostVar& w = h->vars.at(o.chain_scope + "/weights");
+  const HostVar& b = h->vars.at(o.chain_scope + "/biases");
+  __half* dw = nullptr;
+  float* db = nullptr;
+  int rc = upload(h, to_half(pack_conv(w, 1, cout, o.chain_cout, cout, o.chain_cout)), &dw);
+  if (rc) return rc;
+  if ((rc = upload(h, b.data, &db))) return rc;
+  if ((rc = new_act(h, o.chain_scope, OH, OW, o.chain_cout))) return rc;
+  s.w2 = dw;
+  s.bias2 = db;
+  s.n2 = o.chain_cout;
+  s.out2 = h->acts.at(o.chain_scope).p;
+  return VNECT_OK;
+}
+
+static bool can_chain(const ConvSpec& s, const ConvOpts& o, int cout) {
+  return chain_enabled() && !o.chain_scope.empty() && s.block_n == kTailBlockN && s.cg == 2 && cout % kTailBlockN == 0 &&
+         (o.chain_cout == 64 || o.chain_cout == 128 || o.chain_cout == 256);
+}
 
 // Output-channel tile.  Throughput plans (many forwards) use the widest tile; latency plans (a handful of forwards, e.g.
 // the drop-in estimator: one frame x n_scales) use 64-wide tiles so that 4x more CTAs share each layer's serial K loop.
@@ -341,8 +374,18 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
   static const bool bres_on = [] { const char* e = getenv("VNECT_B200_BRES"); return !(e && atoi(e) == 0); }();
   if (bres_on && cout == 64 && s.block_n == 64 && s.cg == 1 && s.epi == EPI_TMA && k * k * cin_pad / 64 <= kMaxResidentKBlocks)
     s.b_resident = 1;
+  // stride-1 3x3 convs on the larger grids read one halo patch per channel block instead of nine shifted boxes
+  // (conv_gemm.cuh HALO); VNECT_B200_HALO=0 turns it off (A/B measurement)
+  static const bool halo_on = [] { const char* e = getenv("VNECT_B200_HALO"); return !(e && atoi(e) == 0); }();
+  if (halo_on && k == 3 && o.in_stride == 1 && s.epi == EPI_TMA && halo_tiling_ok(OH, OW) &&
+      (s.block_n == 64 ? s.cg == 1 : (s.block_n == 128)))
+    s.halo = 1;
   Step st;
   st.kind = 0; st.name = scope;
+  if (k == 1 && can_chain(s, o, cout)) {
+    if ((rc = attach_chain(h, s, o, cout, OH, OW))) return rc;
+    st.name = scope + ">" + o.chain_scope;
+  }
   std::string err;
   if (!build_conv(s, h->num_sms, &st.launch, &err)) return fail(h, VNECT_E_CUDA, "%s: %s", scope.c_str(), err.c_str());
   h->steps.push_back(st);
@@ -353,7 +396,8 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
 //   relu(W_2c * b + bias_2c + W_1 * x + bias_1) == relu([W_2c | W_1] * [b ; x] + (bias_2c + bias_1))
 // one GEMM whose K runs over the 3x3's output and then over the block input; the branch1 tensor never exists.
 static int add_proj_tail(vnect_t* h, const std::string& scope2c, const std::string& scope1, const std::string& in_b,
-                         const std::string& in_x, const std::string& out, int mid, int cin, int cout) {
+                         const std::string& in_x, const std::string& out, int mid, int cin, int cout,
+                         const ConvOpts& o = ConvOpts()) {
   const Act& ab = h->acts.at(in_b);
   const Act& ax = h->acts.at(in_x);
   if (ab.H != ax.H || ab.W != ax.W || ab.C != mid || ax.C != cin)
@@ -384,6 +428,10 @@ static int add_proj_tail(vnect_t* h, const std::string& scope2c, const std::stri
   s.out = h->acts.at(out).p; s.ldc = cout; s.epi = EPI_TMA;
   Step st;
   st.kind = 0; st.name = scope2c + "+" + scope1;
+  if (can_chain(s, o, cout)) {
+    if ((rc = attach_chain(h, s, o, cout, ab.H, ab.W))) return rc;
+    st.name += ">" + o.chain_scope;
+  }
   std::string err;
   if (!build_conv(s, h->num_sms, &st.launch, &err)) return fail(h, VNECT_E_CUDA, "%s: %s", st.name.c_str(), err.c_str());
   h->steps.push_back(st);
@@ -394,21 +442,26 @@ static int add_proj_tail(vnect_t* h, const std::string& scope2c, const std::stri
 // :56).  even_only: the block's output feeds nothing but stride-2 1x1 convs (res2c -> res3a, res3d -> res4a), so
 // the 3x3, the last 1x1 and the residual add are evaluated at even pixels only -- same values, a quarter of the work.
 static int add_block(vnect_t* h, const std::string& pre, const std::string& in, int cin, int mid, int cout, bool proj,
-                     const std::string& suf, bool even_only, const std::string& a_override = "") {
+                     const std::string& suf, bool even_only, const std::string& a_override = "",
+                     const std::string& chain_scope = "", int chain_cout = 0) {
   int rc;
   ConvOpts relu;
   std::string a = a_override;
   if (a.empty()) {
     a = pre + "_branch2a" + suf;
-    rc = add_conv(h, a, 1, in, a, cin, mid, relu);
-    if (rc) return rc;
+    if (!h->acts.count(a)) {  // otherwise the previous block's fused tail has already computed it
+      rc = add_conv(h, a, 1, in, a, cin, mid, relu);
+      if (rc) return rc;
+    }
   }
   ConvOpts mid3; mid3.in_stride = even_only ? 2 : 1;
   rc = add_conv(h, pre + "_branch2b" + suf, 3, a, pre + "_branch2b" + suf, mid, mid, mid3);
   if (rc) return rc;
+  ConvOpts last; last.relu = true;
+  last.chain_scope = chain_scope; last.chain_cout = chain_cout;
   if (proj)
-    return add_proj_tail(h, pre + "_branch2c" + suf, pre + "_branch1" + suf, pre + "_branch2b" + suf, in, pre, mid, cin, cout);
-  ConvOpts last; last.relu = true; last.residual = in; last.res_stride = even_only ? 2 : 1;
+    return add_proj_tail(h, pre + "_branch2c" + suf, pre + "_branch1" + suf, pre + "_branch2b" + suf, in, pre, mid, cin, cout, last);
+  last.residual = in; last.res_stride = even_only ? 2 : 1;
   return add_conv(h, pre + "_branch2c" + suf, 1, pre + "_branch2b" + suf, pre, mid, cout, last);
 }
 
@@ -417,7 +470,7 @@ static void set_batch(ConvLaunch& L, int nb, int sms) {
   p.NB = nb;
   p.M = nb * p.H * p.W;
   p.num_m_tiles = p.mode == 0 ? (p.M + kBlockM - 1) / kBlockM : nb * p.tiles_x * p.tiles_y;
-  L.grid = conv_grid(p, L.cg, sms);
+  L.grid = L.n2 ? tail_grid(p, sms) : conv_grid(p, L.cg, sms);
 }
 
 // cv2 INTER_LINEAR coordinate rule on the host, identical arithmetic to cv_linear_coord (double -> float)
@@ -630,25 +683,32 @@ int vnect_finalize(vnect_t* h) {
       return fail(h, VNECT_E_CUDA, "conv1+pool1: %s", err.c_str());
     h->steps.push_back(st);
   }
-  if ((rc = add_block(h, "res2a", "pool1", 64, 64, 256, true, "", false))) return rc;
+  // each block's tail also computes the next block's 1x1 reduce conv (block_tail.cuh) where the plan allows
+  if ((rc = add_block(h, "res2a", "pool1", 64, 64, 256, true, "", false, "", "res2b_branch2a", 64))) return rc;
+  // res2b's output feeds no reduce conv: res2c's 3x3 reads res2b_branch2a (vnect_model.py:56), res2c_branch2a is dead
   if ((rc = add_block(h, "res2b", "res2a", 256, 64, 256, false, "", false))) return rc;
-  // res2c: the 3x3 reads res2b_branch2a (vnect_model.py:56); its output only feeds stride-2 1x1 convs -> even pixels only
-  if ((rc = add_block(h, "res2c", "res2b", 256, 64, 256, false, "", true, "res2b_branch2a"))) return rc;
-  if ((rc = add_block(h, "res3a", "res2c", 256, 128, 512, true, "", false))) return rc;
-  if ((rc = add_block(h, "res3b", "res3a", 512, 128, 512, false, "", false))) return rc;
-  if ((rc = add_block(h, "res3c", "res3b", 512, 128, 512, false, "", false))) return rc;
-  if ((rc = add_block(h, "res3d", "res3c", 512, 128, 512, false, "", true))) return rc;
-  if ((rc = add_block(h, "res4a", "res3d", 512, 256, 1024, true, "", false))) return rc;
+  // res2c: its output only feeds stride-2 1x1 convs -> even pixels only; the stride-2 reduce of res3a is then a plain
+  // 1x1 conv on the compact tensor and can ride on res2c's tail
+  if ((rc = add_block(h, "res2c", "res2b", 256, 64, 256, false, "", true, "res2b_branch2a", "res3a_branch2a", 128))) return rc;
+  if ((rc = add_block(h, "res3a", "res2c", 256, 128, 512, true, "", false, "", "res3b_branch2a", 128))) return rc;
+  if ((rc = add_block(h, "res3b", "res3a", 512, 128, 512, false, "", false, "", "res3c_branch2a", 128))) return rc;
+  if ((rc = add_block(h, "res3c", "res3b", 512, 128, 512, false, "", false, "", "res3d_branch2a", 128))) return rc;
+  if ((rc = add_block(h, "res3d", "res3c", 512, 128, 512, false, "", true, "", "res4a_branch2a", 256))) return rc;
+  if ((rc = add_block(h, "res4a", "res3d", 512, 256, 1024, true, "", false, "", "res4b_branch2a", 256))) return rc;
   {
+    const char* names[] = {"res4b", "res4c", "res4d", "res4e", "res4f"};
     std::string prev = "res4a";
-    for (const char* b : {"res4b", "res4c", "res4d", "res4e", "res4f"}) {
-      if ((rc = add_block(h, b, prev, 1024, 256, 1024, false, "", false))) return rc;
-      prev = b;
+    for (int i = 0; i < 5; ++i) {
+      // res4f feeds res5a_branch2a_new (512 channels: too wide for the second accumulator) -> not chained
+      const std::string next = i < 4 ? std::string(names[i + 1]) + "_branch2a" : std::string();
+      if ((rc = add_block(h, names[i], prev, 1024, 256, 1024, false, "", false, "", next, next.empty() ? 0 : 256))) return rc;
+      prev = names[i];
     }
   }
-  if ((rc = add_block(h, "res5a", "res4f", 1024, 512, 1024, true, "_new", false))) return rc;
+  if ((rc = add_block(h, "res5a", "res4f", 1024, 512, 1024, true, "_new", false, "", "res5b_branch2a_new", 256))) return rc;
   ConvOpts relu;
-  if ((rc = add_conv(h, "res5b_branch2a_new", 1, "res5a", "res5b_branch2a_new", 1024, 256, relu))) return rc;
+  if (!h->acts.count("res5b_branch2a_new") &&
+      (rc = add_conv(h, "res5b_branch2a_new", 1, "res5a", "res5b_branch2a_new", 1024, 256, relu))) return rc;
   if ((rc = add_conv(h, "res5b_branch2b_new", 3, "res5b_branch2a_new", "res5b_branch2b_new", 256, 128, relu))) return rc;
   if ((rc = add_conv(h, "res5b_branch2c_new", 1, "res5b_branch2b_new", "res5b_branch2c_new", 128, 256, relu))) return rc;
   {  // res5c head: two transposed convs + BN + ReLU + bone lengths + concat (vnect_model.py:188-209), one kernel
