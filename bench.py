@@ -36,9 +36,10 @@ BOX = 368
 SCALES = [1.0, 0.7]
 FRAMES_PER_GPU = 64
 FLOPS_PER_FORWARD = 23_830_290_432  # BASELINE.md section 3 (reference graph, every conv at full resolution)
-# res2c / res3d feed only stride-2 1x1 convs, so their 3x3 and last 1x1 are evaluated at even pixels only (identical
-# results): 3/4 of those four convs' MACs are not executed.  The roofline uses EXECUTED flops.
-SKIPPED_FLOPS = 2 * 3 * ((92 * 92 // 4) * (576 * 64 + 64 * 256) + (46 * 46 // 4) * (1152 * 128 + 128 * 512))
+# res2c / res3d feed only stride-2 1x1 convs, and res2b feeds only res2c's residual add (src/vnect_model.py:56 wires
+# res2c's 3x3 to res2b_branch2a), so the 3x3, last 1x1 and add of those three blocks are evaluated at even pixels only
+# (identical results): 3/4 of those six convs' MACs are not executed.  The roofline uses EXECUTED flops.
+SKIPPED_FLOPS = 2 * 3 * (2 * (92 * 92 // 4) * (576 * 64 + 64 * 256) + (46 * 46 // 4) * (1152 * 128 + 128 * 512))
 EXECUTED_FLOPS_PER_FORWARD = FLOPS_PER_FORWARD - SKIPPED_FLOPS
 METRIC = "frames/sec @368x368 2-scale"
 WORKLOAD = "C2: 64 synthetic 368x368 BGR frames per GPU per step, scales [1.0, 0.7] (128 CNN forwards), W0 seeded random-init weights, filters on"

@@ -23,6 +23,7 @@ extern "C" {
 #define VNECT_E_ZERO_DT (-4)      /* repeated timestamp for a stream: the reference raises ZeroDivisionError
                                      (src/OneEuroFilter.py:66) */
 #define VNECT_E_UNSUPPORTED (-5)
+#define VNECT_E_NUMERIC (-6)      /* NaN / Inf in the CNN output maps: fp16 activations overflowed (un-normalised weights?) */
 
 #define VNECT_JOINTS 21
 #define VNECT_MAX_SCALES 4
@@ -50,6 +51,10 @@ int vnect_create(vnect_t** out, const vnect_config* cfg);
  * "bn5c_branch2a/{gamma,beta,moving_mean,moving_variance}").  Host pointer, copied.  res2c_branch2a/* is accepted
  * and ignored (dead in the reference graph, src/vnect_model.py:54-56). */
 int vnect_set_weight(vnect_t* h, const char* tf_name, const float* data, const int64_t* shape, int32_t rank);
+
+/* weight-file helper: CRC32C (Castagnoli) of a host buffer -- the per-tensor / per-block checksum of the TensorFlow
+ * checkpoint the reference restores (src/estimator.py:55-60); used by vnect_b200/tf_checkpoint.py */
+uint32_t vnect_crc32c(const void* data, uint64_t n);
 
 /* folds batch norm, converts to fp16, packs for the tensor cores, builds the launch plan (what saver.restore +
  * graph import do in src/estimator.py:54-60) */
@@ -144,11 +149,21 @@ int vnect_get_tap(vnect_t* h, const char* name, int32_t n, float* out_nhwc, int6
  * (what utils.extract_2d_joints returns, src/utils.py:153-175, before joint_filter): int32 [n_frames][21][2].
  * Waits for that call to complete.  Parity tests use it to prove that an argmax difference is a near-tie. */
 int vnect_get_raw_argmax(vnect_t* h, int32_t n_frames, int32_t* raw_argmax);
+/* fp16 safety net.  Every estimate / submit / track call counts NaN / Inf values met in the CNN's output maps and the
+ * call that synchronises with that batch (vnect_wait, vnect_estimate, vnect_track, the next use of the lane) fails
+ * with VNECT_E_NUMERIC instead of returning joints computed from garbage.  vnect_check_finite then scans the
+ * activations of the last forward: counts[i] = values of launch i's output (first n forwards) that are NaN / Inf or
+ * saturated (|x| >= 65504); counts has one entry per launch (vnect_step_name order). */
+int vnect_check_finite(vnect_t* h, int32_t n, int64_t* counts);
 int64_t vnect_launch_count(vnect_t* h);      /* kernels launched by this handle so far */
 double vnect_info(vnect_t* h, const char* key); /* "flops_per_forward", "num_sms", "conv_launches_per_forward", ... */
 /* device time of `reps` back-to-back forwards of n images already in device memory (CUDA events on the handle's
  * stream); per_layer_ms may be NULL or float[conv_launches_per_forward + 1] (pool is the last entry) */
 int vnect_time_forward(vnect_t* h, int32_t n, int32_t reps, float* total_ms, float* per_layer_ms);
+/* device time (ms, CUDA events on the handle's stream) of the pre-processing kernels and of the post-process kernel for
+ * n_frames S x S frames: whatever the lane-0 frame buffer and the CNN output maps currently hold; the filter state
+ * of streams 0..n_frames-1 advances by one step per repetition */
+int vnect_time_prepost(vnect_t* h, int32_t n_frames, int32_t reps, float* pre_ms, float* post_ms);
 const char* vnect_step_name(vnect_t* h, int32_t i); /* name of launch i of one forward, NULL past the end */
 
 const char* vnect_last_error(vnect_t* h);

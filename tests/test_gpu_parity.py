@@ -113,7 +113,7 @@ def test_forward_layer_taps_and_maps_w1(engine_w1, oracle_net_w1):
     refs, taps = oracle_net_w1(x, want_taps=True)
     for name in LAYER_TAPS:
         got, ref = engine_w1.tap(name, 2), taps[name]
-        if name in ("res2c", "res3d"):
+        if name in ("res2b", "res2c", "res3d"):
             ref = ref[:, ::2, ::2, :]  # only the pixels the stride-2 consumers read are materialised
         if name == "res5c_branch2a_feat":
             assert np.all(got[..., 212:] == 0)
@@ -807,3 +807,38 @@ def test_two_devices_in_one_process(w0):
     finally:
         for e in engs:
             e.close()
+
+
+def test_fp16_range_guard(w0, oracle_net_w0):
+    """fp16 activations (max 65504).  The W0 network is positively homogeneous (zero biases, identity BN), so scaling
+    conv1 by s scales every activation by s: at s = 1e3 activations reach O(1e3..1e4) and the results still match the
+    fp32 oracle to the usual bound; at s = 1e6 they overflow and the call fails LOUDLY (FloatingPointError) instead of
+    returning joints computed from Inf / NaN maps; check_finite names the layers that saturated."""
+    from vnect_b200 import VNectEngine
+    x = prepost.gen_input_batch(synth.frame_c2(3), 368, [1.0])[0]
+    ref = oracle_net_w0(x)
+    big = dict(w0)
+    big["conv1/weights"] = w0["conv1/weights"] * np.float32(1e3)
+    eng = VNectEngine(big, [1.0], max_frames=1, max_streams=1)
+    try:
+        outs = eng.forward(x)
+        assert max(np.abs(eng.tap(n, 1)).max() for n in ("res2a", "res3a", "res4f", "res5a")) > 1e3
+        for got, want in zip(outs, ref):
+            assert rel_l2(got, want * 1e3) < 3e-3
+        assert sum(eng.check_finite(1).values()) == 0
+        j2, j3 = eng.estimate(synth.frame_c2(3), [0], [1.0], [1.1])
+        assert np.isfinite(j2).all() and np.isfinite(j3).all()
+    finally:
+        eng.close()
+    huge = dict(w0)
+    huge["conv1/weights"] = w0["conv1/weights"] * np.float32(1e6)
+    eng = VNectEngine(huge, [1.0], max_frames=1, max_streams=1)
+    try:
+        with pytest.raises(FloatingPointError, match="non-finite"):
+            eng.estimate(synth.frame_c2(3), [0], [1.0], [1.1])
+        bad = eng.check_finite(1)
+        assert bad["conv1+pool1"] > 0 and sum(v > 0 for v in bad.values()) > 10
+        with pytest.raises(FloatingPointError):        # every batch reports, not only the first
+            eng.estimate(synth.frame_c2(3), [0], [2.0], [2.1])
+    finally:
+        eng.close()

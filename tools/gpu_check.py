@@ -51,7 +51,7 @@ def main():
         for name in order:
             got = eng.tap(name, 2)
             ref = taps[name]
-            if name in ("res2c", "res3d"):
+            if name in ("res2b", "res2c", "res3d"):
                 ref = ref[:, ::2, ::2, :]
             if name == "res5c_branch2a_feat":
                 got = got[..., :212]
@@ -109,6 +109,9 @@ def main():
                     print(f"    {k:24s} {v*1e3:9.1f} us")
         frames = np.stack([synth.frame_c2(i) for i in range(64)])
         eng.reset()
+        eng.estimate(frames, np.arange(64), np.full(64, 4.0), np.full(64, 4.004))
+        pre_ms, post_ms = eng.time_prepost(64, reps=10)
+        print(f"pre-processing (pyramid) {pre_ms*1e3:.1f} us, post-process {post_ms*1e3:.1f} us per 64 two-scale frames")
         for it in range(3):
             t0 = time.time()
             eng.estimate(frames, np.arange(64), np.full(64, 5.0 + it), np.full(64, 5.004 + it))

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvnect_b200.so")
 
-OK, E_INVALID, E_CUDA, E_WEIGHT, E_ZERO_DT, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+OK, E_INVALID, E_CUDA, E_WEIGHT, E_ZERO_DT, E_UNSUPPORTED, E_NUMERIC = 0, -1, -2, -3, -4, -5, -6
 MAX_SCALES = 4
 STREAM_STATE_DOUBLES = 7 * 21 * 5 + 6
 
@@ -32,6 +32,7 @@ _P = C.c_void_p
 SIGNATURES = {
     "vnect_create": (C.c_int, [C.POINTER(_P), C.POINTER(Config)]),
     "vnect_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int32]),
+    "vnect_crc32c": (C.c_uint32, [_P, C.c_uint64]),
     "vnect_finalize": (C.c_int, [_P]),
     "vnect_forward": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P]),
     "vnect_estimate": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
@@ -52,9 +53,11 @@ SIGNATURES = {
     "vnect_set_packed_results": (C.c_int, [_P, _P]),
     "vnect_synchronize": (C.c_int, [_P]),
     "vnect_get_tap": (C.c_int, [_P, C.c_char_p, C.c_int32, _P, C.c_int64, C.POINTER(C.c_int32)]),
+    "vnect_check_finite": (C.c_int, [_P, C.c_int32, _P]),
     "vnect_launch_count": (C.c_int64, [_P]),
     "vnect_info": (C.c_double, [_P, C.c_char_p]),
     "vnect_time_forward": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float), _P]),
+    "vnect_time_prepost": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "vnect_step_name": (C.c_char_p, [_P, C.c_int32]),
     "vnect_last_error": (C.c_char_p, [_P]),
     "vnect_version": (C.c_char_p, []),
@@ -95,4 +98,6 @@ def raise_for(lib, handle, code):
         raise KeyError(msg)
     if code == E_UNSUPPORTED:
         raise NotImplementedError(msg)
+    if code == E_NUMERIC:
+        raise FloatingPointError(msg)
     raise RuntimeError(msg)

@@ -12,8 +12,14 @@
 //
 // One CTA pair (tcgen05 cta_group::2) owns 256 GEMM rows and walks ALL output-channel tiles of those rows (256 columns
 // each), so the second accumulator sees the whole K = Cout.  TMEM: columns [0, 256) main accumulator (single
-// buffered), [256, 256 + N2) second accumulator.  K order of the second GEMM is channel order, the same as the
-// stand-alone reduce conv, so both plans give bit-identical results.
+// buffered), [256, 512) second accumulator (two of them when N2 <= 128).  K order of the second GEMM is channel order,
+// the same as the stand-alone reduce conv, so both plans give bit-identical results.
+//
+// Scheduling (the first version serialised everything and ran 2x slower than the two kernels it replaces):
+//   * every epilogue warpgroup owns TWO staging tiles, so staging chunk c+2 never waits for the second GEMM on chunk c;
+//   * the MMA warp issues the second-GEMM work two chunks behind the main GEMM, across tile AND unit boundaries: the
+//     main accumulator is refilled as soon as it has been read, while the last two chunks are still being staged;
+//   * the second accumulator of a unit is drained after the epilogue has staged its first chunk of the NEXT unit.
 //
 // Warp roles (384 threads): 0 = TMA producer of the main GEMM (A rows + half of the W tile), 1 = MMA issuer (leader
 // CTA), 2 = TMEM allocator, then producer of the W2 tiles, 3 = residual prefetcher, 4-7 / 8-11 = two epilogue
@@ -24,7 +30,6 @@
 namespace vnect {
 
 constexpr int kTailBlockN = 256;
-constexpr int kTailW2Stages = 2;
 
 struct BlockTailParams {
   ConvGemmParams g;      // rows / tiling / main epilogue (mode, M, tiles, cblocks, cblocks2, bias, relu_cols, strides)
@@ -37,45 +42,20 @@ struct TailCfg {
   static constexpr int A_BYTES = kBlockM * 128;
   static constexpr int B_BYTES = (kTailBlockN / 2) * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int W2_STAGES = N2 == 256 ? 2 : 4;
   static constexpr int W2_BYTES = (N2 / 2) * 128;
-  static constexpr int OUT_BYTES = kEpiGroups * kEpiChunkBytes;
-  static constexpr int RES_BYTES = RES ? kResStages * kEpiChunkBytes : 0;
-  static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - OUT_BYTES - RES_BYTES - kTailW2Stages * W2_BYTES) / STAGE_BYTES;
+  static constexpr int OUT_BUFS = 2;                                   // staging tiles per epilogue group
+  static constexpr int OUT_BYTES = kEpiGroups * OUT_BUFS * kEpiChunkBytes;
+  static constexpr int RES_STAGES = RES ? (N2 == 256 ? 2 : 4) : 0;
+  static constexpr int RES_BYTES = RES_STAGES * kEpiChunkBytes;
+  static constexpr int ACC2_BUFS = N2 <= 128 ? 2 : 1;
+  static constexpr int STAGES_RAW = (kSmemBudget - 1024 - 512 - OUT_BYTES - RES_BYTES - W2_STAGES * W2_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + kTailW2Stages * W2_BYTES + OUT_BYTES + RES_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + W2_STAGES * W2_BYTES + OUT_BYTES + RES_BYTES + 1024 + 512;
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   static_assert(N2 == 64 || N2 == 128 || N2 == 256, "second GEMM width");
+  static_assert(kTailBlockN + ACC2_BUFS * N2 <= 512, "accumulators must fit TMEM");
 };
-
-// cluster-scope release / acquire for barriers that order one CTA's generic-proxy smem writes before tensor-core reads
-// triggered from the other CTA of the pair
-__device__ __forceinline__ void mbar_arrive_leader_release(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
-  while (!mbar_try_wait_cluster(bar, parity)) {
-    if (globaltimer_ns() - t0 > 4000000000ull) {
-      printf("vnect: mbarrier (cluster) wait timeout (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 template <int N2, bool RES>
 __global__ void __launch_bounds__(kGemmThreadsTma, 1)
@@ -89,6 +69,9 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   constexpr int BLOCK_K = 64;
   constexpr int CH = BLOCK_N / 64;   // main chunks per output-channel tile
   constexpr int CH2 = N2 / 64;       // chunks of the second accumulator
+  constexpr int W2S = Cfg::W2_STAGES;
+  constexpr int RS = Cfg::RES_STAGES > 0 ? Cfg::RES_STAGES : 1;
+  constexpr int A2 = Cfg::ACC2_BUFS;
   constexpr uint32_t IDESC = make_idesc_f16(2 * kBlockM, BLOCK_N, false);
   constexpr uint32_t IDESC2 = make_idesc_f16(2 * kBlockM, N2, false);
   const ConvGemmParams& p = bp.g;
@@ -98,22 +81,22 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w2_ring = smem + STAGES * Cfg::STAGE_BYTES;
-  uint8_t* out_stage = w2_ring + kTailW2Stages * Cfg::W2_BYTES;
+  uint8_t* out_stage = w2_ring + W2S * Cfg::W2_BYTES;      // [group][buffer] x 16 KB
   uint8_t* res_stage = out_stage + Cfg::OUT_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(res_stage + Cfg::RES_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = full_bar + STAGES;         // [STAGES]
   uint64_t* tmem_full = empty_bar + STAGES;        // main accumulator complete
-  uint64_t* tmem_empty = tmem_full + 1;            // main accumulator drained (8 epilogue warps x 2 CTAs)
-  uint64_t* acc2_full = tmem_empty + 1;
-  uint64_t* acc2_empty = acc2_full + 1;
-  uint64_t* res_full = acc2_empty + 1;             // [kResStages]
-  uint64_t* res_empty = res_full + kResStages;     // [kResStages]
-  uint64_t* w2_full = res_empty + kResStages;      // [kTailW2Stages]
-  uint64_t* w2_empty = w2_full + kTailW2Stages;    // [kTailW2Stages]
-  uint64_t* chunk_ready = w2_empty + kTailW2Stages;  // [2]: staging tile of group g holds a finished chunk of X (both CTAs)
-  uint64_t* chunk_free = chunk_ready + 2;            // [2]: the second GEMM has read it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_free + 2);
+  uint64_t* tmem_empty = tmem_full + 1;            // main accumulator read (8 epilogue warps x 2 CTAs)
+  uint64_t* acc2_full = tmem_empty + 1;            // [2]
+  uint64_t* acc2_empty = acc2_full + 2;            // [2]
+  uint64_t* res_full = acc2_empty + 2;             // [4]
+  uint64_t* res_empty = res_full + 4;              // [4]
+  uint64_t* w2_full = res_empty + 4;               // [4]
+  uint64_t* w2_empty = w2_full + 4;                // [4]
+  uint64_t* chunk_ready = w2_empty + 4;            // [group * 2 + buffer]: the staging tile holds a chunk of X (both CTAs)
+  uint64_t* chunk_free = chunk_ready + 4;          // [group * 2 + buffer]: the second GEMM has read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(chunk_free + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,19 +115,17 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 2 * 8);
-    mbar_init(acc2_full, 1);
-    mbar_init(acc2_empty, 2 * (CH2 >= 2 ? 8 : 4));
-    for (int s = 0; s < kResStages; ++s) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc2_full[s], 1);
+      mbar_init(&acc2_empty[s], 2 * (CH2 >= 2 ? 8 : 4));
+    }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&res_full[s], 1);
       mbar_init(&res_empty[s], 1);
-    }
-    for (int s = 0; s < kTailW2Stages; ++s) {
       mbar_init(&w2_full[s], 1);
       mbar_init(&w2_empty[s], 1);
-    }
-    for (int g = 0; g < 2; ++g) {
-      mbar_init(&chunk_ready[g], 2);  // one arrive per CTA of the pair
-      mbar_init(&chunk_free[g], 1);
+      mbar_init(&chunk_ready[s], 2);  // one arrive per CTA of the pair
+      mbar_init(&chunk_free[s], 1);
     }
     fence_barrier_init();
   }
@@ -159,6 +140,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int m_units = (p.num_m_tiles + 1) / 2;
   const int NT = p.num_n_tiles;
   const int k_iters = p.cblocks + p.cblocks2;
+  const int jobs_per_unit = CH * NT;
 
   auto tile_coords = [&](int unit, int* cx, int* cy, int* cn) {
     const int m_tile = unit * 2 + cta_rank;
@@ -214,37 +196,41 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t main_tiles = 0;       // main accumulator uses so far
-      uint32_t units_done = 0;       // second accumulator uses so far
+      uint32_t tiles = 0;   // main tiles issued so far
+      uint32_t jobs = 0;    // chunks fed to the second GEMM so far (global order: unit, tile, chunk)
       int ws = 0;
       uint32_t wphase = 0;
-      uint32_t chained[2] = {0, 0};  // chunks of group g fed to the second GEMM so far
-      const uint32_t d_main = tmem_base, d_acc2 = tmem_base + BLOCK_N;
-      // second GEMM on chunk j of the unit (j = nt * CH + c): A = staging tile of group j & 1, B = next W2 tile
-      auto chain = [&](int j) {
-        const int g = j & 1;
+      // second GEMM on global chunk `jobs`: A = staging tile (group, buffer) of that chunk, B = next W2 tile
+      auto chain_one = [&]() {
+        const uint32_t s = jobs;
+        const uint32_t cu = s / static_cast<uint32_t>(jobs_per_unit);         // unit (local count) of this chunk
+        const uint32_t j = s - cu * static_cast<uint32_t>(jobs_per_unit);     // K block of the second GEMM
+        const uint32_t g = s & 1u, m = s >> 1, b = m & 1u;                    // group, its main-chunk count, its buffer
+        const uint32_t a2 = cu % A2;
         mbar_wait(&w2_full[ws], wphase);
-        mbar_wait_cluster(&chunk_ready[g], chained[g] & 1u);
-        if (j == 0) mbar_wait(acc2_empty, (units_done & 1u) ^ 1u);
+        mbar_wait(&chunk_ready[g * 2 + b], (m >> 1) & 1u);
+        if (j == 0) mbar_wait(&acc2_empty[a2], ((cu / A2) & 1u) ^ 1u);
         tc_fence_after();
-        const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(out_stage + g * kEpiChunkBytes));
+        const uint32_t d_acc2 = tmem_base + BLOCK_N + a2 * N2;
+        const uint64_t a_desc = make_kmajor_desc<128>(smem_u32(out_stage + (g * 2 + b) * kEpiChunkBytes));
         const uint64_t b_desc = make_kmajor_desc<128>(smem_u32(w2_ring + ws * Cfg::W2_BYTES));
         if (issuer) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16_pair(d_acc2, a_desc + 2 * k, b_desc + 2 * k, IDESC2, (j | k) != 0 ? 1u : 0u);
           umma_commit_pair(&w2_empty[ws]);
-          umma_commit_pair(&chunk_free[g]);
+          umma_commit_pair(&chunk_free[g * 2 + b]);
+          if (j + 1 == static_cast<uint32_t>(jobs_per_unit)) umma_commit_pair(&acc2_full[a2]);
         }
         __syncwarp();
-        ++chained[g];
-        if (++ws == kTailW2Stages) {
+        ++jobs;
+        if (++ws == W2S) {
           ws = 0;
           wphase ^= 1;
         }
       };
       for (int it = worker; it < m_units; it += n_workers) {
         for (int nt = 0; nt < NT; ++nt) {
-          mbar_wait(tmem_empty, (main_tiles & 1u) ^ 1u);
+          mbar_wait(tmem_empty, (tiles & 1u) ^ 1u);
           tc_fence_after();
           for (int kb = 0; kb < k_iters; ++kb) {
             mbar_wait(&full_bar[stage], phase);
@@ -254,7 +240,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint64_t b_desc = make_kmajor_desc<128>(a_addr + Cfg::A_BYTES);
             if (issuer) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16_pair(d_main, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) umma_f16_pair(tmem_base, a_desc + 2 * k, b_desc + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
               umma_commit_pair(&empty_bar[stage]);
             }
             __syncwarp();
@@ -265,22 +251,12 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           if (issuer) umma_commit_pair(tmem_full);
           __syncwarp();
-          ++main_tiles;
-          // software pipeline: the last two chunks of the previous tile are chained AFTER this tile's main MMAs, so
-          // the main accumulator is refilled while the epilogue still works on them
-          if (nt > 0) {
-            chain((nt - 1) * CH + 2);
-            chain((nt - 1) * CH + 3);
-          }
-          chain(nt * CH + 0);
-          chain(nt * CH + 1);
+          ++tiles;
+          // the second GEMM runs two chunks behind: everything up to chunk 1 of the tile just issued
+          while (jobs + 2 < CH * tiles) chain_one();
         }
-        chain((NT - 1) * CH + 2);
-        chain((NT - 1) * CH + 3);
-        if (issuer) umma_commit_pair(acc2_full);
-        __syncwarp();
-        ++units_done;
       }
+      while (jobs < CH * tiles) chain_one();
     }
   } else if (warp == 2) {
     // ================================================================ W2 producer ([N2/2 rows of this CTA] x 64 K per chunk)
@@ -295,15 +271,15 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tma_load_2d_pair(w2_ring + ws * Cfg::W2_BYTES, &tmap_w2, &w2_full[ws], j * BLOCK_K, cta_rank * (N2 / 2));
         }
         __syncwarp();
-        if (++ws == kTailW2Stages) {
+        if (++ws == W2S) {
           ws = 0;
           wphase ^= 1;
         }
       }
     }
-    for (int s2 = 0; s2 < kTailW2Stages; ++s2) {  // drain
+    for (int s2 = 0; s2 < W2S; ++s2) {  // drain
       mbar_wait(&w2_empty[ws], wphase ^ 1);
-      if (++ws == kTailW2Stages) {
+      if (++ws == W2S) {
         ws = 0;
         wphase ^= 1;
       }
@@ -319,8 +295,8 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tile_coords(unit, &cx, &cy, &cn);
         for (int nt = 0; nt < NT; ++nt)
           for (int c0 = 0; c0 < BLOCK_N; c0 += 64, ++ctr) {
-            const int rb = ctr % kResStages;
-            mbar_wait(&res_empty[rb], ((ctr / kResStages) & 1) ^ 1);
+            const int rb = ctr % RS;
+            mbar_wait(&res_empty[rb], ((ctr / RS) & 1) ^ 1);
             if (issuer) {
               mbar_arrive_expect_tx(&res_full[rb], p.res_tx_bytes);
               tma_load_5d(res_stage + rb * kEpiChunkBytes, &tmap_res, &res_full[rb], nt * BLOCK_N + c0,
@@ -338,14 +314,17 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const bool leader = (threadIdx.x == 128 + grp * 128);
     const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
     const uint32_t sw = static_cast<uint32_t>(r & 7);
-    uint8_t* ostage = out_stage + grp * kEpiChunkBytes;
+    uint8_t* my_stage = out_stage + grp * Cfg::OUT_BUFS * kEpiChunkBytes;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t main_tiles = 0, units_done = 0, res_ctr = 0;
-    uint32_t fed = 0;           // chunks of this group handed to the second GEMM so far
-    bool free_pending = false;  // the staging tile's last content was handed to the second GEMM: wait before rewriting
+    uint32_t tiles = 0, res_ctr = 0;
+    uint32_t m = 0;                       // main chunks staged by this group so far; chunk m uses buffer m & 1
+    uint32_t m_last[2] = {0, 0};          // last main chunk staged into each buffer ...
+    bool chained_pending[2] = {false, false};  // ... and whether its second-GEMM read has been waited for
+    uint32_t store_seq = 0, last_store[2] = {0, 0};
+    bool stored[2] = {false, false};
 
-    // fp32 x 64 (+ bias, + residual) -> relu? -> fp16 into the swizzled staging tile
-    auto stage_chunk = [&](const uint32_t (&v)[64], const float* bias, bool relu, const uint8_t* rstage) {
+    // fp32 x 64 (+ bias, + residual) -> relu? -> fp16 into a swizzled staging tile
+    auto stage_chunk = [&](uint8_t* ostage, const uint32_t (&v)[64], const float* bias, bool relu, const uint8_t* rstage) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float f[8];
@@ -379,22 +358,60 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         *reinterpret_cast<uint4*>(ostage + off) = o;
       }
     };
-    // the staging tile may be rewritten once its TMA store has read it and (if it was chained) the second GEMM has
-    auto wait_stage_free = [&]() {
-      if (free_pending) {
-        mbar_wait(&chunk_free[grp], (fed - 1) & 1u);
-        free_pending = false;
+    // buffer b may be rewritten once the second GEMM has read its last chained content and its last TMA store has
+    // read it (the store of the OTHER buffer may still be in flight)
+    auto acquire = [&](int b) {
+      if (chained_pending[b]) {
+        mbar_wait(&chunk_free[grp * 2 + b], (m_last[b] >> 1) & 1u);
+        chained_pending[b] = false;
       }
-      if (leader) bulk_wait_group_read<0>();
+      if (leader && stored[b]) {
+        if (store_seq - last_store[b] <= 1) bulk_wait_group_read<0>();
+        else bulk_wait_group_read<1>();
+      }
       named_bar_sync(1 + grp, 128);
     };
+    // second accumulator of local unit `du` -> Y (bias2, ReLU), through the staging tile the next main chunk will use
+    auto drain_acc2 = [&](uint32_t du, int cx, int cy, int cn) {
+      if (grp >= CH2) return;
+      const uint32_t a2 = du % A2;
+      mbar_wait(&acc2_full[a2], (du / A2) & 1u);
+      tc_fence_after();
+      const int b = m & 1u;
+      uint8_t* ostage = my_stage + b * kEpiChunkBytes;
+#pragma unroll 1
+      for (int e = grp; e < CH2; e += 2) {
+        uint32_t v[64];
+        tmem_ld_32x32(t_lane + BLOCK_N + a2 * N2 + e * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_32x32(t_lane + BLOCK_N + a2 * N2 + e * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tmem_ld_wait();
+        if (e + 2 >= CH2) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&acc2_empty[a2]);
+        }
+        acquire(b);
+        stage_chunk(ostage, v, bp.bias2 + e * 64, true, nullptr);
+        fence_proxy_async_smem();
+        named_bar_sync(1 + grp, 128);
+        if (leader) {
+          tma_store_5d(&tmap_out2, ostage, e * 64, cx, cy, 0, cn);
+          bulk_commit_group();
+        }
+        last_store[b] = ++store_seq;
+        stored[b] = true;
+      }
+    };
 
+    bool drain_due = false;
+    uint32_t drain_unit = 0, units = 0;
+    int dcx = 0, dcy = 0, dcn = 0;
     for (int it = worker; it < m_units; it += n_workers) {
       const int unit = p.reverse ? m_units - 1 - it : it;
       int cx, cy, cn;
       tile_coords(unit, &cx, &cy, &cn);
       for (int nt = 0; nt < NT; ++nt) {
-        mbar_wait(tmem_full, main_tiles & 1u);
+        mbar_wait(tmem_full, tiles & 1u);
         tc_fence_after();
 #pragma unroll 1
         for (int c = grp; c < CH; c += 2) {
@@ -413,53 +430,40 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           uint32_t rb = 0;
           if constexpr (RES) {
             const uint32_t ctr = res_ctr + static_cast<uint32_t>(c);
-            rb = ctr % kResStages;
-            mbar_wait(&res_full[rb], (ctr / kResStages) & 1);
+            rb = ctr % RS;
+            mbar_wait(&res_full[rb], (ctr / RS) & 1);
             rstage = res_stage + rb * kEpiChunkBytes;
           }
-          wait_stage_free();
-          stage_chunk(v, p.bias != nullptr ? p.bias + col0 : nullptr, col0 < p.relu_cols, rstage);
-          fence_proxy_async_all();  // generic-proxy smem writes -> visible to the TMA store and to the tensor cores
+          const int b = m & 1u;
+          uint8_t* ostage = my_stage + b * kEpiChunkBytes;
+          acquire(b);
+          stage_chunk(ostage, v, p.bias != nullptr ? p.bias + col0 : nullptr, col0 < p.relu_cols, rstage);
+          fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store and to the tensor cores
           named_bar_sync(1 + grp, 128);
           if (leader) {
             tma_store_5d(&tmap_out, ostage, col0, cx, cy, 0, cn);
             bulk_commit_group();
             if constexpr (RES) mbar_arrive(&res_empty[rb]);
-            mbar_arrive_leader_release(&chunk_ready[grp]);  // this CTA's half of the chunk is in place
+            mbar_arrive_leader(&chunk_ready[grp * 2 + b]);  // this CTA's half of the chunk is in place
           }
-          ++fed;
-          free_pending = true;
+          last_store[b] = ++store_seq;
+          stored[b] = true;
+          m_last[b] = m;
+          chained_pending[b] = true;
+          ++m;
+          if (drain_due) {  // the previous unit's second accumulator, now that this unit is under way
+            drain_acc2(drain_unit, dcx, dcy, dcn);
+            drain_due = false;
+          }
         }
         res_ctr += CH;
-        ++main_tiles;
+        ++tiles;
       }
-      // ---- second accumulator -> Y (bias2, ReLU), written through the same staging tile
-      if (grp < CH2) {
-        mbar_wait(acc2_full, units_done & 1u);
-        tc_fence_after();
-#pragma unroll 1
-        for (int e = grp; e < CH2; e += 2) {
-          uint32_t v[64];
-          tmem_ld_32x32(t_lane + BLOCK_N + e * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld_32x32(t_lane + BLOCK_N + e * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-          tmem_ld_wait();
-          if (e + 2 >= CH2) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(acc2_empty);
-          }
-          wait_stage_free();
-          stage_chunk(v, bp.bias2 + e * 64, true, nullptr);
-          fence_proxy_async_all();
-          named_bar_sync(1 + grp, 128);
-          if (leader) {
-            tma_store_5d(&tmap_out2, ostage, e * 64, cx, cy, 0, cn);
-            bulk_commit_group();
-          }
-        }
-      }
-      ++units_done;
+      drain_due = true;
+      drain_unit = units++;
+      dcx = cx; dcy = cy; dcn = cn;
     }
+    if (drain_due) drain_acc2(drain_unit, dcx, dcy, dcn);
     if (leader) bulk_wait_group<0>();
   }
 

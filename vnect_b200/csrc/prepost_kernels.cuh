@@ -349,9 +349,10 @@ struct PostParams {
   double* out2d;                  // [n_frames][21][2]
   float* out3d;                   // [n_frames][21][3]
   double* packed;                 // optional [n_frames][21][5] = (row, col, x, y, z): the layout the multi-GPU gather moves
+  unsigned int* nonfinite;        // counts (frame, joint) blocks that met a NaN / Inf in the CNN's maps (fp16 overflow guard)
 };
 
-constexpr int kPostThreads = 128;
+constexpr int kPostThreadsDefault = 256;  // threads per (frame, joint) block; 128 / 256 / 512 are instantiated
 
 // 1/s-resized (float32, cv2 arithmetic: separate mul/add) + cropped value of raw planar map `m` at cell (y, x).
 __device__ __forceinline__ float scaled_cell(const float* __restrict__ m, int hs, const ScaleTable& T, int y, int x) {
@@ -379,6 +380,7 @@ __device__ __forceinline__ void upsample_candidate(int k, int hs, int* d, int* i
 
 // grid = n_frames * 21 blocks of 128 threads; block (frame, joint).  The last block of a frame to finish runs the
 // per-frame tail (root subtraction, 3D filters, 2D rescale).
+template <int kPostThreads>
 __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p) {
   extern __shared__ double s_avg[];  // [hs][hs] averaged heat-map of this joint
   __shared__ short s_cd[2 * kMaxHm], s_ci[2 * kMaxHm];
@@ -421,6 +423,7 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
   __syncthreads();
   double cell_best = -INFINITY, cell_amax = 0.0;
   int cell_best_idx = 0;
+  int nonfinite = 0;
   for (int y = warp_id; y < hs; y += kPostThreads / 32) {
     for (int x = lane_id; x < hs; x += 32) {
       double acc = 0.0;
@@ -447,6 +450,7 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
       s_avg[y * hs + x] = a;
       if (a > cell_best) { cell_best = a; cell_best_idx = y * hs + x; }
       cell_amax = fmax(cell_amax, fabs(a));
+      nonfinite |= !(fabs(a) <= 1.7976931348623157e308);  // NaN or Inf (fmax above would silently drop a NaN)
     }
   }
   // block-wide largest cell: its neighbourhood gives a lower bound L0 on the upsampled maximum, which prunes almost
@@ -460,7 +464,9 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
     cell_amax = fmax(cell_amax, __shfl_xor_sync(0xffffffffu, cell_amax, o));
   }
   if (lane_id == 0) { s_val[warp_id] = cell_best; s_idx[warp_id] = cell_best_idx; s_amax[warp_id] = cell_amax; }
-  __syncthreads();
+  // fp16 activations overflow at 65504: an Inf / NaN anywhere in the CNN almost surely reaches the maps.  Count it (the
+  // host turns a non-zero count into an error) instead of returning joints computed from garbage.
+  if (__syncthreads_or(nonfinite) && tid == 0 && p.nonfinite != nullptr) atomicAdd(p.nonfinite, 1u);
   {
     cell_best = s_val[0]; cell_best_idx = s_idx[0]; cell_amax = s_amax[0];
 #pragma unroll
@@ -565,7 +571,9 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
       const int map = tid / (4 * p.n_scales);
       const size_t plane = (size_t)hs * hs;
       const float* m = p.maps + ((size_t)(frame * p.n_scales + sc) * 84 + kJoints * (1 + map) + joint) * plane;
-      s_gather[tid] = scaled_cell(m, hs, p.tables[sc], (cell & 2) ? y1 : y0, (cell & 1) ? x1 : x0);
+      const float gv = scaled_cell(m, hs, p.tables[sc], (cell & 2) ? y1 : y0, (cell & 1) ? x1 : x0);
+      s_gather[tid] = gv;
+      if (!(fabsf(gv) <= 3.4028234e38f) && p.nonfinite != nullptr) atomicAdd(p.nonfinite, 1u);
     }
     __syncthreads();
     if (tid < 3) {
@@ -653,6 +661,17 @@ __global__ void track_update_kernel(const double* __restrict__ joints2d, const i
     const int h = (int)fmin(__dadd_rn(__dsub_rn(ymax, ymin), buffer_y), (double)(FH - y));
     boxes[stream_ids[frame]] = make_int4(x, y, w, h);
   }
+}
+
+// Debug scan (vnect_check_finite): values of an fp16 activation tensor that are NaN / Inf or saturated (|x| >= 65504).
+__global__ void count_nonfinite_kernel(const __half* __restrict__ x, size_t n, unsigned long long* __restrict__ out) {
+  unsigned long long c = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = __half2float(x[i]);
+    c += !(fabsf(v) < 65504.f);
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // VNectEstimator.joint_filter (estimator.py:83-95) on explicit values: 21*dim scalar filters of one stream.

@@ -245,6 +245,14 @@ class VNectEngine:
         self._check(self._lib.vnect_get_tap(self._h, name.encode(), n, _ptr(out), out.size, dims))
         return out
 
+    def check_finite(self, n=1):
+        """{launch name: count of NaN / Inf / saturated fp16 values in its output} for the first n forwards of the last
+        batch -- names the layer where un-normalised weights overflow fp16 (65504)."""
+        names = self.step_names()
+        counts = np.zeros(len(names), np.int64)
+        self._check(self._lib.vnect_check_finite(self._h, int(n), _ptr(counts)))
+        return dict(zip(names, counts.tolist()))
+
     def reset(self, stream_id=-1):
         self._check(self._lib.vnect_reset_stream(self._h, int(stream_id)))
 
@@ -280,6 +288,13 @@ class VNectEngine:
         per = np.zeros(len(names), np.float32) if per_layer else None
         self._check(self._lib.vnect_time_forward(self._h, n, reps, C.byref(total), _ptr(per) if per_layer else None))
         return (total.value, dict(zip(names, per.tolist()))) if per_layer else total.value
+
+
+    def time_prepost(self, n_frames, reps=10):
+        """Device time (ms) of the pre-processing kernels and of the post-process kernel for n_frames box-size frames."""
+        pre, post = C.c_float(), C.c_float()
+        self._check(self._lib.vnect_time_prepost(self._h, int(n_frames), int(reps), C.byref(pre), C.byref(post)))
+        return pre.value, post.value
 
 
 class VNectEstimator:

@@ -11,6 +11,7 @@ import pickle
 import numpy as np
 
 DEFAULT_PICKLES = ("./models/caffe_model/params.pkl", "../models/caffe_model/params.pkl")  # init_weights.py:35-36
+DEFAULT_CHECKPOINT_DIRS = ("./models/tf_model/", "../models/tf_model/")  # src/estimator.py:55-60
 
 
 def _conv_scopes():
@@ -85,14 +86,68 @@ def load_pickle(path):
     return {k: np.asarray(v, dtype=np.float32) for k, v in d.items()}
 
 
+def load_npz(path):
+    """A numpy archive {name: ndarray} (np.savez of the params dict)."""
+    with np.load(path, allow_pickle=False) as z:
+        return {k: np.asarray(z[k], dtype=np.float32) for k in z.files}
+
+
+def load_tf_checkpoint(path):
+    """The TensorFlow-1.x checkpoint the reference restores (src/estimator.py:55-60): ``path`` is the directory holding
+    the ``checkpoint`` state file, or a checkpoint prefix such as ./models/tf_model/vnect_tf."""
+    from . import tf_checkpoint
+    prefix = path
+    if os.path.isdir(path):
+        prefix = tf_checkpoint.latest_checkpoint(path)
+        if prefix is None:
+            raise FileNotFoundError("no 'checkpoint' state file in %s" % path)
+    for suffix in (".index", ".meta"):
+        if prefix.endswith(suffix):
+            prefix = prefix[:-len(suffix)]
+    return tf_checkpoint.read_checkpoint(prefix)
+
+
+def save(path, wdict):
+    """Write a weight dict in the format the suffix names: .pkl (the reference's params.pkl), .npz, or a TensorFlow
+    checkpoint prefix (anything else)."""
+    if path.endswith(".pkl"):
+        with open(path, "wb") as f:
+            pickle.dump({k: np.asarray(v) for k, v in wdict.items()}, f)
+    elif path.endswith(".npz"):
+        np.savez(path, **wdict)
+    else:
+        from . import tf_checkpoint
+        tf_checkpoint.write_checkpoint(path, wdict)
+
+
+def check_complete(wdict):
+    """All 109 variables of the reference graph with their shapes (incl. the dead res2c_branch2a/*, which the
+    checkpoint holds and the graph ignores); extra keys (saver bookkeeping) are dropped."""
+    out = {}
+    for name, shp in variable_shapes().items():
+        if name not in wdict:
+            raise KeyError("weights lack variable '%s'" % name)
+        arr = np.asarray(wdict[name], dtype=np.float32)
+        if tuple(arr.shape) != tuple(shp):
+            raise KeyError("variable '%s' has shape %s, expected %s" % (name, tuple(arr.shape), tuple(shp)))
+        out[name] = arr
+    return out
+
+
 def resolve(spec=None):
-    """spec: dict | path to params.pkl | 'random:W0[:seed]' | None (env VNECT_B200_WEIGHTS, then the reference's
-    default pickle locations).  Raises FileNotFoundError when nothing is found, like the reference does when its
-    checkpoint is absent (src/estimator.py:55-60)."""
+    """spec: dict | params.pkl | .npz | TensorFlow checkpoint (directory or prefix) | 'random:W0[:seed]' | None (env
+    VNECT_B200_WEIGHTS, then the reference's default locations: the TF checkpoint of src/estimator.py:55-60, then the
+    pickle of init_weights.py:35-36).  Raises FileNotFoundError when nothing is found, like the reference does when its
+    checkpoint is absent."""
     if isinstance(spec, dict):
         return spec
     if spec is None:
         spec = os.environ.get("VNECT_B200_WEIGHTS")
+    if spec is None:
+        for d in DEFAULT_CHECKPOINT_DIRS:
+            if os.path.isfile(os.path.join(d, "checkpoint")):
+                spec = d
+                break
     if spec is None:
         for p in DEFAULT_PICKLES:
             if os.path.isfile(p):
@@ -100,9 +155,16 @@ def resolve(spec=None):
                 break
     if spec is None:
         raise FileNotFoundError(
-            "no VNect weights: pass weights=<dict | params.pkl path | 'random:W0'> or set VNECT_B200_WEIGHTS "
-            "(the reference's trained weights are not distributed; see models/caffe_model/README.md there)")
-    if str(spec).startswith("random:"):
-        parts = str(spec).split(":")
+            "no VNect weights: pass weights=<dict | params.pkl | .npz | TF checkpoint | 'random:W0'> or set "
+            "VNECT_B200_WEIGHTS (the reference's trained weights are not distributed; see models/*/README.md there)")
+    spec = str(spec)
+    if spec.startswith("random:"):
+        parts = spec.split(":")
         return seeded_init(parts[1], int(parts[2]) if len(parts) > 2 else 0)
+    if spec.endswith(".npz"):
+        return load_npz(spec)
+    if spec.endswith(".pkl"):
+        return load_pickle(spec)
+    if os.path.isdir(spec) or os.path.isfile(spec + ".index") or spec.endswith((".index", ".meta")):
+        return load_tf_checkpoint(spec)
     return load_pickle(spec)
