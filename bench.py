@@ -136,7 +136,7 @@ def cpu_reference_arm(n_frames, threads=None):
     return n_frames / dt, threads
 
 
-def run_reference(args):
+def run_reference(args, out=sys.stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -160,7 +160,7 @@ def run_reference(args):
                          "sample": "%d two-scale 368x368 frames per step, oracle estimator (torch-CPU fp32 CNN + cv2/numpy pre/post)" % n},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 def run_c4(eng, parallel, dev, stream, rank, world, local, barrier):
@@ -244,7 +244,18 @@ def run_c4(eng, parallel, dev, stream, rank, world, local, barrier):
     return out
 
 
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but NCCL (and anything else in C) writes its log to file descriptor 1
+    unless NCCL_DEBUG_FILE says otherwise.  Point fd 1 at stderr for the whole run and keep the real stdout for the
+    result line: nothing is muted, it just lands on stderr."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -255,7 +266,7 @@ def main():
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 strong-scaling leg (256 streams x 32 steps)")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out)
 
     import torch
     import torch.distributed as dist
@@ -273,9 +284,11 @@ def main():
     if world > 1:
         # stdout carries exactly one JSON line; NCCL's own log (version, "nranks N" of the communicator) goes to
         # stderr instead of being muted, so the rank count of the gather can be read from the run's log
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # (whatever the launcher set wins; the image's default level VERSION is raised to INFO so that the communicator's
+        # "nranks" line exists in the log, wherever NCCL_DEBUG_FILE points)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
     nf = args.frames
     n_streams = nf * world
@@ -487,7 +500,7 @@ def main():
             "latency_ms_p50_batch1": statistics.median(lat) if lat else None,
             "latency_ms_p95_batch1": lat[int(0.95 * (len(lat) - 1))] if lat else None,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -122,6 +122,13 @@ int vnect_postprocess(vnect_t* h, const float* hm, const float* xm, const float*
  * detected before the stream's state is touched.  The same checks guard vnect_estimate / vnect_submit / vnect_track. */
 int vnect_filter(vnect_t* h, int32_t stream_id, int32_t dim, int32_t values_are_f32, double t, double* values);
 
+/* replaces Joints2Angles.__call__ / joints2angles (src/joints2angles.py:44-110): the eight arm angles (radians:
+ * s0_l, s1_l, e0_l, e1_l, s0_r, s1_r, e0_r, e1_r) of n frames from their 3D joints (host float32 [n][21][3], as
+ * returned by vnect_estimate), smoothed per stream by the eight OneEuroFilters of joints2angles.py:35-42 when t
+ * (host float64 [n] clock readings) is not NULL.  angles: host float64 [n][8]. */
+int vnect_joints2angles(vnect_t* h, const float* joints3d, int32_t n, const int32_t* stream_ids, const double* t,
+                        double* angles);
+
 /* forget the temporal-filter state of one stream (a new VNectEstimator() in the reference); -1 = all streams */
 int vnect_reset_stream(vnect_t* h, int32_t stream_id);
 

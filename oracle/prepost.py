@@ -367,3 +367,41 @@ class OracleTracker:
         j2[:, 1] += x
         self.rect = tracker_update(j2, w_img, h_img)
         return j2, j3, used
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# joints2angles.py:60-110, restated (numpy called exactly where the reference calls it, so the float32 / float64 mix of
+# the intermediate results is the reference's own)
+def _cal_angle(v1, v2):
+    return np.arccos(np.dot(v1, v2) / (np.linalg.norm(v1) * np.linalg.norm(v2)))
+
+
+def joints2angles(joints_3d):
+    """Eight arm angles (radians): s0_l, s1_l, e0_l, e1_l, s0_r, s1_r, e0_r, e1_r."""
+    s2e_l, e2w_l = joints_3d[6] - joints_3d[5], joints_3d[7] - joints_3d[6]
+    s2e_r, e2w_r = joints_3d[3] - joints_3d[2], joints_3d[4] - joints_3d[3]
+    v1_l = joints_3d[2] - joints_3d[5]
+    v1_r = -v1_l
+    v2 = [0, 1, 0]
+    v3_l, v3_r = np.cross(s2e_l, v2), np.cross(s2e_r, v2)
+    v4_l, v4_r = np.cross(s2e_l, e2w_l), np.cross(s2e_r, e2w_r)
+    s0_l = np.pi * 3 / 4 - _cal_angle(v1_l, v3_l)
+    s1_l = np.pi / 2 - _cal_angle(v2, s2e_l)
+    e0_l = -_cal_angle(v3_l, v4_l)
+    e1_l = _cal_angle(s2e_l, e2w_l)
+    s0_r = np.pi / 4 - _cal_angle(v1_r, v3_r)
+    s1_r = np.pi / 2 - _cal_angle(v2, s2e_r)
+    e0_r = _cal_angle(v3_r, v4_r)
+    e1_r = _cal_angle(s2e_r, e2w_r)
+    return s0_l - np.pi / 4, s1_l, e0_l, -e1_l, s0_r + np.pi / 4, -s1_r, e0_r, e1_r
+
+
+class OracleJoints2Angles:
+    """Joints2Angles.__call__ (joints2angles.py:44-57): the eight angles through eight OneEuroFilters (120 Hz, 0.5, 0.5, 1)."""
+
+    def __init__(self, clock=time.time):
+        self.clock = clock
+        self.filters = [OneEuroFilter(freq=120, mincutoff=0.5, beta=0.5, dcutoff=1.0) for _ in range(8)]
+
+    def __call__(self, joints_3d):
+        return [self.filters[i](a, self.clock()) for i, a in enumerate(joints2angles(joints_3d))]

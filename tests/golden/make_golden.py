@@ -22,7 +22,10 @@ Fixtures (all small):
               vectors for SURVEY.md T5 -- the scripts are executed unchanged against the drop-in on the GPU box, which
               has no reference tree.  Not product code; nothing under vnect_b200/ reads it.
 
-`python tests/golden/make_golden.py filter_joint video ref_scripts` regenerates only the named fixtures.
+  angles.npz  src/joints2angles.py run unchanged: the static joints2angles() on seeded 3D joints and the filtered
+              Joints2Angles.__call__ over a joint trajectory with scripted clock readings
+
+`python tests/golden/make_golden.py filter_joint video ref_scripts angles` regenerates only the named fixtures.
 """
 import hashlib
 import os
@@ -170,6 +173,42 @@ def make_ref_scripts():
     np.savez_compressed(os.path.join(OUT, "ref_scripts.npz"), **out)
 
 
+ANGLE_FRAMES = 40
+
+
+def angle_inputs():
+    """Seeded 3D joints (float32 mm, root-relative like the estimator's output) and clock readings: a random pose per
+    frame for the static function, plus a smooth trajectory for the filtered call."""
+    rng = np.random.default_rng(77)
+    poses = rng.uniform(-600, 600, (ANGLE_FRAMES, 21, 3)).astype(np.float32)
+    start = rng.uniform(-500, 500, (21, 3))
+    traj = (start[None] + np.cumsum(rng.standard_normal((ANGLE_FRAMES, 21, 3)) * 6, axis=0)).astype(np.float32)
+    t = 3000 + np.cumsum(rng.uniform(0.006, 0.05, ANGLE_FRAMES))
+    return poses, traj, t
+
+
+def make_angles():
+    import contextlib
+    import importlib
+    import io
+    ref_shim.load_reference_modules()
+    j2a = importlib.import_module("joints2angles")
+    poses, traj, t = angle_inputs()
+    static = np.array([[float(a) for a in j2a.Joints2Angles.joints2angles(p)] for p in poses])
+    with contextlib.redirect_stdout(io.StringIO()):
+        obj = j2a.Joints2Angles()
+        real = j2a.time
+        filtered = []
+        try:
+            for k in range(ANGLE_FRAMES):
+                j2a.time = ref_shim.ScriptedClock([float(t[k])] * 8)   # one time.time() per angle (joints2angles.py:49)
+                filtered.append([float(a) for a in obj(traj[k])])
+        finally:
+            j2a.time = real
+    np.savez_compressed(os.path.join(OUT, "angles.npz"), poses=poses, traj=traj, t=t, static=static,
+                        filtered=np.array(filtered), versions=str(VERSIONS))
+
+
 def main():
     assert ref_shim.reference_available(), "run in the dev container (needs /root/reference)"
     utils, oef, est_mod = ref_shim.load_reference_modules()
@@ -181,10 +220,13 @@ def main():
             make_video()
         if "ref_scripts" in only:
             make_ref_scripts()
+        if "angles" in only:
+            make_angles()
         return
     make_filter_joint(est_mod)
     make_video()
     make_ref_scripts()
+    make_angles()
 
     # ---- pre.npz
     pre = dict(versions=str(VERSIONS))

@@ -255,3 +255,14 @@ def test_area2x_partial_blocks_match_cv2():
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         ref = cv2.resize(img, (0, 0), fx=0.5, fy=0.5, interpolation=cv2.INTER_LINEAR)
         assert np.array_equal(prepost.area2x_u8(img), ref), (h, w)
+
+
+def test_joints2angles_golden(golden):
+    """tests/golden/angles.npz (src/joints2angles.py run unchanged): static angles bit for bit, filtered ones too."""
+    g = golden("angles.npz")
+    for p, want in zip(g["poses"], g["static"]):
+        assert np.array_equal(np.array([float(a) for a in prepost.joints2angles(p)]), want)
+    ts = iter(np.repeat(g["t"], 8))
+    obj = prepost.OracleJoints2Angles(clock=lambda: float(next(ts)))
+    for frame, want in zip(g["traj"], g["filtered"]):
+        assert np.array_equal(np.array([float(a) for a in obj(frame)]), want)

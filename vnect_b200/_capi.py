@@ -48,6 +48,7 @@ SIGNATURES = {
     "vnect_export_stream_state": (C.c_int, [_P, C.c_int32, _P]),
     "vnect_import_stream_state": (C.c_int, [_P, C.c_int32, _P]),
     "vnect_get_raw_argmax": (C.c_int, [_P, C.c_int32, _P]),
+    "vnect_joints2angles": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "vnect_reset_stream": (C.c_int, [_P, C.c_int32]),
     "vnect_set_stream": (C.c_int, [_P, _P]),
     "vnect_set_packed_results": (C.c_int, [_P, _P]),

@@ -663,6 +663,87 @@ __global__ void track_update_kernel(const double* __restrict__ joints2d, const i
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Joints2Angles (reference: src/joints2angles.py:60-110): eight arm angles of a robot from the 3D joints -- the step
+// right after the hot path for the robot use case.  One thread per frame.  The reference
+// mixes float32 (joint differences, their cross product, their norms) and float64 (everything touched by the integer
+// list [0, 1, 0]); the same types are used here, dot products are accumulated left to right.  numpy's dot goes through
+// BLAS (unspecified order / FMA) and its arccos through libm, so parity is to a tolerance, not bit-exact.
+struct Vec3f { float x, y, z; };
+struct Vec3d { double x, y, z; };
+__device__ __forceinline__ Vec3f sub3f(const float* a, const float* b) {
+  return {__fsub_rn(a[0], b[0]), __fsub_rn(a[1], b[1]), __fsub_rn(a[2], b[2])};
+}
+__device__ __forceinline__ Vec3f cross3f(Vec3f a, Vec3f b) {  // np.cross on float32: separate products, then subtract
+  return {__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+          __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x))};
+}
+__device__ __forceinline__ float dot3f(Vec3f a, Vec3f b) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ double dot3d(Vec3d a, Vec3d b) {
+  return __dadd_rn(__dadd_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y)), __dmul_rn(a.z, b.z));
+}
+__device__ __forceinline__ Vec3d widen(Vec3f a) { return {(double)a.x, (double)a.y, (double)a.z}; }
+__device__ __forceinline__ double clamp_acos(double c) { return acos(c); }  // np.arccos: NaN outside [-1, 1], like acos
+
+struct AnglesParams {
+  const float* joints3d;   // [n][21][3]
+  const int* stream_ids;   // [n]
+  const double* t;         // [n] clock readings, or nullptr = no filtering (Joints2Angles(filter=False))
+  FilterState* st;         // [max_streams][8]
+  double* angles;          // [n][8] radians: s0_l, s1_l, e0_l, e1_l, s0_r, s1_r, e0_r, e1_r
+  int n;
+};
+
+__global__ void joints2angles_kernel(AnglesParams p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.n) return;
+  const float* j = p.joints3d + (size_t)i * kJoints * 3;
+  const float *sh_l = j + 5 * 3, *el_l = j + 6 * 3, *wr_l = j + 7 * 3, *sh_r = j + 2 * 3, *el_r = j + 3 * 3, *wr_r = j + 4 * 3;
+  const Vec3f s2e_l = sub3f(el_l, sh_l), e2w_l = sub3f(wr_l, el_l);
+  const Vec3f s2e_r = sub3f(el_r, sh_r), e2w_r = sub3f(wr_r, el_r);
+  const Vec3f v1_l = sub3f(sh_r, sh_l);
+  const Vec3f v1_r = {-v1_l.x, -v1_l.y, -v1_l.z};
+  const Vec3d down = {0.0, 1.0, 0.0};
+  // cross(a, [0, 1, 0]) in float64 = (-a.z, 0, a.x) up to the sign of zero
+  const Vec3d v3_l = {-(double)s2e_l.z, 0.0, (double)s2e_l.x}, v3_r = {-(double)s2e_r.z, 0.0, (double)s2e_r.x};
+  const Vec3f v4_l = cross3f(s2e_l, e2w_l), v4_r = cross3f(s2e_r, e2w_r);
+  auto norm_f = [](Vec3f a) { return (double)__fsqrt_rn(dot3f(a, a)); };   // float32 norm, promoted when multiplied
+  auto norm_d = [](Vec3d a) { return __dsqrt_rn(dot3d(a, a)); };
+  // cal_angle(v1, v2) = arccos(dot / (|v1| * |v2|)) with numpy's result types
+  auto ang_fd = [&](Vec3f a, Vec3d b) { return clamp_acos(__ddiv_rn(dot3d(widen(a), b), __dmul_rn(norm_f(a), norm_d(b)))); };
+  auto ang_dd_f = [&](Vec3d a, Vec3f b) { return clamp_acos(__ddiv_rn(dot3d(a, widen(b)), __dmul_rn(norm_d(a), norm_f(b)))); };
+  auto ang_ff = [&](Vec3f a, Vec3f b) {  // all float32: float32 cosine, float32 arccos
+    const float c = __fdiv_rn(dot3f(a, b), __fmul_rn(__fsqrt_rn(dot3f(a, a)), __fsqrt_rn(dot3f(b, b))));
+    return (double)acosf(c);
+  };
+  const double kPi = 3.141592653589793;
+  double a[8];
+  a[0] = __dsub_rn(__ddiv_rn(__dmul_rn(kPi, 3.0), 4.0), ang_fd(v1_l, v3_l));   // s0_l
+  a[1] = __dsub_rn(__ddiv_rn(kPi, 2.0), ang_dd_f(down, s2e_l));               // s1_l
+  a[2] = -ang_dd_f(v3_l, v4_l);                                                // e0_l
+  a[3] = ang_ff(s2e_l, e2w_l);                                                 // e1_l (float32 in the reference)
+  a[4] = __dsub_rn(__ddiv_rn(kPi, 4.0), ang_fd(v1_r, v3_r));                   // s0_r
+  a[5] = __dsub_rn(__ddiv_rn(kPi, 2.0), ang_dd_f(down, s2e_r));               // s1_r
+  a[6] = ang_dd_f(v3_r, v4_r);                                                 // e0_r
+  a[7] = ang_ff(s2e_r, e2w_r);                                                 // e1_r (float32)
+  a[0] = __dsub_rn(a[0], __ddiv_rn(kPi, 4.0));   // the script's final pose offsets (joints2angles.py:101-105)
+  a[3] = -a[3];
+  a[4] = __dadd_rn(a[4], __ddiv_rn(kPi, 4.0));
+  a[5] = -a[5];
+  if (p.t != nullptr) {
+    const FilterCfg cfg = {120.0, 0.5, 0.5, 1.0};  // joints2angles.py:35-41
+    FilterState* st = p.st + (size_t)p.stream_ids[i] * 8;
+    for (int k = 0; k < 8; ++k) {
+      FilterState s = st[k];
+      a[k] = oef_step(s, cfg, a[k], p.t[i], false);
+      st[k] = s;
+    }
+  }
+  for (int k = 0; k < 8; ++k) p.angles[(size_t)i * 8 + k] = a[k];
+}
+
 // Debug scan (vnect_check_finite): values of an fp16 activation tensor that are NaN / Inf or saturated (|x| >= 65504).
 __global__ void count_nonfinite_kernel(const __half* __restrict__ x, size_t n, unsigned long long* __restrict__ out) {
   unsigned long long c = 0;

@@ -105,6 +105,12 @@ struct vnect_handle {
   std::vector<double> last_t2d, last_t3d;  // host mirror of the filters' last timestamps (NaN = none yet)
   PyramidParams pyr{};
   double* d_packed = nullptr;  // caller-owned device buffer [max_frames][21][5] (vnect_set_packed_results) or null
+  FilterState* d_st_ang = nullptr;      // [max_streams][8] one-euro filters of Joints2Angles (joints2angles.py:35-42)
+  std::vector<double> last_t_ang;
+  float* d_ang_in = nullptr;            // [max_frames][21][3]
+  double* d_ang_t = nullptr;            // [max_frames]
+  int* d_ang_ids = nullptr;
+  double* d_ang_out = nullptr;          // [max_frames][8]
   unsigned int* d_nonfinite = nullptr;  // (frame, joint) blocks whose maps held NaN / Inf since the last check
   unsigned long long* d_scan = nullptr; // vnect_check_finite scratch
 };
@@ -572,6 +578,12 @@ static int alloc_prepost(vnect_t* h) {
   if ((rc = dev_alloc(h, &h->d_raw_argmax, (size_t)mf * kJoints * 2))) return rc;
   if ((rc = dev_alloc(h, &h->d_counter, mf))) return rc;
   if ((rc = dev_alloc(h, &h->d_filter_scratch, 64))) return rc;
+  if ((rc = dev_alloc(h, &h->d_st_ang, (size_t)ms * 8))) return rc;
+  if ((rc = dev_alloc(h, &h->d_ang_in, (size_t)mf * kJoints * 3))) return rc;
+  if ((rc = dev_alloc(h, &h->d_ang_t, mf))) return rc;
+  if ((rc = dev_alloc(h, &h->d_ang_ids, mf))) return rc;
+  if ((rc = dev_alloc(h, &h->d_ang_out, (size_t)mf * 8))) return rc;
+  h->last_t_ang.assign(ms, NAN);
   if ((rc = dev_alloc(h, &h->d_nonfinite, 1))) return rc;
   if ((rc = dev_alloc(h, &h->d_scan, 1))) return rc;
   if ((rc = dev_alloc(h, &h->d_boxes, ms))) return rc;
@@ -1252,6 +1264,13 @@ int vnect_reset_stream(vnect_t* h, int32_t stream_id) {
   CU(h, cudaStreamSynchronize(h->stream));
   CU(h, cudaMemcpy(h->d_st2d + (size_t)lo * kJoints * 2, s2.data(), s2.size() * sizeof(FilterState), cudaMemcpyHostToDevice));
   CU(h, cudaMemcpy(h->d_st3d + (size_t)lo * kJoints * 3, s3.data(), s3.size() * sizeof(FilterState), cudaMemcpyHostToDevice));
+  {
+    FilterState za = z;
+    za.freq = 120.0;  // joints2angles.py:36
+    std::vector<FilterState> sa((size_t)(hi - lo) * 8, za);
+    CU(h, cudaMemcpy(h->d_st_ang + (size_t)lo * 8, sa.data(), sa.size() * sizeof(FilterState), cudaMemcpyHostToDevice));
+    for (int i = lo; i < hi; ++i) h->last_t_ang[i] = NAN;
+  }
   for (int i = lo; i < hi; ++i) h->last_t2d[i] = h->last_t3d[i] = NAN;
   // the tracked crop box restarts as the whole frame (run_estimator.py:68: rect = 0, 0, W_img, H_img); the geometry
   // kernel clips it to the actual frame size
@@ -1292,6 +1311,38 @@ static int quiesce(vnect_t* h) {
       L.pending = false;
     }
   CU(h, cudaStreamSynchronize(h->stream));
+  return VNECT_OK;
+}
+
+int vnect_joints2angles(vnect_t* h, const float* joints3d, int32_t n, const int32_t* stream_ids, const double* t,
+                        double* angles) {
+  if (!h || !h->d_st_ang || !joints3d || !angles) return fail(h, VNECT_E_INVALID, "handle not created / null buffer");
+  ON_DEVICE(h);
+  if (n < 1 || n > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n %d not in [1, %d]", n, h->cfg.max_frames);
+  std::vector<int> ids(n);
+  for (int i = 0; i < n; ++i) {
+    ids[i] = stream_ids ? stream_ids[i] : i;
+    if (ids[i] < 0 || ids[i] >= h->cfg.max_streams) return fail(h, VNECT_E_INVALID, "stream id out of range");
+    if (t) {  // same clock rules as the joint filters (OneEuroFilter.py:21-22, 66)
+      const double last = h->last_t_ang[ids[i]];
+      if (last == last && last != 0.0 && t[i] != 0.0) {
+        if (t[i] == last) return fail(h, VNECT_E_ZERO_DT, "float division by zero (stream %d: repeated timestamp %.17g)", ids[i], t[i]);
+        if (t[i] < last) return fail(h, VNECT_E_INVALID, "alpha should be in (0.0, 1.0] (stream %d: timestamp %.17g earlier than the previous %.17g)", ids[i], t[i], last);
+      }
+    }
+  }
+  if (t) for (int i = 0; i < n; ++i) h->last_t_ang[ids[i]] = t[i];
+  CU(h, cudaMemcpyAsync(h->d_ang_in, joints3d, (size_t)n * kJoints * 3 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_ang_ids, ids.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (t) CU(h, cudaMemcpyAsync(h->d_ang_t, t, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  AnglesParams ap;
+  ap.joints3d = h->d_ang_in; ap.stream_ids = h->d_ang_ids; ap.t = t ? h->d_ang_t : nullptr;
+  ap.st = h->d_st_ang; ap.angles = h->d_ang_out; ap.n = n;
+  joints2angles_kernel<<<(n + 63) / 64, 64, 0, h->stream>>>(ap);
+  CU(h, cudaGetLastError());
+  ++h->launches;
+  CU(h, cudaMemcpyAsync(angles, h->d_ang_out, (size_t)n * 8 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));  // ids is a host temporary
   return VNECT_OK;
 }
 

@@ -219,6 +219,20 @@ class VNectEngine:
         self._check(self._lib.vnect_filter(self._h, int(stream_id), int(dim), 1 if is_f32 else 0, float(t), _ptr(v)))
         return v.reshape(JOINTS, dim)
 
+    def joints2angles(self, joints_3d, stream_ids=None, t=None):
+        """src/joints2angles.py:60-110 for n frames: [n,21,3] float32 -> [n,8] float64 radians, one-euro filtered per
+        stream when clock readings ``t`` are given."""
+        j = np.ascontiguousarray(joints_3d, dtype=np.float32)
+        if j.ndim == 2:
+            j = j[None]
+        n = j.shape[0]
+        ids = np.arange(n, dtype=np.int32) if stream_ids is None else np.ascontiguousarray(stream_ids, dtype=np.int32)
+        tt = None if t is None else np.ascontiguousarray(np.broadcast_to(np.asarray(t, dtype=np.float64), (n,)))
+        out = np.empty((n, 8), np.float64)
+        self._check(self._lib.vnect_joints2angles(self._h, _ptr(j), n, _ptr(ids), _ptr(tt) if tt is not None else None,
+                                                  _ptr(out)))
+        return out
+
     def raw_argmax(self, n=1):
         """Unfiltered (row, col) argmax in box pixels of the last estimate / submit / track call, int32 [n,21,2]."""
         out = np.empty((n, JOINTS, 2), np.int32)
@@ -388,3 +402,35 @@ class VNectEstimator:
         if self._verbose:
             print('FPS: {:>2.2f}'.format(1 / (time.time() - t0)))
         return joints_2d, joints_3d
+
+
+class Joints2Angles:
+    """Drop-in for the reference class (src/joints2angles.py:23-57): ``angles = Joints2Angles()(joints_3d)`` returns the
+    list [s0_l, s1_l, e0_l, e1_l, s0_r, s1_r, e0_r, e1_r] in radians and prints them, computed (and one-euro filtered) on
+    the device.  ``engine`` may be shared with an estimator; otherwise a small CNN-less context is created."""
+
+    def __init__(self, filter=True, engine=None, clock=None, verbose=True):
+        if verbose:
+            print('Initializing Joints2Angles...')
+        self.filter = filter
+        self._engine = engine or VNectEngine(False, [1.0], max_frames=1, max_streams=1)
+        self._clock = clock or time.time
+        self._verbose = verbose
+        if verbose:
+            print('Joints2Angles initialized.')
+
+    def __call__(self, joints_3d):
+        t = [self._clock()] if self.filter else None
+        angles = [float(a) for a in self._engine.joints2angles(np.asarray(joints_3d)[None], [0], t)[0]]
+        if self._verbose:
+            print('%5.2f | %5.2f | %5.2f | %5.2f | %5.2f | %5.2f | %5.2f | %5.2f' % tuple(angles))
+        return angles
+
+    @staticmethod
+    def joints2angles(joints_3d, engine=None):
+        eng = engine or VNectEngine(False, [1.0], max_frames=1, max_streams=1)
+        try:
+            return tuple(float(a) for a in eng.joints2angles(np.asarray(joints_3d)[None])[0])
+        finally:
+            if engine is None:
+                eng.close()
