@@ -851,10 +851,11 @@ def test_joints2angles_vs_reference_golden(golden):
     from vnect_b200 import Joints2Angles, VNectEngine
     g = golden("angles.npz")
     n = len(g["poses"])
-    eng = VNectEngine(False, [1.0], max_frames=n, max_streams=2)
+    eng = VNectEngine(False, [1.0], max_frames=n, max_streams=n)
     try:
-        got = eng.joints2angles(g["poses"], stream_ids=np.zeros(n, np.int32) if False else None) if n <= 2 else \\
-            np.concatenate([eng.joints2angles(g["poses"][i:i + 1], [0]) for i in range(n)])
+        got = eng.joints2angles(g["poses"])                       # n independent frames in one call, no filtering
+        one = np.concatenate([eng.joints2angles(g["poses"][i:i + 1], [0]) for i in range(n)])
+        assert np.array_equal(got, one)
         tol = np.array([2e-6, 2e-6, 2e-6, 2e-3, 2e-6, 2e-6, 2e-6, 2e-3])
         assert np.all(np.abs(got - g["static"]) <= tol), np.abs(got - g["static"]).max(axis=0)
         filt = np.concatenate([eng.joints2angles(g["traj"][k:k + 1], [1], [float(g["t"][k])]) for k in range(n)])
