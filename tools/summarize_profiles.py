@@ -93,7 +93,7 @@ def traffic():
         if m == "gpu__time_duration.sum":
             val *= {"ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}[unit]
         d[m] = val
-    conv = [d for d in per.values() if "conv_gemm" in d["name"] or "stem_pool" in d["name"] or "stem_roll" in d["name"]]
+    conv = [d for d in per.values() if any(k in d["name"] for k in ("conv_gemm", "block_tail", "stem_roll"))]
     ct = sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in conv)
     tt = sum(d["gpu__time_duration.sum"] for d in conv)
     out = ["# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,"
@@ -112,11 +112,33 @@ def traffic():
     json.dump({"source": f"profiles/{tag}_step_traffic.txt (ncu, one step of 64 frames x 2 scales)",
                "conv_family_launches": len(conv), "conv_family_dram_bytes_per_step": ct,
                "conv_family_dram_bytes_per_launch_avg": ct / len(conv), "conv_family_time_us_under_ncu": tt,
-               "frames_per_step": 64}, open(os.path.join(out_dir, "conv_traffic.json"), "w"), indent=1)
+               "frames_per_step": 64,
+               "captured_at_commit": subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True,
+                                                    text=True).stdout.strip()},
+              open(os.path.join(out_dir, "conv_traffic.json"), "w"), indent=1)
     print("wrote traffic:", ct / 1e9, "GB")
+
+
+def full_csv():
+    """gpurun_out/<tag>_full_all.csv (raw page of an --set full capture of every launch of one step) -> one block per launch"""
+    path = os.path.join(ROOT, "gpurun_out", f"{tag}_full_all.csv")
+    if not os.path.isfile(path):
+        return
+    part = [r for r in csv.reader(open(path)) if len(r) > 20]
+    hdr, units, rows = part[0], part[1], part[2:]
+    idx = {m: hdr.index(m) for m in METRICS if m in hdr}
+    kn = hdr.index("Kernel Name")
+    with open(os.path.join(out_dir, f"{tag}_ncu_full_step.txt"), "w") as f:
+        f.write("# ncu --set full --clock-control none over every launch of one bench step (64 frames x 2 scales)\n")
+        for n, r in enumerate(rows):
+            f.write(f"\n[{n}] " + r[kn].replace("CUtensorMap_st, ", "")[:120] + "\n")
+            for m, i in idx.items():
+                f.write(f"    {m:75s} {r[i]:>16s} {units[i]}\n")
+    print("wrote full step:", len(rows), "launches")
 
 
 launches()
 traffic()
+full_csv()
 full("prof_conv*.ncu-rep", "conv")
 full("prof_prepost.ncu-rep", "prepost")
