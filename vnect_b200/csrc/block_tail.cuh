@@ -318,24 +318,22 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t tiles = 0, res_ctr = 0;
     uint32_t m = 0;                       // main chunks staged by this group so far; chunk m uses buffer m & 1
-    uint32_t m_last[2] = {0, 0};          // last main chunk staged into each buffer ...
-    bool chained_pending[2] = {false, false};  // ... and whether its second-GEMM read has been waited for
-    uint32_t store_seq = 0, last_store[2] = {0, 0};
-    bool stored[2] = {false, false};
+    // per staging buffer (kept in scalars: indexing small arrays by a run-time buffer number puts them in local memory)
+    uint32_t m_last0 = 0, m_last1 = 0;              // last main chunk staged into the buffer ...
+    bool chained0 = false, chained1 = false;        // ... and whether its second-GEMM read has not been waited for yet
+    uint32_t store_seq = 0, last_store0 = 0, last_store1 = 0;
+    bool stored0 = false, stored1 = false;
 
     // fp32 x 64 (+ bias, + residual) -> relu? -> fp16 into a swizzled staging tile
-    auto stage_chunk = [&](uint8_t* ostage, const uint32_t (&v)[64], const float* bias, bool relu, const uint8_t* rstage) {
+    // bias_lo / bias_hi: this lane's two of the chunk's 64 bias values (columns lane and 32 + lane), loaded by the caller
+    // before the TMEM read so their latency is hidden; distributed by shuffles here
+    auto stage_chunk = [&](uint8_t* ostage, const uint32_t (&v)[64], float bias_lo, float bias_hi, bool relu, const uint8_t* rstage) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
-        if (bias != nullptr) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * j + 4));
-          f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-          f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-        }
+        for (int e = 0; e < 8; ++e)
+          f[e] = __uint_as_float(v[8 * j + e]) + __shfl_sync(0xffffffffu, j < 4 ? bias_lo : bias_hi, (8 * j + e) & 31);
         const uint32_t off = row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);
         if (rstage != nullptr) {
           const uint4 rv = *reinterpret_cast<const uint4*>(rstage + off);
@@ -361,15 +359,20 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // buffer b may be rewritten once the second GEMM has read its last chained content and its last TMA store has
     // read it (the store of the OTHER buffer may still be in flight)
     auto acquire = [&](int b) {
-      if (chained_pending[b]) {
-        mbar_wait(&chunk_free[grp * 2 + b], (m_last[b] >> 1) & 1u);
-        chained_pending[b] = false;
+      const bool chained = b ? chained1 : chained0;
+      if (chained) {
+        mbar_wait(&chunk_free[grp * 2 + b], ((b ? m_last1 : m_last0) >> 1) & 1u);
+        if (b) chained1 = false; else chained0 = false;
       }
-      if (leader && stored[b]) {
-        if (store_seq - last_store[b] <= 1) bulk_wait_group_read<0>();
+      if (leader && (b ? stored1 : stored0)) {
+        if (store_seq - (b ? last_store1 : last_store0) <= 1) bulk_wait_group_read<0>();
         else bulk_wait_group_read<1>();
       }
       named_bar_sync(1 + grp, 128);
+    };
+    auto note_store = [&](int b) {
+      ++store_seq;
+      if (b) { last_store1 = store_seq; stored1 = true; } else { last_store0 = store_seq; stored0 = true; }
     };
     // second accumulator of local unit `du` -> Y (bias2, ReLU), through the staging tile the next main chunk will use
     auto drain_acc2 = [&](uint32_t du, int cx, int cy, int cn) {
@@ -381,6 +384,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint8_t* ostage = my_stage + b * kEpiChunkBytes;
 #pragma unroll 1
       for (int e = grp; e < CH2; e += 2) {
+        const float bias_lo = __ldg(bp.bias2 + e * 64 + lane), bias_hi = __ldg(bp.bias2 + e * 64 + 32 + lane);
         uint32_t v[64];
         tmem_ld_32x32(t_lane + BLOCK_N + a2 * N2 + e * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         tmem_ld_32x32(t_lane + BLOCK_N + a2 * N2 + e * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
@@ -391,15 +395,14 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (lane == 0) mbar_arrive_leader(&acc2_empty[a2]);
         }
         acquire(b);
-        stage_chunk(ostage, v, bp.bias2 + e * 64, true, nullptr);
+        stage_chunk(ostage, v, bias_lo, bias_hi, true, nullptr);
         fence_proxy_async_smem();
         named_bar_sync(1 + grp, 128);
         if (leader) {
           tma_store_5d(&tmap_out2, ostage, e * 64, cx, cy, 0, cn);
           bulk_commit_group();
         }
-        last_store[b] = ++store_seq;
-        stored[b] = true;
+        note_store(b);
       }
     };
 
@@ -416,6 +419,12 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll 1
         for (int c = grp; c < CH; c += 2) {
           const int c0 = c * 64;
+          const int col0 = nt * BLOCK_N + c0;
+          float bias_lo = 0.f, bias_hi = 0.f;
+          if (p.bias != nullptr) {
+            bias_lo = __ldg(p.bias + col0 + lane);
+            bias_hi = __ldg(p.bias + col0 + 32 + lane);
+          }
           uint32_t v[64];
           tmem_ld_32x32(t_lane + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
           tmem_ld_32x32(t_lane + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
@@ -425,7 +434,6 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tmem_empty);
           }
-          const int col0 = nt * BLOCK_N + c0;
           const uint8_t* rstage = nullptr;
           uint32_t rb = 0;
           if constexpr (RES) {
@@ -437,7 +445,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const int b = m & 1u;
           uint8_t* ostage = my_stage + b * kEpiChunkBytes;
           acquire(b);
-          stage_chunk(ostage, v, p.bias != nullptr ? p.bias + col0 : nullptr, col0 < p.relu_cols, rstage);
+          stage_chunk(ostage, v, bias_lo, bias_hi, col0 < p.relu_cols, rstage);
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store and to the tensor cores
           named_bar_sync(1 + grp, 128);
           if (leader) {
@@ -446,10 +454,8 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if constexpr (RES) mbar_arrive(&res_empty[rb]);
             mbar_arrive_leader(&chunk_ready[grp * 2 + b]);  // this CTA's half of the chunk is in place
           }
-          last_store[b] = ++store_seq;
-          stored[b] = true;
-          m_last[b] = m;
-          chained_pending[b] = true;
+          note_store(b);
+          if (b) { m_last1 = m; chained1 = true; } else { m_last0 = m; chained0 = true; }
           ++m;
           if (drain_due) {  // the previous unit's second accumulator, now that this unit is under way
             drain_acc2(drain_unit, dcx, dcy, dcn);

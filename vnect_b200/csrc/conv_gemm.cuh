@@ -543,6 +543,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           waited = true;
         }
+        // the chunk's 64 bias values, two per lane, requested BEFORE the accumulator is read so that their latency hides
+        // behind the TMEM load (a per-use __ldg put ~16 % of the epilogue warps' stall samples on the bias adds)
+        float bias_lo = 0.f, bias_hi = 0.f;
+        if (p.bias != nullptr) {
+          bias_lo = __ldg(p.bias + col_base + c0 + lane);
+          bias_hi = __ldg(p.bias + col_base + c0 + 32 + lane);
+        }
         uint32_t v[64];
         tmem_ld_32x32(t_row + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         tmem_ld_32x32(t_row + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
@@ -569,12 +576,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
-          if (p.bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * j));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 8 * j + 4));
-            f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-            f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e)  // column 8j+e of the chunk: lane (8j+e) & 31 of the low / high half holds its bias
+            f[e] += __shfl_sync(0xffffffffu, j < 4 ? bias_lo : bias_hi, (8 * j + e) & 31);
           const uint32_t off = row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);  // 128B swizzle, as the TMA unit does
           if constexpr (EPI == EPI_TMA_RES) {
             const uint4 rv = *reinterpret_cast<const uint4*>(rstage + off);
