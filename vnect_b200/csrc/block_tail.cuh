@@ -131,6 +131,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
   if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
   tc_fence_before();
+  __syncthreads();  // orders the TMEM allocator's smem write of the base address before everybody's read of it
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;

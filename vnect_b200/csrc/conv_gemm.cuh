@@ -34,9 +34,17 @@ enum EpiKind : int {
 };
 
 constexpr int kEpiChunkBytes = kBlockM * 128;  // one 64-column fp16 chunk of a tile: 128 rows x 128 B
-constexpr int kOutStages = 1;   // per epilogue warpgroup (two groups alternate, so each ring needs one slot)
+// Experiment switches (selftest builds only, `make experiments`): each removes one stage of the TMA epilogue so that the
+// per-chunk cost can be attributed; results are wrong by construction, only the timing is read.
+#ifndef VNECT_EXP_OUT_STAGES
+#define VNECT_EXP_OUT_STAGES 1
+#endif
+constexpr int kOutStages = VNECT_EXP_OUT_STAGES;   // per epilogue warpgroup (two groups alternate, so each ring needs one slot)
 constexpr int kEpiGroups = 2;
-constexpr int kResStages = 4;
+#ifndef VNECT_EXP_RES_STAGES
+#define VNECT_EXP_RES_STAGES 4
+#endif
+constexpr int kResStages = VNECT_EXP_RES_STAGES;
 
 struct ConvGemmParams {
   // ---- tiling of the GEMM rows
@@ -116,7 +124,7 @@ struct GemmCfg {
                                         : (2 * BLOCK_N <= 256) ? 256
                                                                : 512;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + HALO_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
-  static_assert(STAGES >= 2 || (HALO && BRES), "pipeline needs at least two stages");
+  static_assert(STAGES >= 2 || (HALO && BRES) || (VNECT_EXP_RES_STAGES > 4 && STAGES >= 1), "pipeline needs at least two stages");
   static_assert(!HALO || (EPI == EPI_TMA && SWZ == 128), "the halo-patch path is the plain 3x3 conv: EPI_TMA, 128B swizzle");
   static_assert(2 * STAGES + 5 + 2 * kResStages + 2 <= 64, "barriers must fit their 512-byte region");
   static_assert(2 * BLOCK_N <= 512, "two accumulator stages must fit TMEM");
@@ -199,8 +207,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   }
   tc_fence_before();
+  __syncthreads();  // orders the TMEM allocator's smem write of the base address before everybody's read of it
   if constexpr (CG == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
-  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // PDL: everything above (barrier init, descriptor prefetch, TMEM allocation) may overlap the previous layer's tail;
@@ -551,9 +559,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           bias_hi = __ldg(p.bias + col_base + c0 + 32 + lane);
         }
         uint32_t v[64];
+#ifdef VNECT_EXP_NO_TMEM_LD
+#pragma unroll
+        for (int e = 0; e < 64; ++e) v[e] = static_cast<uint32_t>(e + lane);
+#else
         tmem_ld_32x32(t_row + c0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
         tmem_ld_32x32(t_row + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tmem_ld_wait();
+#endif
         if (c + 2 >= CH) {  // this group's last chunk of the tile: its share of the accumulator has been read
           tc_fence_before();
           __syncwarp();
@@ -571,8 +584,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         named_bar_sync(1 + grp, 128);
         const int col0 = col_base + c0;
         const bool relu = col0 < p.relu_cols;
+#ifdef VNECT_EXP_NO_PACK
+#pragma unroll
+        for (int j = 0; j < 0; ++j) {
+#else
 #pragma unroll
         for (int j = 0; j < 8; ++j) {  // 8 x 16 B = this row's 64 output channels
+#endif
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
@@ -580,7 +598,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int e = 0; e < 8; ++e)  // column 8j+e of the chunk: lane (8j+e) & 31 of the low / high half holds its bias
             f[e] += __shfl_sync(0xffffffffu, j < 4 ? bias_lo : bias_hi, (8 * j + e) & 31);
           const uint32_t off = row_off + ((static_cast<uint32_t>(j) ^ sw) << 4);  // 128B swizzle, as the TMA unit does
+#ifndef VNECT_EXP_NO_RES
           if constexpr (EPI == EPI_TMA_RES) {
+#else
+          if constexpr (false) {
+#endif
             const uint4 rv = *reinterpret_cast<const uint4*>(rstage + off);
             const __half2* h = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
@@ -607,7 +629,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         named_bar_sync(1 + grp, 128);
         if (leader) {
+#ifndef VNECT_EXP_NO_STORE
           tma_store_5d(&tmap_out, ostage, col0, cx, cy, 0, cn);
+#endif
           bulk_commit_group();
           if constexpr (EPI == EPI_TMA_RES) mbar_arrive(&res_empty[rb]);
         }
