@@ -407,13 +407,7 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
     const size_t plane = (size_t)cells;
     for (int sc = 0; sc < p.n_scales; ++sc) {
       const float* m = p.maps + ((size_t)(frame * p.n_scales + sc) * 84 + joint) * plane;
-      if ((cells & 3) == 0) {  // planes are 16-byte aligned whenever hs*hs is a multiple of 4 (46, 56, 64): 16-byte loads
-        const float4* m4 = reinterpret_cast<const float4*>(m);
-        float4* s4 = reinterpret_cast<float4*>(s_raw + sc * cells);
-        for (int c = tid; c < cells / 4; c += kPostThreads) s4[c] = __ldg(m4 + c);
-      } else {
-        for (int c = tid; c < cells; c += kPostThreads) s_raw[sc * cells + c] = __ldg(m + c);
-      }
+      for (int c = tid; c < cells; c += kPostThreads) s_raw[sc * cells + c] = __ldg(m + c);
     }
   }
   // per-axis candidate tables of the x8 upsample (see upsample_candidate)
@@ -430,70 +424,33 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
   double cell_best = -INFINITY, cell_amax = 0.0;
   int cell_best_idx = 0;
   int nonfinite = 0;
-  {
-    // Every thread owns the cells (rows warp_id, warp_id + warps, ...) x (columns lane, lane + 32): their float64 sums
-    // stay in registers across the scales (same order of additions as the reference: scale 0 first), the column
-    // coefficients of a scale are loaded once per thread and the row coefficients once per row -- the first version
-    // re-read eight table entries per cell and scale and spent most of its instructions on that.
-    constexpr int kWarps = kPostThreads / 32;
-    constexpr int kRows = (kMaxHm + kWarps - 1) / kWarps;
-    double acc[kRows][2];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) acc[r][0] = acc[r][1] = 0.0;
-    const int xs[2] = {lane_id, lane_id + 32};
-    for (int sc = 0; sc < p.n_scales; ++sc) {
-      const ScaleTable& T = p.tables[sc];
-      const float* m = s_raw + sc * cells;
-      if (T.identity) {
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          const int y = warp_id + r * kWarps;
-          if (y >= hs) break;
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            if (xs[k] < hs) acc[r][k] = __dadd_rn(acc[r][k], (double)m[y * hs + xs[k]]);
-        }
-      } else {  // cv2 float32 resize arithmetic: separate multiplies and adds
-        int x0[2], x1[2];
-        float a0[2], a1[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int xc = min(xs[k], hs - 1);
-          x0[k] = T.i0[xc]; x1[k] = T.i1[xc]; a0[k] = T.a0[xc]; a1[k] = T.a1[xc];
-        }
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          const int y = warp_id + r * kWarps;
-          if (y >= hs) break;
+  for (int y = warp_id; y < hs; y += kPostThreads / 32) {
+    for (int x = lane_id; x < hs; x += 32) {
+      double acc = 0.0;
+      for (int sc = 0; sc < p.n_scales; ++sc) {
+        const ScaleTable& T = p.tables[sc];
+        const float* m = s_raw + sc * cells;
+        float v;
+        if (T.identity) {
+          v = m[y * hs + x];
+        } else {  // cv2 float32 resize arithmetic: separate multiplies and adds
           const float* r0 = m + T.j0[y] * hs;
           const float* r1 = m + T.j1[y] * hs;
-          const float b0 = T.b0[y], b1 = T.b1[y];
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            if (xs[k] >= hs) continue;
-            const float t0 = __fadd_rn(__fmul_rn(r0[x0[k]], a0[k]), __fmul_rn(r0[x1[k]], a1[k]));
-            const float t1 = __fadd_rn(__fmul_rn(r1[x0[k]], a0[k]), __fmul_rn(r1[x1[k]], a1[k]));
-            const float v = __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, b1));
-            acc[r][k] = __dadd_rn(acc[r][k], (double)v);
-          }
+          const int x0 = T.i0[x], x1 = T.i1[x];
+          const float a0 = T.a0[x], a1 = T.a1[x];
+          const float t0 = __fadd_rn(__fmul_rn(r0[x0], a0), __fmul_rn(r0[x1], a1));
+          const float t1 = __fadd_rn(__fmul_rn(r1[x0], a0), __fmul_rn(r1[x1], a1));
+          v = __fadd_rn(__fmul_rn(t0, T.b0[y]), __fmul_rn(t1, T.b1[y]));
         }
+        acc = __dadd_rn(acc, (double)v);
       }
-    }
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int y = warp_id + r * kWarps;
-      if (y >= hs) break;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (xs[k] >= hs) continue;
-        // hm_avg /= len(scales): for 1, 2 or 4 scales the quotient is an exact scaling, bit-identical to the division
-        const double a = p.n_scales == 1 ? acc[r][k] : p.n_scales == 2 ? __dmul_rn(acc[r][k], 0.5)
-                         : p.n_scales == 4 ? __dmul_rn(acc[r][k], 0.25) : __ddiv_rn(acc[r][k], (double)p.n_scales);
-        s_avg[y * hs + xs[k]] = a;
-        if (a > cell_best) { cell_best = a; cell_best_idx = y * hs + xs[k]; }
-        cell_amax = fmax(cell_amax, fabs(a));
-        nonfinite |= !(fabs(a) <= 1.7976931348623157e308);  // NaN or Inf (fmax above would silently drop a NaN)
-      }
+      // hm_avg /= len(scales): for 1, 2 or 4 scales the quotient is an exact scaling, bit-identical to the division
+      const double a = p.n_scales == 1 ? acc : p.n_scales == 2 ? __dmul_rn(acc, 0.5) : p.n_scales == 4 ? __dmul_rn(acc, 0.25)
+                                                                                   : __ddiv_rn(acc, (double)p.n_scales);
+      s_avg[y * hs + x] = a;
+      if (a > cell_best) { cell_best = a; cell_best_idx = y * hs + x; }
+      cell_amax = fmax(cell_amax, fabs(a));
+      nonfinite |= !(fabs(a) <= 1.7976931348623157e308);  // NaN or Inf (fmax above would silently drop a NaN)
     }
   }
   // block-wide largest cell: its neighbourhood gives a lower bound L0 on the upsampled maximum, which prunes almost
