@@ -285,7 +285,9 @@ struct ScaleTable {  // per pyramid scale: where output cell c of the cropped, 1
   float a0[kMaxHm], a1[kMaxHm];
   short j0[kMaxHm], j1[kMaxHm];      // y axis (rows clamped, f kept)
   float b0[kMaxHm], b1[kMaxHm];
+  int4 rowpk[kMaxHm];                 // the y-axis entries again, one 16-byte load: (j0*hs, j1*hs, bits of b0, bits of b1)
   int identity;                       // s == 1: plain copy
+  int row_lo, row_hi;                 // raw rows the cropped resize ever reads (only those are staged on chip)
 };
 
 struct FilterCfg { double freq, mincutoff, beta, dcutoff; };
@@ -345,14 +347,67 @@ struct PostParams {
   double* j2_box;                 // [n_frames][21][2] scratch: filtered 2D joints in box pixels (also an output tap)
   float* j3_raw;                  // [n_frames][21][3] scratch: x100 location-map samples before root subtraction
   int* raw_argmax;                // [n_frames][21][2] unfiltered argmax (row, col), a tap for parity tests
-  unsigned int* frame_counter;    // [n_frames], zeroed before launch
+  unsigned int* frame_counter;    // [n_frames]: zero between launches (the last block of a frame puts it back to zero)
   double* out2d;                  // [n_frames][21][2]
   float* out3d;                   // [n_frames][21][3]
   double* packed;                 // optional [n_frames][21][5] = (row, col, x, y, z): the layout the multi-GPU gather moves
   unsigned int* nonfinite;        // counts (frame, joint) blocks that met a NaN / Inf in the CNN's maps (fp16 overflow guard)
+  // shared-memory plan of one block (post_smem_plan, host): which raw cells of every scale's heat-map plane are staged
+  // and where.  An identity scale needs its whole plane, a resized one only the rows its centre crop samples.
+  int identity_mask;              // bit sc: scale sc is a plain copy
+  int plane_start[kMaxScales];    // first raw cell staged
+  int plane_len[kMaxScales];      // cells staged
+  int plane_off[kMaxScales];      // where, in floats from the start of the dynamic shared memory (multiple of 4)
+  int sum_off;                    // float32 plane of per-cell sums over the scales
+  int alias_scale;                // the sums overwrite this (identity) scale's staged plane in place; -1: own plane
+  int smem_floats;                // dynamic shared memory, in floats
 };
 
-constexpr int kPostThreadsDefault = 256;  // threads per (frame, joint) block; 128 / 256 / 512 are instantiated
+// Host side of the plan above.  `rows_lo/hi` per scale come from the ScaleTable.
+inline void post_smem_plan(PostParams& p, const ScaleTable* host_tables) {
+  const int cells = p.hs * p.hs;
+  const bool vec = (cells & 3) == 0;  // 16-byte cp.async needs 16-byte aligned plane starts
+  int off = 0;
+  p.identity_mask = 0;
+  p.alias_scale = -1;
+  for (int sc = 0; sc < kMaxScales; ++sc) { p.plane_start[sc] = p.plane_len[sc] = p.plane_off[sc] = 0; }
+  for (int sc = 0; sc < p.n_scales; ++sc) {
+    const ScaleTable& T = host_tables[sc];
+    int start = 0, end = cells;
+    if (T.identity) {
+      p.identity_mask |= 1 << sc;
+      if (p.alias_scale < 0) p.alias_scale = sc;
+    } else {
+      start = T.row_lo * p.hs;
+      end = (T.row_hi + 1) * p.hs;
+      if (vec) { start &= ~3; end = (end + 3) & ~3; }
+      if (end > cells) end = cells;
+    }
+    p.plane_start[sc] = start;
+    p.plane_len[sc] = end - start;
+    p.plane_off[sc] = off;
+    off += (end - start + 3) & ~3;
+  }
+  if (p.alias_scale >= 0) {
+    p.sum_off = p.plane_off[p.alias_scale];
+  } else {
+    p.sum_off = off;
+    off += (cells + 3) & ~3;
+  }
+  p.smem_floats = off;
+}
+
+constexpr int kPostMaxThreads = 512;
+constexpr int kPostMaxWarps = kPostMaxThreads / 32;
+constexpr int kQuadCap = 192;  // survivor quads kept in the list; more than that (flat maps) takes the full scan
+
+// threads per (frame, joint) block: `rows` heat-map rows per pass, one thread per cell of those rows
+inline int post_threads(int hs, int rows) {
+  int t = (rows * hs + 31) & ~31;
+  if (t > kPostMaxThreads) t = kPostMaxThreads;
+  if (t < 64) t = 64;  // hs <= kMaxHm = 64 cells per row; the gather uses up to 12 * kMaxScales = 48 threads
+  return t;
+}
 
 // 1/s-resized (float32, cv2 arithmetic: separate mul/add) + cropped value of raw planar map `m` at cell (y, x).
 __device__ __forceinline__ float scaled_cell(const float* __restrict__ m, int hs, const ScaleTable& T, int y, int x) {
@@ -378,174 +433,297 @@ __device__ __forceinline__ void upsample_candidate(int k, int hs, int* d, int* i
   else             { *d = 8 * r + 4;  *i = r; *f = 0.0625; }
 }
 
-// grid = n_frames * 21 blocks of 128 threads; block (frame, joint).  The last block of a frame to finish runs the
-// per-frame tail (root subtraction, 3D filters, 2D rescale).
-template <int kPostThreads>
-__global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p) {
-  extern __shared__ double s_avg[];  // [hs][hs] averaged heat-map of this joint
-  __shared__ short s_cd[2 * kMaxHm], s_ci[2 * kMaxHm];
-  __shared__ float s_cf[2 * kMaxHm];
+// OpenCV+IPP's float64 x8 upsample at fractions (fy, fx) inside the source quad (s00 s01 / s10 s11): fma per axis
+__device__ __forceinline__ double upsample_quad(double s00, double s01, double s10, double s11, double fy, double fx) {
+  const double h0 = __fma_rn(__dsub_rn(s01, s00), fx, s00);
+  const double h1 = __fma_rn(__dsub_rn(s11, s10), fx, s10);
+  return __fma_rn(__dsub_rn(h1, h0), fy, h0);
+}
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// grid = n_frames * 21 blocks; block (frame, joint), thread = one cell of the `rpp` heat-map rows a pass covers.
+//
+//  A. the raw heat-map planes of every scale go to shared memory with 16-byte cp.async (the only HBM traffic that
+//     scales with the map: 4 * hs * hs bytes per scale);
+//  B. one float32 pass: cv2-exact resized value of every scale, float32 sum over the scales per cell, the largest
+//     cell.  The float32 sum differs from the reference's float64 accumulation by < n_scales * 2^-24 relative;
+//  C. a lower bound on the maximum of the x8 upsample from the 4 x 4 upsample candidates around the largest cell; every
+//     cell below (bound - 1e-6 * largest |sum|) provably cannot belong to the source quad of the argmax (an upsampled
+//     value is a convex combination of its quad), so only the quads around the few remaining cells survive;
+//  D. the survivors are evaluated EXACTLY as the reference does (float64 accumulation over the scales, /= n,
+//     OpenCV+IPP's fma upsample), ties to the first index like np.argmax.  Pruning only removes candidates that
+//     cannot win, so the result equals the exhaustive float64 scan bit for bit; if more than kQuadCap quads survive
+//     (flat or saturated maps) every quad that passes the same test is scanned in place;
+//  E. 2D 1-euro filters, location-map gather at the FILTERED point, and -- in the last block of the frame to arrive --
+//     root subtraction, 3D filters and the rescale to input pixels.
+template <int NS, int MASK>  // MASK >= 0: the identity mask (PostParams::identity_mask) is this compile-time constant
+__global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const __grid_constant__ PostParams p) {
+  extern __shared__ float4 s_dyn4[];
+  float* s_dyn = reinterpret_cast<float*>(s_dyn4);
+  __shared__ int4 s_rowpk[NS][kMaxHm];  // y-axis resize entries as byte offsets: (j0*hs*4, j1*hs*4, b0, b1)
+  __shared__ float s_wmax[kPostMaxWarps], s_wmin[kPostMaxWarps], s_wamax[kPostMaxWarps];
+  __shared__ int s_widx[kPostMaxWarps];
+  __shared__ double s_bval[kPostMaxWarps];
+  __shared__ int s_bidx[kPostMaxWarps];
+  __shared__ unsigned short s_quads[kQuadCap];
+  __shared__ int s_nq;
   __shared__ double s_pt[2];
   __shared__ float s_gather[12 * kMaxScales];
-  __shared__ double s_val[kPostThreads / 32], s_amax[kPostThreads / 32];
-  __shared__ int s_idx[kPostThreads / 32];
   __shared__ int s_is_last;
+  __shared__ __align__(16) FilterState s_st2[2];
+  __shared__ double s_t2;
+  __shared__ int s_sid;
+
   const int frame = blockIdx.x / kJoints;
   const int joint = blockIdx.x - frame * kJoints;
   const int hs = p.hs, S = p.S;
-  const int tid = threadIdx.x;
+  constexpr int ns = NS;  // p.n_scales
+  const int idmask = MASK >= 0 ? MASK : p.identity_mask;
+  const int cells = hs * hs, nc = 2 * hs;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int warp_id = tid >> 5, lane_id = tid & 31, nwarps = nthreads >> 5;
+  const int rpp = nthreads / hs;          // rows per pass (host guarantees nthreads >= hs)
+  const bool act = tid < rpp * hs;
+  const int ro = tid / hs, x = tid - ro * hs;
+
+  // per-thread column entries of the resize tables, the row entries to shared memory (static data: may be read before
+  // the predecessor has finished)
+  int cx0[NS], cx1[NS];
+  float ca0[NS], ca1[NS];
+#pragma unroll
+  for (int sc = 0; sc < NS; ++sc) {
+    cx0[sc] = cx1[sc] = 0;
+    ca0[sc] = ca1[sc] = 0.f;
+    if (!((idmask >> sc) & 1)) {
+      const ScaleTable& T = p.tables[sc];
+      cx0[sc] = T.i0[x] * 4; cx1[sc] = T.i1[x] * 4;  // byte offsets inside a row
+      ca0[sc] = T.a0[x]; ca1[sc] = T.a1[x];
+      for (int i = tid; i < hs; i += nthreads) {
+        int4 rp = T.rowpk[i];
+        rp.x *= 4; rp.y *= 4;
+        s_rowpk[sc][i] = rp;
+      }
+    }
+  }
+  if (tid == 0) s_nq = 0;
   pdl_launch_dependents();
   pdl_wait();  // the maps come from the last conv
 
-  // ---- 1. multi-scale float64 average of the heat-map (estimator.py:105-129).  Warp w owns rows w, w+4, ...; lane l
-  // owns columns l, l+32.  The whole plane of every scale is first staged in shared memory with coalesced loads (one
-  // round trip to HBM instead of a dependent chain per cell), then resampled from there.
-  const int warp_id = tid >> 5, lane_id = tid & 31;
-  const int cells = hs * hs;
-  float* s_raw = reinterpret_cast<float*>(s_avg + cells);  // [n_scales][hs*hs] raw planes
-  {
-    const size_t plane = (size_t)cells;
-    for (int sc = 0; sc < p.n_scales; ++sc) {
-      const float* m = p.maps + ((size_t)(frame * p.n_scales + sc) * 84 + joint) * plane;
-      for (int c = tid; c < cells; c += kPostThreads) s_raw[sc * cells + c] = __ldg(m + c);
+  // ---- A. stage the planes
+  const char* pl[NS];  // byte pointer such that pl[sc] + 4 * (absolute raw cell) is that cell
+#pragma unroll
+  for (int sc = 0; sc < NS; ++sc) {
+    const float* g = p.maps + ((size_t)(frame * ns + sc) * 84 + joint) * cells + p.plane_start[sc];
+    float* d = s_dyn + p.plane_off[sc];
+    const int len = p.plane_len[sc];
+    if ((cells & 3) == 0) {
+      for (int i = tid * 4; i < len; i += nthreads * 4) cp_async_16(d + i, g + i);
+    } else {
+      for (int i = tid; i < len; i += nthreads) d[i] = __ldg(g + i);
+    }
+    pl[sc] = reinterpret_cast<const char*>(d - p.plane_start[sc]);
+  }
+  // the two 2D filters of this joint: state fetched now, used after the argmax
+  static_assert(sizeof(FilterState) == 48, "three 16-byte pieces per filter state");
+  if (tid < 6 && p.filters_on) {
+    const int sid = p.stream_ids[frame];
+    cp_async_16(reinterpret_cast<char*>(s_st2) + tid * 16,
+                reinterpret_cast<const char*>(p.st2d + ((size_t)sid * kJoints + joint) * 2) + tid * 16);
+    if (tid == 0) { s_sid = sid; s_t2 = p.t2d[frame]; }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- B. float32 sums over the scales (estimator.py:105-129 in float32), largest cell
+  float* s_sum = s_dyn + p.sum_off;
+  float tmax = -INFINITY, tmin = INFINITY, tvmax = 0.f, chk = 0.f;
+  int ty = 0;
+  if (act) {
+#pragma unroll 2
+    for (int y = ro; y < hs; y += rpp) {
+      const int cb = (y * hs + x) * 4;
+      float s = 0.f;
+#pragma unroll
+      for (int sc = 0; sc < NS; ++sc) {
+        float v;
+        if ((idmask >> sc) & 1) {
+          v = *reinterpret_cast<const float*>(pl[sc] + cb);
+        } else {  // cv2 float32 resize arithmetic: separate multiplies and adds
+          const int4 rp = s_rowpk[sc][y];
+          const char* c0 = pl[sc] + cx0[sc];
+          const char* c1 = pl[sc] + cx1[sc];
+          const float t0 = __fadd_rn(__fmul_rn(*reinterpret_cast<const float*>(c0 + rp.x), ca0[sc]),
+                                     __fmul_rn(*reinterpret_cast<const float*>(c1 + rp.x), ca1[sc]));
+          const float t1 = __fadd_rn(__fmul_rn(*reinterpret_cast<const float*>(c0 + rp.y), ca0[sc]),
+                                     __fmul_rn(*reinterpret_cast<const float*>(c1 + rp.y), ca1[sc]));
+          v = __fadd_rn(__fmul_rn(t0, __int_as_float(rp.z)), __fmul_rn(t1, __int_as_float(rp.w)));
+        }
+        s = sc == 0 ? v : __fadd_rn(s, v);
+        if (NS > 2) tvmax = fmaxf(tvmax, fabsf(v));  // partial sums of three or more terms can exceed the final |s|
+      }
+      *reinterpret_cast<float*>(reinterpret_cast<char*>(s_sum) + cb) = s;  // may overwrite pl[alias_scale]'s cell: this thread was its only reader
+      chk = __fmaf_rn(s, 0.f, chk);  // NaN as soon as one s is NaN or Inf (a non-finite v always makes s non-finite)
+      if (s > tmax) { tmax = s; ty = y; }
+      tmin = fminf(tmin, s);
     }
   }
-  // per-axis candidate tables of the x8 upsample (see upsample_candidate)
-  const int nc = 2 * hs;
-  for (int k = tid; k < nc; k += kPostThreads) {
-    int d, i;
-    double f;
-    upsample_candidate(k, hs, &d, &i, &f);
-    s_cd[k] = (short)d;
-    s_ci[k] = (short)i;
-    s_cf[k] = (float)f;  // 0, 1/16, 15/16: exact in float
+  const int bad = chk != chk;
+  float bmax = tmax, bmin = tmin, bvmax = tvmax;
+  int bidx = ty * hs + x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bmax, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (ov > bmax) { bmax = ov; bidx = oi; }
+    bmin = fminf(bmin, __shfl_xor_sync(0xffffffffu, bmin, o));
+    if (NS > 2) bvmax = fmaxf(bvmax, __shfl_xor_sync(0xffffffffu, bvmax, o));
+  }
+  if (lane_id == 0) { s_wmax[warp_id] = bmax; s_widx[warp_id] = bidx; s_wmin[warp_id] = bmin; s_wamax[warp_id] = bvmax; }
+  // fp16 activations overflow at 65504: an Inf / NaN anywhere in the CNN almost surely reaches the maps.  Count it (the
+  // host turns a non-zero count into an error) instead of returning joints computed from garbage.
+  const int any_bad = __syncthreads_or(bad);
+  if (any_bad && tid == 0 && p.nonfinite != nullptr) atomicAdd(p.nonfinite, 1u);
+  bmax = s_wmax[0]; bidx = s_widx[0]; bmin = s_wmin[0]; bvmax = s_wamax[0];
+  for (int w = 1; w < nwarps; ++w) {
+    if (s_wmax[w] > bmax) { bmax = s_wmax[w]; bidx = s_widx[w]; }
+    bmin = fminf(bmin, s_wmin[w]);
+    bvmax = fmaxf(bvmax, s_wamax[w]);
+  }
+  const float bamax = fmaxf(fmaxf(fabsf(bmax), fabsf(bmin)), bvmax);  // largest |s| (and |v| for three or more scales)
+
+  // ---- C. bound from the 4 x 4 candidates around the largest cell (every warp computes the same value)
+  float thr;
+  {
+    const int r0 = bidx / hs, c0 = bidx - r0 * hs;
+    const int ky0 = max(2 * r0 - 1, 0), kx0 = max(2 * c0 - 1, 0);
+    const int ky = min(ky0 + ((lane_id >> 2) & 3), nc - 1), kx = min(kx0 + (lane_id & 3), nc - 1);
+    int dy, dx, iy, ix;
+    double fy, fx;
+    upsample_candidate(ky, hs, &dy, &iy, &fy);
+    upsample_candidate(kx, hs, &dx, &ix, &fx);
+    const int iy1 = min(iy + 1, hs - 1), ix1 = min(ix + 1, hs - 1);
+    double v = upsample_quad((double)s_sum[iy * hs + ix], (double)s_sum[iy * hs + ix1], (double)s_sum[iy1 * hs + ix],
+                             (double)s_sum[iy1 * hs + ix1], fy, fx);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    // margin: the float32 summation errs by < 2^-24 |s| at two scales and by < (n-1) * 2^-24 * n * max|v| per cell at
+    // n >= 3 (on both sides of the comparison: 1.5e-6 * max|v| at n = 4), the upsample's own rounding by 1e-16
+    thr = any_bad ? -INFINITY : __double2float_rd(v - (double)bamax * (1e-6 * ns));
+  }
+  // cells that may belong to the argmax's quad -> the (up to four) quads around each
+  if (act && tmax >= thr) {
+    for (int y = ro; y < hs; y += rpp) {
+      if (s_sum[y * hs + x] >= thr) {
+        for (int qy = max(y - 1, 0); qy <= y; ++qy)
+          for (int qx = max(x - 1, 0); qx <= x; ++qx) {
+            const int slot = atomicAdd(&s_nq, 1);
+            if (slot < kQuadCap) s_quads[slot] = (unsigned short)(qy * hs + qx);
+          }
+      }
+    }
   }
   __syncthreads();
-  double cell_best = -INFINITY, cell_amax = 0.0;
-  int cell_best_idx = 0;
-  int nonfinite = 0;
-  for (int y = warp_id; y < hs; y += kPostThreads / 32) {
-    for (int x = lane_id; x < hs; x += 32) {
-      double acc = 0.0;
-      for (int sc = 0; sc < p.n_scales; ++sc) {
-        const ScaleTable& T = p.tables[sc];
-        const float* m = s_raw + sc * cells;
+
+  // ---- D. exact float64 evaluation of the survivors (utils.py:153-175 on estimator.py:105-129's hm_avg)
+  auto exact_cell = [&](int y, int xx) -> double {
+    const int c = y * hs + xx;
+    double acc = 0.0;
+#pragma unroll
+    for (int sc = 0; sc < NS; ++sc) {
+      {
         float v;
-        if (T.identity) {
-          v = m[y * hs + x];
-        } else {  // cv2 float32 resize arithmetic: separate multiplies and adds
-          const float* r0 = m + T.j0[y] * hs;
-          const float* r1 = m + T.j1[y] * hs;
-          const int x0 = T.i0[x], x1 = T.i1[x];
-          const float a0 = T.a0[x], a1 = T.a1[x];
+        if ((idmask >> sc) & 1) {
+          // the staged plane of alias_scale now holds the sums: its raw value comes from L2
+          v = sc == p.alias_scale ? __ldg(p.maps + ((size_t)(frame * ns + sc) * 84 + joint) * cells + c)
+                                  : *reinterpret_cast<const float*>(pl[sc] + c * 4);
+        } else {
+          const ScaleTable& T = p.tables[sc];
+          const int4 rp = s_rowpk[sc][y];
+          const float* r0 = reinterpret_cast<const float*>(pl[sc] + rp.x);
+          const float* r1 = reinterpret_cast<const float*>(pl[sc] + rp.y);
+          const int x0 = T.i0[xx], x1 = T.i1[xx];
+          const float a0 = T.a0[xx], a1 = T.a1[xx];
           const float t0 = __fadd_rn(__fmul_rn(r0[x0], a0), __fmul_rn(r0[x1], a1));
           const float t1 = __fadd_rn(__fmul_rn(r1[x0], a0), __fmul_rn(r1[x1], a1));
-          v = __fadd_rn(__fmul_rn(t0, T.b0[y]), __fmul_rn(t1, T.b1[y]));
+          v = __fadd_rn(__fmul_rn(t0, __int_as_float(rp.z)), __fmul_rn(t1, __int_as_float(rp.w)));
         }
         acc = __dadd_rn(acc, (double)v);
       }
-      // hm_avg /= len(scales): for 1, 2 or 4 scales the quotient is an exact scaling, bit-identical to the division
-      const double a = p.n_scales == 1 ? acc : p.n_scales == 2 ? __dmul_rn(acc, 0.5) : p.n_scales == 4 ? __dmul_rn(acc, 0.25)
-                                                                                   : __ddiv_rn(acc, (double)p.n_scales);
-      s_avg[y * hs + x] = a;
-      if (a > cell_best) { cell_best = a; cell_best_idx = y * hs + x; }
-      cell_amax = fmax(cell_amax, fabs(a));
-      nonfinite |= !(fabs(a) <= 1.7976931348623157e308);  // NaN or Inf (fmax above would silently drop a NaN)
     }
-  }
-  // block-wide largest cell: its neighbourhood gives a lower bound L0 on the upsampled maximum, which prunes almost
-  // every candidate below (a candidate is a convex combination of its 4 cells, so it cannot beat L0 unless one of
-  // them does, up to rounding -- hence the relative margin)
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, cell_best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, cell_best_idx, o);
-    if (ov > cell_best) { cell_best = ov; cell_best_idx = oi; }
-    cell_amax = fmax(cell_amax, __shfl_xor_sync(0xffffffffu, cell_amax, o));
-  }
-  if (lane_id == 0) { s_val[warp_id] = cell_best; s_idx[warp_id] = cell_best_idx; s_amax[warp_id] = cell_amax; }
-  // fp16 activations overflow at 65504: an Inf / NaN anywhere in the CNN almost surely reaches the maps.  Count it (the
-  // host turns a non-zero count into an error) instead of returning joints computed from garbage.
-  if (__syncthreads_or(nonfinite) && tid == 0 && p.nonfinite != nullptr) atomicAdd(p.nonfinite, 1u);
-  {
-    cell_best = s_val[0]; cell_best_idx = s_idx[0]; cell_amax = s_amax[0];
-#pragma unroll
-    for (int w = 1; w < kPostThreads / 32; ++w) {
-      if (s_val[w] > cell_best) { cell_best = s_val[w]; cell_best_idx = s_idx[w]; }
-      cell_amax = fmax(cell_amax, s_amax[w]);
-    }
-  }
-  __syncthreads();  // s_val / s_idx are reused below
-
-  // ---- 2. argmax of the x8 bilinear upsample (utils.py:153-175), OpenCV+IPP arithmetic: fma(S1-S0, f, S0) per axis
-  auto eval = [&](int ky, int kx, double* v_out, int* idx_out) {
-    const int iy = s_ci[ky], ix = s_ci[kx];
-    const int iy1 = min(iy + 1, hs - 1), ix1 = min(ix + 1, hs - 1);
-    const double fy = (double)s_cf[ky], fx = (double)s_cf[kx];
-    const double s00 = s_avg[iy * hs + ix], s01 = s_avg[iy * hs + ix1];
-    const double s10 = s_avg[iy1 * hs + ix], s11 = s_avg[iy1 * hs + ix1];
-    const double h0 = __fma_rn(__dsub_rn(s01, s00), fx, s00);
-    const double h1 = __fma_rn(__dsub_rn(s11, s10), fx, s10);
-    *v_out = __fma_rn(__dsub_rn(h1, h0), fy, h0);
-    *idx_out = (int)s_cd[ky] * S + (int)s_cd[kx];
+    // hm_avg /= len(scales): for 1, 2 or 4 scales the quotient is an exact scaling, bit-identical to the division
+    return ns == 1 ? acc : ns == 2 ? __dmul_rn(acc, 0.5) : ns == 4 ? __dmul_rn(acc, 0.25) : __ddiv_rn(acc, (double)ns);
   };
   double best = -INFINITY;
   int best_idx = 0x7fffffff;
-  {  // seed: the 4 x 4 candidates around the largest cell (every thread computes the same bound, no sync needed)
-    const int r0 = cell_best_idx / hs, c0 = cell_best_idx - r0 * hs;
-    const int ky0 = max(2 * r0 - 1, 0), kx0 = max(2 * c0 - 1, 0);
-    const int ky = min(ky0 + (lane_id >> 2), nc - 1), kx = min(kx0 + (lane_id & 3), nc - 1);
-    double v = -INFINITY;
-    int idx = 0x7fffffff;
-    if (lane_id < 16) eval(ky, kx, &v, &idx);
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    best = __shfl_sync(0xffffffffu, v, 0);  // only a bound: the index is recovered by the full scan below
-  }
-  const double prune = best - cell_amax * 9.1e-13;  // 2^-40 of the largest |cell|: far above the FMAs' rounding
-  best = -INFINITY;
-  // scan by source quad (cells (qy, qy+1) x (qx, qx+1)): one max-of-4 test prunes all of the quad's candidates
-  // (axis candidates of cell 0: k = 0..2, of cell i: k = 2i+1, 2i+2, of the last cell: k = 2*hs-1)
-  for (int qy = warp_id; qy < hs; qy += kPostThreads / 32) {
-    const int qy1 = min(qy + 1, hs - 1);
+  // quad = cells (qy, qy+1) x (qx, qx+1), clamped; its axis candidates: cell 0: k = 0..2, cell i: k = 2i+1, 2i+2, the
+  // last cell: k = 2*hs-1
+  auto eval_quad = [&](int qy, int qx) {
+    const int qy1 = min(qy + 1, hs - 1), qx1 = min(qx + 1, hs - 1);
+    const double e00 = exact_cell(qy, qx);
+    const double e01 = qx1 == qx ? e00 : exact_cell(qy, qx1);
+    const double e10 = qy1 == qy ? e00 : exact_cell(qy1, qx);
+    const double e11 = qy1 == qy ? e01 : (qx1 == qx ? e10 : exact_cell(qy1, qx1));
     const int ky_lo = qy == 0 ? 0 : 2 * qy + 1, ky_hi = qy == hs - 1 ? nc - 1 : 2 * qy + 2;
-    for (int qx = lane_id; qx < hs; qx += 32) {
-      const int qx1 = min(qx + 1, hs - 1);
-      const double m4 = fmax(fmax(s_avg[qy * hs + qx], s_avg[qy * hs + qx1]), fmax(s_avg[qy1 * hs + qx], s_avg[qy1 * hs + qx1]));
-      if (m4 < prune) continue;
-      const int kx_lo = qx == 0 ? 0 : 2 * qx + 1, kx_hi = qx == hs - 1 ? nc - 1 : 2 * qx + 2;
-      for (int ky = ky_lo; ky <= ky_hi; ++ky)
-        for (int kx = kx_lo; kx <= kx_hi; ++kx) {
-          double v;
-          int idx;
-          eval(ky, kx, &v, &idx);
-          if (v > best || (v == best && idx < best_idx)) { best = v; best_idx = idx; }
-        }
+    const int kx_lo = qx == 0 ? 0 : 2 * qx + 1, kx_hi = qx == hs - 1 ? nc - 1 : 2 * qx + 2;
+    for (int ky = ky_lo; ky <= ky_hi; ++ky) {
+      int dy, iy;
+      double fy;
+      upsample_candidate(ky, hs, &dy, &iy, &fy);
+      for (int kx = kx_lo; kx <= kx_hi; ++kx) {
+        int dx, ix;
+        double fx;
+        upsample_candidate(kx, hs, &dx, &ix, &fx);
+        const double v = upsample_quad(e00, e01, e10, e11, fy, fx);
+        const int idx = dy * S + dx;
+        if (v > best || (v == best && idx < best_idx)) { best = v; best_idx = idx; }
+      }
+    }
+  };
+  const int nq = s_nq;
+  const bool one_warp = nq <= 32;  // the usual case: a handful of quads, all on warp 0 -- the others go straight to the barrier
+  if (nq <= kQuadCap) {
+    for (int i = tid; i < nq; i += nthreads) {
+      const int q = s_quads[i];
+      const int qy = q / hs;
+      eval_quad(qy, q - qy * hs);
+    }
+  } else if (act) {
+    for (int y = ro; y < hs; y += rpp) {
+      const int y1 = min(y + 1, hs - 1), x1 = min(x + 1, hs - 1);
+      const float m4 = fmaxf(fmaxf(s_sum[y * hs + x], s_sum[y * hs + x1]), fmaxf(s_sum[y1 * hs + x], s_sum[y1 * hs + x1]));
+      if (m4 >= thr) eval_quad(y, x);
     }
   }
+  if (!one_warp || warp_id == 0) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
-    if (ov > best || (ov == best && oi < best_idx)) { best = ov; best_idx = oi; }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_idx, o);
+      if (ov > best || (ov == best && oi < best_idx)) { best = ov; best_idx = oi; }
+    }
+    if (lane_id == 0) { s_bval[warp_id] = best; s_bidx[warp_id] = best_idx; }
   }
-  if ((tid & 31) == 0) { s_val[tid >> 5] = best; s_idx[tid >> 5] = best_idx; }
-  __syncthreads();
+  if (!one_warp) __syncthreads();  // block-uniform
 
-  // ---- 3. 2D filters, then the location-map gather at the FILTERED point (estimator.py:132-134)
+  // ---- E. 2D filters, then the location-map gather at the FILTERED point (estimator.py:132-134)
   if (tid < 32) {
-    best = s_val[0]; best_idx = s_idx[0];
-#pragma unroll
-    for (int w = 1; w < kPostThreads / 32; ++w)
-      if (s_val[w] > best || (s_val[w] == best && s_idx[w] < best_idx)) { best = s_val[w]; best_idx = s_idx[w]; }
+    if (!one_warp) {
+      best = s_bval[0]; best_idx = s_bidx[0];
+      for (int w = 1; w < nwarps; ++w)
+        if (s_bval[w] > best || (s_bval[w] == best && s_bidx[w] < best_idx)) { best = s_bval[w]; best_idx = s_bidx[w]; }
+    }
     const int row = best_idx / S, col = best_idx - row * S;
     double coord = (tid == 0) ? (double)row : (double)col;
     if (tid < 2) {
       p.raw_argmax[(frame * kJoints + joint) * 2 + tid] = (tid == 0) ? row : col;
       if (p.filters_on) {
-        FilterState st = p.st2d[((size_t)p.stream_ids[frame] * kJoints + joint) * 2 + tid];
-        coord = oef_step(st, p.cfg2d, coord, p.t2d[frame], false);
-        p.st2d[((size_t)p.stream_ids[frame] * kJoints + joint) * 2 + tid] = st;
+        FilterState st2 = s_st2[tid];
+        coord = oef_step(st2, p.cfg2d, coord, s_t2, false);
+        p.st2d[((size_t)s_sid * kJoints + joint) * 2 + tid] = st2;
       }
       p.j2_box[(frame * kJoints + joint) * 2 + tid] = coord;
     }
@@ -558,19 +736,18 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
   // and the dependent global loads dominated the kernel); the float64 arithmetic and its order are unchanged.
   {
     const double py = s_pt[0], px = s_pt[1];
-    const double sx = __dsub_rn(__ddiv_rn(__dadd_rn(px, 0.5), 8.0), 0.5);
-    const double sy = __dsub_rn(__ddiv_rn(__dadd_rn(py, 0.5), 8.0), 0.5);
+    const double sx = __dsub_rn(__dmul_rn(__dadd_rn(px, 0.5), 0.125), 0.5);  // / 8 exactly
+    const double sy = __dsub_rn(__dmul_rn(__dadd_rn(py, 0.5), 0.125), 0.5);
     int x0 = (int)sx, y0 = (int)sy;  // truncation toward zero, like int()
     x0 = min(max(x0, 0), hs - 1);    // memory safety only: filtered joints stay inside the box
     y0 = min(max(y0, 0), hs - 1);
     const int x1 = min(x0 + 1, hs - 1), y1 = min(y0 + 1, hs - 1);
-    const int items = 12 * p.n_scales;
+    const int items = 12 * ns;
     if (tid < items) {
-      const int sc = tid % p.n_scales;
-      const int cell = (tid / p.n_scales) & 3;
-      const int map = tid / (4 * p.n_scales);
-      const size_t plane = (size_t)hs * hs;
-      const float* m = p.maps + ((size_t)(frame * p.n_scales + sc) * 84 + kJoints * (1 + map) + joint) * plane;
+      const int sc = tid % ns;
+      const int cell = (tid / ns) & 3;
+      const int map = tid / (4 * ns);
+      const float* m = p.maps + ((size_t)(frame * ns + sc) * 84 + kJoints * (1 + map) + joint) * cells;
       const float gv = scaled_cell(m, hs, p.tables[sc], (cell & 2) ? y1 : y0, (cell & 1) ? x1 : x0);
       s_gather[tid] = gv;
       if (!(fabsf(gv) <= 3.4028234e38f) && p.nonfinite != nullptr) atomicAdd(p.nonfinite, 1u);
@@ -581,8 +758,9 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
 #pragma unroll
       for (int cell = 0; cell < 4; ++cell) {
         double acc = 0.0;
-        for (int sc = 0; sc < p.n_scales; ++sc) acc = __dadd_rn(acc, (double)s_gather[(tid * 4 + cell) * p.n_scales + sc]);
-        v[cell] = __ddiv_rn(acc, (double)p.n_scales);
+        for (int sc = 0; sc < ns; ++sc) acc = __dadd_rn(acc, (double)s_gather[(tid * 4 + cell) * ns + sc]);
+        // an exact scaling for 1, 2 or 4 scales, bit-identical to the division
+        v[cell] = ns == 1 ? acc : ns == 2 ? __dmul_rn(acc, 0.5) : ns == 4 ? __dmul_rn(acc, 0.25) : __ddiv_rn(acc, (double)ns);
       }
       const double wx1 = __dsub_rn((double)x1, sx), wx0 = __dsub_rn(sx, (double)x0);
       const double wy1 = __dsub_rn((double)y1, sy), wy0 = __dsub_rn(sy, (double)y0);
@@ -593,15 +771,16 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
     }
   }
 
-  // ---- 4. per-frame tail in the last block to arrive
+  // ---- per-frame tail in the last block to arrive
   __threadfence();
   __syncthreads();
   if (tid == 0) s_is_last = (atomicAdd(&p.frame_counter[frame], 1u) == kJoints - 1);
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
-  if (tid < kJoints * 3) {
-    const int j = tid / 3, c = tid - j * 3;
+  if (tid == 0) p.frame_counter[frame] = 0;  // ready for the next launch (no memset node between the conv and this kernel)
+  for (int i = tid; i < kJoints * 3; i += nthreads) {
+    const int j = i / 3, c = i - j * 3;
     const volatile float* raw = p.j3_raw + frame * kJoints * 3;
     float v = __fsub_rn(raw[j * 3 + c], raw[kRootJoint * 3 + c]);  // joints_3d -= joints_3d[14] (utils.py:218)
     if (p.filters_on) {
@@ -612,8 +791,8 @@ __global__ void __launch_bounds__(kPostThreads) postprocess_kernel(PostParams p)
     p.out3d[(frame * kJoints + j) * 3 + c] = v;
     if (p.packed != nullptr) p.packed[(frame * kJoints + j) * 5 + 2 + c] = (double)v;
   }
-  if (tid < kJoints * 2) {
-    const int j = tid >> 1, c = tid & 1;
+  for (int i = tid; i < kJoints * 2; i += nthreads) {
+    const int j = i >> 1, c = i & 1;
     const volatile double* jb = p.j2_box + frame * kJoints * 2;
     double off = (c == 0) ? (double)p.off_y : (double)p.off_x, scaler = p.scaler;  // estimator.py:138-139
     double v2 = 0.0;

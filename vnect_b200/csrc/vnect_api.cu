@@ -61,6 +61,7 @@ struct vnect_handle {
   uint8_t* d_sq = nullptr;
   float* d_f32_in = nullptr;  // vnect_forward staging [cap_fw][S][S][3]
   ScaleTable* d_tables = nullptr;
+  std::vector<ScaleTable> h_tables;  // host copy: the post-process block's shared-memory plan is derived from it
   PyramidTable* d_pyr_tables = nullptr;
   FilterState *d_st2d = nullptr, *d_st3d = nullptr;
   double* d_j2_box = nullptr;
@@ -536,8 +537,19 @@ static int build_tables(vnect_t* h) {
       T.j1[c] = (short)std::min(std::max(i + 1, 0), hs - 1);
       T.b0[c] = 1.f - f;
       T.b1[c] = f;
+      int b0_bits, b1_bits;
+      memcpy(&b0_bits, &T.b0[c], 4);
+      memcpy(&b1_bits, &T.b1[c], 4);
+      T.rowpk[c] = make_int4(T.j0[c] * hs, T.j1[c] * hs, b0_bits, b1_bits);
+    }
+    T.row_lo = hs - 1;
+    T.row_hi = 0;
+    for (int c = 0; c < hs; ++c) {
+      T.row_lo = std::min<int>(T.row_lo, T.j0[c]);
+      T.row_hi = std::max<int>(T.row_hi, T.j1[c]);
     }
   }
+  h->h_tables = t;
   return upload(h, t, &h->d_tables);
 }
 
@@ -954,26 +966,38 @@ static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, i
   p.out2d = dev_out2d; p.out3d = dev_out3d;
   p.packed = h->d_packed;
   p.nonfinite = guard ? h->d_nonfinite : nullptr;  // caller-supplied maps (vnect_postprocess) are taken as they are
-  CU(h, cudaMemsetAsync(h->d_counter, 0, n_frames * sizeof(unsigned int), h->stream));
-  // averaged plane (float64) + the raw plane of every scale (float32)
-  const size_t smem = (size_t)h->hs * h->hs * (sizeof(double) + h->n_scales * sizeof(float));
-  // threads per (frame, joint) block: every phase of the kernel is a short latency-bound chain, so wider blocks shorten
-  // it (VNECT_B200_POST_THREADS = 128 | 256 | 512 for A/B runs)
-  static const int threads = [] {
-    const char* e = getenv("VNECT_B200_POST_THREADS");
-    const int t = e ? atoi(e) : kPostThreadsDefault;
-    return (t == 128 || t == 256 || t == 512) ? t : kPostThreadsDefault;
+  post_smem_plan(p, h->h_tables.data());
+  // Threads per (frame, joint) block = the cells of `rows` heat-map rows.  A full batch is bound by instruction issue
+  // summed over all blocks (two rows: every lane busy at hs = 46); a few frames leave most SMs empty, so wider blocks
+  // shorten each block's own chain instead.  VNECT_B200_POST_ROWS overrides for A/B runs.
+  static const int rows_env = [] {
+    const char* e = getenv("VNECT_B200_POST_ROWS");
+    return e ? atoi(e) : 0;
   }();
-  static unsigned long long done128 = 0, done256 = 0, done512 = 0;
-  if (threads == 128) {
-    CU(h, ensure_dyn_smem(postprocess_kernel<128>, 96 * 1024, &done128));
-    CU(h, launch_pdl(postprocess_kernel<128>, dim3(n_frames * kJoints), dim3(128), smem, h->stream, p));
-  } else if (threads == 256) {
-    CU(h, ensure_dyn_smem(postprocess_kernel<256>, 96 * 1024, &done256));
-    CU(h, launch_pdl(postprocess_kernel<256>, dim3(n_frames * kJoints), dim3(256), smem, h->stream, p));
+  const int rows = rows_env > 0 ? rows_env : n_frames >= 48 ? 2 : n_frames >= 12 ? 4 : 8;
+  const int threads = post_threads(h->hs, rows);
+  const size_t smem = (size_t)p.smem_floats * sizeof(float);
+  static unsigned long long done[kMaxScales] = {0, 0, 0, 0};
+  auto launch = [&](auto kern, unsigned long long* mask) -> cudaError_t {
+    if (cudaError_t e = ensure_dyn_smem(kern, 96 * 1024, mask); e != cudaSuccess) return e;
+    return launch_pdl(kern, dim3(n_frames * kJoints), dim3(threads), smem, h->stream, p);
+  };
+  // the usual pyramid (scale 1.0 first, smaller ones after) gets its identity mask as a compile-time constant
+  static unsigned long long done1[kMaxScales] = {0, 0, 0, 0};
+  if (p.identity_mask == 1) {
+    switch (h->n_scales) {
+      case 1: CU(h, launch(postprocess_kernel<1, 1>, &done1[0])); break;
+      case 2: CU(h, launch(postprocess_kernel<2, 1>, &done1[1])); break;
+      case 3: CU(h, launch(postprocess_kernel<3, 1>, &done1[2])); break;
+      default: CU(h, launch(postprocess_kernel<4, 1>, &done1[3])); break;
+    }
   } else {
-    CU(h, ensure_dyn_smem(postprocess_kernel<512>, 96 * 1024, &done512));
-    CU(h, launch_pdl(postprocess_kernel<512>, dim3(n_frames * kJoints), dim3(512), smem, h->stream, p));
+    switch (h->n_scales) {
+      case 1: CU(h, launch(postprocess_kernel<1, -1>, &done[0])); break;
+      case 2: CU(h, launch(postprocess_kernel<2, -1>, &done[1])); break;
+      case 3: CU(h, launch(postprocess_kernel<3, -1>, &done[2])); break;
+      default: CU(h, launch(postprocess_kernel<4, -1>, &done[3])); break;
+    }
   }
   ++h->launches;
   return VNECT_OK;
