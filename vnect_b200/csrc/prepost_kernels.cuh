@@ -361,16 +361,19 @@ struct PostParams {
   int sum_off;                    // float32 plane of per-cell sums over the scales
   int alias_scale;                // the sums overwrite this (identity) scale's staged plane in place; -1: own plane
   int smem_floats;                // dynamic shared memory, in floats
+  int y_split;                    // the sum pass starts on rows [0, y_split) while the rest is still in flight
+  int plane_split[kMaxScales];    // staged cells (from plane_start) that rows [0, y_split) need
+  unsigned long long* trace;      // optional [blocks][16] globaltimer readings at the phase boundaries (VNECT_B200_POST_TRACE)
 };
 
 // Host side of the plan above.  `rows_lo/hi` per scale come from the ScaleTable.
-inline void post_smem_plan(PostParams& p, const ScaleTable* host_tables) {
+inline void post_smem_plan(PostParams& p, const ScaleTable* host_tables, int y_split) {
   const int cells = p.hs * p.hs;
   const bool vec = (cells & 3) == 0;  // 16-byte cp.async needs 16-byte aligned plane starts
   int off = 0;
   p.identity_mask = 0;
   p.alias_scale = -1;
-  for (int sc = 0; sc < kMaxScales; ++sc) { p.plane_start[sc] = p.plane_len[sc] = p.plane_off[sc] = 0; }
+  for (int sc = 0; sc < kMaxScales; ++sc) { p.plane_start[sc] = p.plane_len[sc] = p.plane_off[sc] = p.plane_split[sc] = 0; }
   for (int sc = 0; sc < p.n_scales; ++sc) {
     const ScaleTable& T = host_tables[sc];
     int start = 0, end = cells;
@@ -386,6 +389,15 @@ inline void post_smem_plan(PostParams& p, const ScaleTable* host_tables) {
     p.plane_start[sc] = start;
     p.plane_len[sc] = end - start;
     p.plane_off[sc] = off;
+    int split = end - start;
+    if (y_split > 0 && y_split < p.hs) {
+      const int last = T.identity ? y_split * p.hs : (T.j1[y_split - 1] + 1) * p.hs;  // first raw cell rows < y_split never read
+      split = last - start;
+      if (vec) split = (split + 3) & ~3;
+      if (split > end - start) split = end - start;
+      if (split < 0) split = 0;
+    }
+    p.plane_split[sc] = split;
     off += (end - start + 3) & ~3;
   }
   if (p.alias_scale >= 0) {
@@ -395,10 +407,12 @@ inline void post_smem_plan(PostParams& p, const ScaleTable* host_tables) {
     off += (cells + 3) & ~3;
   }
   p.smem_floats = off;
+  p.y_split = (y_split > 0 && y_split < p.hs) ? y_split : p.hs;
 }
 
 constexpr int kPostMaxThreads = 512;
 constexpr int kPostMaxWarps = kPostMaxThreads / 32;
+constexpr int kQuadPar = 32;   // up to this many: one thread per cell / per candidate
 constexpr int kQuadCap = 192;  // survivor quads kept in the list; more than that (flat maps) takes the full scan
 
 // threads per (frame, joint) block: `rows` heat-map rows per pass, one thread per cell of those rows
@@ -444,6 +458,42 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// The part of a 1-euro step that depends on the clock only (OneEuroFilter.py:64-67 and the derivative's alpha,
+// :69-70): it can run while the value is still being computed.  Same operations as oef_step, in the same order.
+struct FilterPrep { double freq, te, a_d; };
+__device__ __forceinline__ FilterPrep oef_prepare(const FilterState& st, const FilterCfg& cfg, double t) {
+  FilterPrep f;
+  f.freq = st.freq;
+  if (st.has_time && st.lasttime != 0.0 && t != 0.0) f.freq = __ddiv_rn(1.0, __dsub_rn(t, st.lasttime));
+  f.te = __ddiv_rn(1.0, f.freq);
+  const double tau = __ddiv_rn(1.0, __dmul_rn(6.283185307179586, cfg.dcutoff));
+  f.a_d = __ddiv_rn(1.0, __dadd_rn(1.0, __ddiv_rn(tau, f.te)));
+  return f;
+}
+__device__ __forceinline__ double oef_finish(FilterState& st, const FilterCfg& cfg, const FilterPrep& f, double x, double t,
+                                             bool x_is_f32) {
+  st.freq = f.freq;
+  st.lasttime = t;
+  st.has_time = 1;
+  double dx = 0.0;
+  if (st.has_prev) {
+    const double diff = x_is_f32 ? (double)__fsub_rn((float)x, (float)st.prev) : __dsub_rn(x, st.prev);
+    dx = __dmul_rn(diff, st.freq);
+  }
+  const double edx = st.has_prev ? __dadd_rn(__dmul_rn(f.a_d, dx), __dmul_rn(__dsub_rn(1.0, f.a_d), st.s_dx)) : dx;
+  const double cutoff = __dadd_rn(cfg.mincutoff, __dmul_rn(cfg.beta, fabs(edx)));
+  const double tau = __ddiv_rn(1.0, __dmul_rn(6.283185307179586, cutoff));
+  const double a = __ddiv_rn(1.0, __dadd_rn(1.0, __ddiv_rn(tau, f.te)));
+  const double sm = st.has_prev ? __dadd_rn(__dmul_rn(a, x), __dmul_rn(__dsub_rn(1.0, a), st.s_x)) : x;
+  st.prev = x;
+  st.s_x = sm;
+  st.s_dx = edx;
+  st.has_prev = 1;
+  return sm;
+}
 
 // grid = n_frames * 21 blocks; block (frame, joint), thread = one cell of the `rpp` heat-map rows a pass covers.
 //
@@ -460,6 +510,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //     (flat or saturated maps) every quad that passes the same test is scanned in place;
 //  E. 2D 1-euro filters, location-map gather at the FILTERED point, and -- in the last block of the frame to arrive --
 //     root subtraction, 3D filters and the rescale to input pixels.
+#define POST_TRACE(i) do { if (p.trace != nullptr && threadIdx.x == 0) p.trace[(size_t)blockIdx.x * 16 + (i)] = globaltimer_ns(); } while (0)
 template <int NS, int MASK>  // MASK >= 0: the identity mask (PostParams::identity_mask) is this compile-time constant
 __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const __grid_constant__ PostParams p) {
   extern __shared__ float4 s_dyn4[];
@@ -476,6 +527,8 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
   __shared__ int s_is_last;
   __shared__ __align__(16) FilterState s_st2[2];
   __shared__ double s_t2;
+  __shared__ double s_exact[kQuadPar * 4];
+  __shared__ double s_prep[2][3];
   __shared__ int s_sid;
 
   const int frame = blockIdx.x / kJoints;
@@ -489,6 +542,8 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
   const int rpp = nthreads / hs;          // rows per pass (host guarantees nthreads >= hs)
   const bool act = tid < rpp * hs;
   const int ro = tid / hs, x = tid - ro * hs;
+  POST_TRACE(0);
+  if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 16 + 11] = (unsigned long long)clock64();
 
   // per-thread column entries of the resize tables, the row entries to shared memory (static data: may be read before
   // the predecessor has finished)
@@ -512,39 +567,44 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
   if (tid == 0) s_nq = 0;
   pdl_launch_dependents();
   pdl_wait();  // the maps come from the last conv
+  POST_TRACE(1);
 
-  // ---- A. stage the planes
+  // ---- A. stage the planes, in two cp.async groups: what rows [0, y_split) of the sum pass read, then the rest
   const char* pl[NS];  // byte pointer such that pl[sc] + 4 * (absolute raw cell) is that cell
 #pragma unroll
-  for (int sc = 0; sc < NS; ++sc) {
-    const float* g = p.maps + ((size_t)(frame * ns + sc) * 84 + joint) * cells + p.plane_start[sc];
-    float* d = s_dyn + p.plane_off[sc];
-    const int len = p.plane_len[sc];
-    if ((cells & 3) == 0) {
-      for (int i = tid * 4; i < len; i += nthreads * 4) cp_async_16(d + i, g + i);
-    } else {
-      for (int i = tid; i < len; i += nthreads) d[i] = __ldg(g + i);
+  for (int part = 0; part < 2; ++part) {
+#pragma unroll
+    for (int sc = 0; sc < NS; ++sc) {
+      const float* g = p.maps + ((size_t)(frame * ns + sc) * 84 + joint) * cells + p.plane_start[sc];
+      float* d = s_dyn + p.plane_off[sc];
+      const int lo = part == 0 ? 0 : p.plane_split[sc], hi = part == 0 ? p.plane_split[sc] : p.plane_len[sc];
+      if ((cells & 3) == 0) {
+        for (int i = lo + tid * 4; i < hi; i += nthreads * 4) cp_async_16(d + i, g + i);
+      } else {
+        for (int i = lo + tid; i < hi; i += nthreads) d[i] = __ldg(g + i);
+      }
+      pl[sc] = reinterpret_cast<const char*>(d - p.plane_start[sc]);
     }
-    pl[sc] = reinterpret_cast<const char*>(d - p.plane_start[sc]);
+    if (part == 0) {
+      // the two 2D filters of this joint: state fetched now, used after the argmax
+      static_assert(sizeof(FilterState) == 48, "three 16-byte pieces per filter state");
+      if (tid < 6 && p.filters_on) {
+        const int sid = p.stream_ids[frame];
+        cp_async_16(reinterpret_cast<char*>(s_st2) + tid * 16,
+                    reinterpret_cast<const char*>(p.st2d + ((size_t)sid * kJoints + joint) * 2) + tid * 16);
+        if (tid == 0) { s_sid = sid; s_t2 = p.t2d[frame]; }
+      }
+    }
+    cp_async_commit();
   }
-  // the two 2D filters of this joint: state fetched now, used after the argmax
-  static_assert(sizeof(FilterState) == 48, "three 16-byte pieces per filter state");
-  if (tid < 6 && p.filters_on) {
-    const int sid = p.stream_ids[frame];
-    cp_async_16(reinterpret_cast<char*>(s_st2) + tid * 16,
-                reinterpret_cast<const char*>(p.st2d + ((size_t)sid * kJoints + joint) * 2) + tid * 16);
-    if (tid == 0) { s_sid = sid; s_t2 = p.t2d[frame]; }
-  }
-  cp_async_wait_all();
-  __syncthreads();
 
   // ---- B. float32 sums over the scales (estimator.py:105-129 in float32), largest cell
   float* s_sum = s_dyn + p.sum_off;
   float tmax = -INFINITY, tmin = INFINITY, tvmax = 0.f, chk = 0.f;
   int ty = 0;
-  if (act) {
+  auto sum_rows = [&](int y_begin, int y_end) {  // y_begin is a multiple of rpp
 #pragma unroll 2
-    for (int y = ro; y < hs; y += rpp) {
+    for (int y = y_begin + ro; y < y_end; y += rpp) {
       const int cb = (y * hs + x) * 4;
       float s = 0.f;
 #pragma unroll
@@ -570,8 +630,16 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
       if (s > tmax) { tmax = s; ty = y; }
       tmin = fminf(tmin, s);
     }
-  }
+  };
+  cp_async_wait_but_one();
+  __syncthreads();
+  POST_TRACE(2);
+  if (act) sum_rows(0, p.y_split);
+  cp_async_wait_all();
+  __syncthreads();
+  if (act) sum_rows(p.y_split, hs);
   const int bad = chk != chk;
+  POST_TRACE(3);
   float bmax = tmax, bmin = tmin, bvmax = tvmax;
   int bidx = ty * hs + x;
 #pragma unroll
@@ -594,6 +662,7 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
     bvmax = fmaxf(bvmax, s_wamax[w]);
   }
   const float bamax = fmaxf(fmaxf(fabsf(bmax), fabsf(bmin)), bvmax);  // largest |s| (and |v| for three or more scales)
+  POST_TRACE(4);
 
   // ---- C. bound from the 4 x 4 candidates around the largest cell (every warp computes the same value)
   float thr;
@@ -616,17 +685,22 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
   }
   // cells that may belong to the argmax's quad -> the (up to four) quads around each
   if (act && tmax >= thr) {
-    for (int y = ro; y < hs; y += rpp) {
-      if (s_sum[y * hs + x] >= thr) {
-        for (int qy = max(y - 1, 0); qy <= y; ++qy)
-          for (int qx = max(x - 1, 0); qx <= x; ++qx) {
-            const int slot = atomicAdd(&s_nq, 1);
-            if (slot < kQuadCap) s_quads[slot] = (unsigned short)(qy * hs + qx);
-          }
-      }
+    unsigned long long rows = 0;  // bit k: this thread's k-th cell passes (hs <= 64 rows)
+    int k = 0;
+#pragma unroll 4
+    for (int y = ro; y < hs; y += rpp, ++k) rows |= (unsigned long long)(s_sum[y * hs + x] >= thr) << k;
+    while (rows) {
+      const int y = ro + (__ffsll((long long)rows) - 1) * rpp;
+      rows &= rows - 1;
+      for (int qy = max(y - 1, 0); qy <= y; ++qy)
+        for (int qx = max(x - 1, 0); qx <= x; ++qx) {
+          const int slot = atomicAdd(&s_nq, 1);
+          if (slot < kQuadCap) s_quads[slot] = (unsigned short)(qy * hs + qx);
+        }
     }
   }
   __syncthreads();
+  POST_TRACE(5);
 
   // ---- D. exact float64 evaluation of the survivors (utils.py:153-175 on estimator.py:105-129's hm_avg)
   auto exact_cell = [&](int y, int xx) -> double {
@@ -684,8 +758,37 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
     }
   };
   const int nq = s_nq;
-  const bool one_warp = nq <= 32;  // the usual case: a handful of quads, all on warp 0 -- the others go straight to the barrier
-  if (nq <= kQuadCap) {
+  const bool one_warp = nq <= kQuadPar;  // the usual case: a handful of quads
+  if (one_warp) {
+    // every cell of every surviving quad on its own thread, then every candidate on its own lane of warp 0; meanwhile
+    // two lanes of warp 1 advance the clock-only part of this joint's 2D filters
+    for (int i = tid; i < nq * 4; i += nthreads) {
+      const int q = s_quads[i >> 2];
+      const int qy = q / hs, qx = q - qy * hs;
+      s_exact[i] = exact_cell(min(qy + ((i >> 1) & 1), hs - 1), min(qx + (i & 1), hs - 1));
+    }
+    if (p.filters_on && tid >= 32 && tid < 34) {
+      const FilterPrep f = oef_prepare(s_st2[tid - 32], p.cfg2d, s_t2);
+      s_prep[tid - 32][0] = f.freq; s_prep[tid - 32][1] = f.te; s_prep[tid - 32][2] = f.a_d;
+    }
+    __syncthreads();
+    if (warp_id == 0) {
+      for (int i = lane_id; i < nq * 9; i += 32) {
+        const int qi = i / 9, slot = i - qi * 9;
+        const int q = s_quads[qi];
+        const int qy = q / hs, qx = q - qy * hs;
+        const int ky = (qy == 0 ? 0 : 2 * qy + 1) + slot / 3, kx = (qx == 0 ? 0 : 2 * qx + 1) + slot % 3;
+        if (ky > (qy == hs - 1 ? nc - 1 : 2 * qy + 2) || kx > (qx == hs - 1 ? nc - 1 : 2 * qx + 2)) continue;
+        int dy, dx, iy, ix;
+        double fy, fx;
+        upsample_candidate(ky, hs, &dy, &iy, &fy);
+        upsample_candidate(kx, hs, &dx, &ix, &fx);
+        const double v = upsample_quad(s_exact[qi * 4], s_exact[qi * 4 + 1], s_exact[qi * 4 + 2], s_exact[qi * 4 + 3], fy, fx);
+        const int idx = dy * S + dx;
+        if (v > best || (v == best && idx < best_idx)) { best = v; best_idx = idx; }
+      }
+    }
+  } else if (nq <= kQuadCap) {
     for (int i = tid; i < nq; i += nthreads) {
       const int q = s_quads[i];
       const int qy = q / hs;
@@ -708,6 +811,7 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
     if (lane_id == 0) { s_bval[warp_id] = best; s_bidx[warp_id] = best_idx; }
   }
   if (!one_warp) __syncthreads();  // block-uniform
+  POST_TRACE(6);
 
   // ---- E. 2D filters, then the location-map gather at the FILTERED point (estimator.py:132-134)
   if (tid < 32) {
@@ -722,13 +826,19 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
       p.raw_argmax[(frame * kJoints + joint) * 2 + tid] = (tid == 0) ? row : col;
       if (p.filters_on) {
         FilterState st2 = s_st2[tid];
-        coord = oef_step(st2, p.cfg2d, coord, s_t2, false);
+        if (one_warp) {
+          const FilterPrep f = {s_prep[tid][0], s_prep[tid][1], s_prep[tid][2]};
+          coord = oef_finish(st2, p.cfg2d, f, coord, s_t2, false);
+        } else {
+          coord = oef_step(st2, p.cfg2d, coord, s_t2, false);
+        }
         p.st2d[((size_t)s_sid * kJoints + joint) * 2 + tid] = st2;
       }
       p.j2_box[(frame * kJoints + joint) * 2 + tid] = coord;
     }
     const double py = __shfl_sync(0xffffffffu, coord, 0), px = __shfl_sync(0xffffffffu, coord, 1);
     if (tid == 0) { s_pt[0] = py; s_pt[1] = px; }
+    POST_TRACE(7);
   }
   __syncthreads();
   // utils.hm_pt_interp_bilinear (utils.py:58-79) on the three averaged location maps.  The 3 maps x 4 cells x n_scales
@@ -772,10 +882,12 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
   }
 
   // ---- per-frame tail in the last block to arrive
+  POST_TRACE(8);
   __threadfence();
   __syncthreads();
   if (tid == 0) s_is_last = (atomicAdd(&p.frame_counter[frame], 1u) == kJoints - 1);
   __syncthreads();
+  POST_TRACE(9);
   if (!s_is_last) return;
   __threadfence();
   if (tid == 0) p.frame_counter[frame] = 0;  // ready for the next launch (no memset node between the conv and this kernel)
@@ -808,7 +920,10 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
     p.out2d[(frame * kJoints + j) * 2 + c] = v2;
     if (p.packed != nullptr) p.packed[(frame * kJoints + j) * 5 + c] = v2;
   }
+  POST_TRACE(10);
+  if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 16 + 12] = (unsigned long long)clock64();
 }
+#undef POST_TRACE
 
 // Bounding-box tracker of the reference's video loop (run_estimator.py:110-119), one warp per frame:
 //   buffer_x = 0.8 * (x_max - x_min + 1);  buffer_y = 0.2 * (y_max - y_min + 1)

@@ -61,6 +61,7 @@ struct vnect_handle {
   uint8_t* d_sq = nullptr;
   float* d_f32_in = nullptr;  // vnect_forward staging [cap_fw][S][S][3]
   ScaleTable* d_tables = nullptr;
+  unsigned long long* d_post_trace = nullptr;  // VNECT_B200_POST_TRACE=1: phase timestamps of the last post-process launch
   std::vector<ScaleTable> h_tables;  // host copy: the post-process block's shared-memory plan is derived from it
   PyramidTable* d_pyr_tables = nullptr;
   FilterState *d_st2d = nullptr, *d_st3d = nullptr;
@@ -589,6 +590,7 @@ static int alloc_prepost(vnect_t* h) {
   if ((rc = dev_alloc(h, &h->d_j3_raw, (size_t)mf * kJoints * 3))) return rc;
   if ((rc = dev_alloc(h, &h->d_raw_argmax, (size_t)mf * kJoints * 2))) return rc;
   if ((rc = dev_alloc(h, &h->d_counter, mf))) return rc;
+  if (getenv("VNECT_B200_POST_TRACE") && (rc = dev_alloc(h, &h->d_post_trace, (size_t)mf * kJoints * 16))) return rc;
   if ((rc = dev_alloc(h, &h->d_filter_scratch, 64))) return rc;
   if ((rc = dev_alloc(h, &h->d_st_ang, (size_t)ms * 8))) return rc;
   if ((rc = dev_alloc(h, &h->d_ang_in, (size_t)mf * kJoints * 3))) return rc;
@@ -966,7 +968,6 @@ static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, i
   p.out2d = dev_out2d; p.out3d = dev_out3d;
   p.packed = h->d_packed;
   p.nonfinite = guard ? h->d_nonfinite : nullptr;  // caller-supplied maps (vnect_postprocess) are taken as they are
-  post_smem_plan(p, h->h_tables.data());
   // Threads per (frame, joint) block = the cells of `rows` heat-map rows.  A full batch is bound by instruction issue
   // summed over all blocks (two rows: every lane busy at hs = 46); a few frames leave most SMs empty, so wider blocks
   // shorten each block's own chain instead.  VNECT_B200_POST_ROWS overrides for A/B runs.
@@ -976,6 +977,9 @@ static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, i
   }();
   const int rows = rows_env > 0 ? rows_env : n_frames >= 48 ? 2 : n_frames >= 12 ? 4 : 8;
   const int threads = post_threads(h->hs, rows);
+  const int rpp = threads / h->hs;
+  post_smem_plan(p, h->h_tables.data(), (h->hs / 2 / rpp) * rpp);
+  p.trace = h->d_post_trace;
   const size_t smem = (size_t)p.smem_floats * sizeof(float);
   static unsigned long long done[kMaxScales] = {0, 0, 0, 0};
   auto launch = [&](auto kern, unsigned long long* mask) -> cudaError_t {
@@ -1636,6 +1640,64 @@ int vnect_time_prepost(vnect_t* h, int32_t n_frames, int32_t reps, float* pre_ms
     CU(h, cudaEventSynchronize(e1));
     CU(h, cudaEventElapsedTime(&ms, e0, e1));
     if (r >= 0) post += ms;
+  }
+  if (h->d_post_trace) {  // developer diagnostics: where a (frame, joint) block of the last launch spent its time
+    const int nb = n_frames * kJoints;
+    std::vector<unsigned long long> tr((size_t)nb * 16);
+    CU(h, cudaMemcpy(tr.data(), h->d_post_trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull, t1 = 0;
+    for (int b = 0; b < nb; ++b) { t0 = std::min(t0, tr[(size_t)b * 16]); for (int k = 0; k <= 10; ++k) t1 = std::max(t1, tr[(size_t)b * 16 + k]); }
+    static const char* names[] = {"start", "pdl_wait", "staged", "sum pass", "reduced", "marked", "exact+reduce", "2D filter", "gather", "fence+atomic", "tail"};
+    fprintf(stderr, "post-process trace (%d blocks, kernel span %.2f us): phase end relative to the block's start, mean / max us; block start spread %.2f us\n",
+            nb, (t1 - t0) * 1e-3, 0.0);
+    double start_max = 0;
+    for (int b = 0; b < nb; ++b) start_max = std::max(start_max, (tr[(size_t)b * 16] - t0) * 1e-3);
+    fprintf(stderr, "  last block started %.2f us after the first\n", start_max);
+    for (int b = 0; b < nb; ++b)
+      if (tr[(size_t)b * 16 + 10] > tr[(size_t)b * 16]) {  // a block that ran the tail: SM cycles per ns over its lifetime
+        fprintf(stderr, "  SM clock during the kernel: %.0f MHz\n",
+                1e3 * (double)(tr[(size_t)b * 16 + 12] - tr[(size_t)b * 16 + 11]) / (double)(tr[(size_t)b * 16 + 10] - tr[(size_t)b * 16]));
+        break;
+      }
+    for (int k = 1; k <= 10; ++k) {
+      double sum = 0, mx = 0; int cnt = 0;
+      for (int b = 0; b < nb; ++b) {
+        const unsigned long long v = tr[(size_t)b * 16 + k], s0 = tr[(size_t)b * 16];
+        if (v < s0 || v > t1) continue;  // stale slot (tail runs in one block per frame)
+        if (k == 10 && v < tr[(size_t)b * 16 + 9]) continue;
+        sum += (v - s0) * 1e-3; mx = std::max(mx, (v - s0) * 1e-3); ++cnt;
+      }
+      fprintf(stderr, "  %-14s %7.2f / %7.2f us  (%d blocks)\n", names[k], cnt ? sum / cnt : 0.0, mx, cnt);
+    }
+  }
+  if (h->d_post_trace) {  // developer diagnostics: where a (frame, joint) block of the last launch spent its time
+    const int nb = n_frames * kJoints;
+    std::vector<unsigned long long> tr((size_t)nb * 16);
+    CU(h, cudaMemcpy(tr.data(), h->d_post_trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull, t1 = 0;
+    for (int b = 0; b < nb; ++b) { t0 = std::min(t0, tr[(size_t)b * 16]); for (int k = 0; k <= 10; ++k) t1 = std::max(t1, tr[(size_t)b * 16 + k]); }
+    static const char* names[] = {"start", "pdl_wait", "staged", "sum pass", "reduced", "marked", "exact+reduce", "2D filter", "gather", "fence+atomic", "tail"};
+    fprintf(stderr, "post-process trace (%d blocks, kernel span %.2f us): phase end relative to the block's start, mean / max us; block start spread %.2f us\n",
+            nb, (t1 - t0) * 1e-3, 0.0);
+    double start_max = 0;
+    for (int b = 0; b < nb; ++b) start_max = std::max(start_max, (tr[(size_t)b * 16] - t0) * 1e-3);
+    fprintf(stderr, "  last block started %.2f us after the first\n", start_max);
+    for (int b = 0; b < nb; ++b)
+      if (tr[(size_t)b * 16 + 10] > tr[(size_t)b * 16]) {  // a block that ran the tail: SM cycles per ns over its lifetime
+        fprintf(stderr, "  SM clock during the kernel: %.0f MHz\n",
+                1e3 * (double)(tr[(size_t)b * 16 + 12] - tr[(size_t)b * 16 + 11]) / (double)(tr[(size_t)b * 16 + 10] - tr[(size_t)b * 16]));
+        break;
+      }
+    for (int k = 1; k <= 10; ++k) {
+      double sum = 0, mx = 0; int cnt = 0;
+      for (int b = 0; b < nb; ++b) {
+        const unsigned long long v = tr[(size_t)b * 16 + k], s0 = tr[(size_t)b * 16];
+        if (v < s0 || v > t1) continue;  // stale slot (tail runs in one block per frame)
+        if (k == 10 && v < tr[(size_t)b * 16 + 9]) continue;
+        sum += (v - s0) * 1e-3; mx = std::max(mx, (v - s0) * 1e-3); ++cnt;
+      }
+      fprintf(stderr, "  %-14s %7.2f / %7.2f us  (%d blocks)\n", names[k], cnt ? sum / cnt : 0.0, mx, cnt);
+    }
   }
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
