@@ -169,77 +169,152 @@ constexpr int kMaxBox = 512;
 // once on the host with the same arithmetic as cv_linear_coord / cv_coef (the scales are fixed at vnect_create).
 struct PyramidTable {
   short4 xt[kMaxBox];  // x axis (index clamp + f reset): .x/.y = byte offsets of the two source pixels, .z/.w = weights
-  short yj0[kMaxBox], yj1[kMaxBox], yb0[kMaxBox], yb1[kMaxBox];  // y axis: rows clamped, f kept
+  short4 yt[kMaxBox];  // y axis (rows clamped, f kept): .x/.y = the two source rows, .z/.w = weights
 };
+
+constexpr int kPyrRows = 8;       // output rows per block
+constexpr int kPyrThreads = 256;
 
 struct PyramidParams {
   int n_frames, S, n_scales;
   int64_t sq_pitch, sq_frame_stride;  // square u8 input (may alias the raw frames when they are already S x S)
   int R[kMaxScales];                  // resized side cvRound(S*s); == S for s >= 1 (identity)
   int pad0[kMaxScales];               // (S - R) / 2
+  unsigned int r_magic[kMaxScales];   // floor(2^32 / R) + 1: i / R == umulhi(i, r_magic) for the indices used here
   double inv_scale[kMaxScales];       // 1 / s
   const PyramidTable* tables;         // [n_scales], device
+  const __half* lut;                  // [256]: fp16(float32(v) / 255 - 0.4) for every 8-bit value
   // stem layout: [forward][parity][rows_per_parity][row_pitch] halves, pixel (y, x) lives at padded (y+2, x+2)
   int rows_per_parity, row_pitch;
+  int full;                           // also write the black surround of the shrunken scales (see below)
+  int src_row_bytes;                  // S * 3 rounded up to 16: pitch of the staged source rows
 };
 
 // estimator.gen_input_batch (estimator.py:70-81): per scale shrink + zero pad (utils.py:123-150), then
 // float32(u8)/255 - 0.4, stored as fp16 in the parity-split padded NHWC4 layout the stem conv's TMA reads.
-// grid = (S rows, n_frames * n_scales forwards): one block per output row, so there is no per-pixel index division
-// (the first version spent ~230 instructions per pixel, mostly 64-bit div/mod, and was issue-bound at 140 us/batch;
-// staging the source rows in shared memory was tried and measured slower: 102 us vs 87 us).
-__global__ void __launch_bounds__(128) pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restrict__ x1,
-                                                      const __grid_constant__ PyramidParams p) {
+//
+// grid = (ceil(S / 8), n_frames * n_scales forwards); a block writes 8 output rows of one forward.
+//  * scale 1: pure conversion, four pixels (12 source bytes as three aligned words, 32 output bytes) per thread;
+//  * shrunken scale: only the R x R picture is computed.  Its black surround is the same constant for every frame
+//    (fp16(0/255 - 0.4)), lives in a slot of x1 that always holds this scale, and is therefore written ONCE
+//    (`full`, at start-up and after vnect_forward has overwritten the buffer): 51 % of a 0.7-scale forward's bytes.
+//    The source rows the block's 8 output rows sample (~8/s + 2) are staged in shared memory with 16-byte loads, so
+//    the 12 taps of a pixel are shared-memory byte loads and every source byte leaves L2 once per block.
+//  * the normalisation is a 256-entry table built on the host (an IEEE division per channel was a third of the first
+//    version's instructions; rebuilding the table in every block was most of the second's).
+__global__ void __launch_bounds__(kPyrThreads) pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restrict__ x1,
+                                                              const __grid_constant__ PyramidParams p) {
+  extern __shared__ __align__(16) uint8_t s_rows[];
+  __shared__ __align__(4) __half s_lut[256];
   pdl_launch_dependents();
-  // float32(v)/255 - 0.4 -> fp16 for every 8-bit value, once per block: the IEEE division per channel was a third of
-  // the kernel's instructions.
-  __shared__ __half norm_lut[256];
-  for (int v = threadIdx.x; v < 256; v += blockDim.x)
-    norm_lut[v] = __float2half_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), 0.4f));
-  __syncthreads();
-  pdl_wait();  // x1 may still be read by the previous batch's stem kernel
-  const int y = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid < 128) reinterpret_cast<uint32_t*>(s_lut)[tid] = reinterpret_cast<const uint32_t*>(p.lut)[tid];
+  pdl_wait();  // x1 may still be read by the previous batch's stem kernel; sq comes from the copy / squarify before us
+  const int S = p.S;
   const int fwd = blockIdx.y;
   const int frame = fwd / p.n_scales, si = fwd - frame * p.n_scales;
   const int R = p.R[si], pad0 = p.pad0[si];
-  const PyramidTable* __restrict__ T = p.tables + si;
   const uint8_t* src = sq + (int64_t)frame * p.sq_frame_stride;
-  const int pr = y + 2;
-  __half* orow = x1 + (((int64_t)fwd * 2 + (pr & 1)) * p.rows_per_parity + (pr >> 1)) * p.row_pitch + 8;  // pc = x + 2
-  const bool identity = (R == p.S);
-  const int ry = y - pad0;
-  const bool row_in = identity || (ry >= 0 && ry < R);
-  int b0 = 0, b1 = 0;
-  const uint8_t *r0 = src + (int64_t)y * p.sq_pitch, *r1 = r0;
-  if (!identity && row_in) {
-    b0 = T->yb0[ry];
-    b1 = T->yb1[ry];
-    r0 = src + (int64_t)T->yj0[ry] * p.sq_pitch;
-    r1 = src + (int64_t)T->yj1[ry] * p.sq_pitch;
+  const int y0 = blockIdx.x * kPyrRows, y1 = min(y0 + kPyrRows, S);
+  // output row y starts at padded row y + 2, padded column 2 (8 halves)
+  auto out_row = [&](int y) -> __half* {
+    const int pr = y + 2;
+    return x1 + (((int64_t)fwd * 2 + (pr & 1)) * p.rows_per_parity + (pr >> 1)) * p.row_pitch + 8;
+  };
+  auto lut2 = [&](uint32_t a, uint32_t b) -> uint32_t {  // two table entries packed
+    return (uint32_t)__half_as_ushort(s_lut[a]) | ((uint32_t)__half_as_ushort(s_lut[b]) << 16);
+  };
+  __syncthreads();
+  if (R == S) {
+    const int qpr = S >> 2;  // 4-pixel groups per row (S is a multiple of 16)
+    const int nq = (y1 - y0) * qpr;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)p.sq_pitch) & 3) == 0;
+    for (int q = tid; q < nq; q += kPyrThreads) {
+      const int ly = q / qpr, qx = q - ly * qpr;
+      const uint8_t* s = src + (int64_t)(y0 + ly) * p.sq_pitch + qx * 12;
+      uint32_t w0, w1, w2;
+      if (aligned) {
+        w0 = __ldg(reinterpret_cast<const uint32_t*>(s));
+        w1 = __ldg(reinterpret_cast<const uint32_t*>(s) + 1);
+        w2 = __ldg(reinterpret_cast<const uint32_t*>(s) + 2);
+      } else {
+        w0 = s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24);
+        w1 = s[4] | (s[5] << 8) | (s[6] << 16) | ((uint32_t)s[7] << 24);
+        w2 = s[8] | (s[9] << 8) | (s[10] << 16) | ((uint32_t)s[11] << 24);
+      }
+      const uint32_t zero = (uint32_t)__half_as_ushort(__float2half_rn(0.f)) << 16;
+      uint4 o0, o1;
+      o0.x = lut2(w0 & 0xff, (w0 >> 8) & 0xff);
+      o0.y = (uint32_t)__half_as_ushort(s_lut[(w0 >> 16) & 0xff]) | zero;
+      o0.z = lut2(w0 >> 24, w1 & 0xff);
+      o0.w = (uint32_t)__half_as_ushort(s_lut[(w1 >> 8) & 0xff]) | zero;
+      o1.x = lut2((w1 >> 16) & 0xff, w1 >> 24);
+      o1.y = (uint32_t)__half_as_ushort(s_lut[w2 & 0xff]) | zero;
+      o1.z = lut2((w2 >> 8) & 0xff, (w2 >> 16) & 0xff);
+      o1.w = (uint32_t)__half_as_ushort(s_lut[w2 >> 24]) | zero;
+      uint4* o = reinterpret_cast<uint4*>(out_row(y0 + ly) + qx * 16);
+      o[0] = o0;
+      o[1] = o1;
+    }
+    return;
   }
-  for (int x = threadIdx.x; x < p.S; x += blockDim.x) {
-    int v[3] = {0, 0, 0};
-    if (identity) {
-      const uint8_t* q = r0 + x * 3;
-      v[0] = q[0]; v[1] = q[1]; v[2] = q[2];
+  const PyramidTable* __restrict__ T = p.tables + si;
+  const int ry0 = max(y0, pad0) - pad0, ry1 = min(y1, pad0 + R) - pad0;  // picture rows of this block
+  if (ry0 < ry1) {
+    // stage the source rows [s_lo, s_hi] (the row entries are non-decreasing)
+    const int s_lo = T->yt[ry0].x, s_hi = T->yt[ry1 - 1].y;
+    const int rb = p.src_row_bytes;
+    const uint8_t* g0 = src + (int64_t)s_lo * p.sq_pitch;
+    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)p.sq_pitch) & 15) == 0) {
+      const int vpr = rb >> 4;
+      const int nv = (s_hi - s_lo + 1) * vpr;
+      for (int i = tid; i < nv; i += kPyrThreads) {
+        const int r = i / vpr, c = i - r * vpr;
+        *reinterpret_cast<uint4*>(s_rows + r * rb + c * 16) = __ldg(reinterpret_cast<const uint4*>(g0 + (int64_t)r * p.sq_pitch) + c);
+      }
     } else {
-      const int rx = x - pad0;
-      if (row_in && rx >= 0 && rx < R) {
-        const short4 xt = T->xt[rx];
-        const int o0 = xt.x, o1 = xt.y, a0 = xt.z, a1 = xt.w;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int t0 = r0[o0 + c] * a0 + r0[o1 + c] * a1;
-          const int t1 = r1[o0 + c] * a0 + r1[o1 + c] * a1;
-          v[c] = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
-        }
+      const int nb = (s_hi - s_lo + 1) * S * 3;
+      for (int i = tid; i < nb; i += kPyrThreads) {
+        const int r = i / (S * 3), c = i - r * (S * 3);
+        s_rows[r * rb + c] = g0[(int64_t)r * p.sq_pitch + c];
       }
     }
-    __half h[4];
+    __syncthreads();
+    const int npx = (ry1 - ry0) * R;
+    const unsigned int magic = p.r_magic[si];
+    for (int i = tid; i < npx; i += kPyrThreads) {
+      const int ly = (int)__umulhi((unsigned int)i, magic);
+      const int rx = i - ly * R, ry = ry0 + ly;
+      const short4 yt = T->yt[ry];
+      const short4 xt = T->xt[rx];
+      const uint8_t* r0 = s_rows + (yt.x - s_lo) * rb;
+      const uint8_t* r1 = s_rows + (yt.y - s_lo) * rb;
+      const int o0 = xt.x, o1 = xt.y, a0 = xt.z, a1 = xt.w;
+      // (b * (t >> 4)) >> 16 as the high word of (b << 16) * (t >> 4): all operands are non-negative
+      const unsigned int b0 = (unsigned int)yt.z << 16, b1 = (unsigned int)yt.w << 16;
+      uint32_t v[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) h[c] = norm_lut[v[c]];
-    h[3] = __float2half_rn(0.f);
-    *reinterpret_cast<uint2*>(orow + x * 4) = *reinterpret_cast<const uint2*>(h);
+      for (int c = 0; c < 3; ++c) {
+        const int t0 = r0[o0 + c] * a0 + r0[o1 + c] * a1;
+        const int t1 = r1[o0 + c] * a0 + r1[o1 + c] * a1;
+        v[c] = (__umulhi(b0, (unsigned int)(t0 >> 4)) + __umulhi(b1, (unsigned int)(t1 >> 4)) + 2u) >> 2;
+      }
+      uint2 o;
+      o.x = lut2(v[0], v[1]);
+      o.y = (uint32_t)__half_as_ushort(s_lut[v[2]]) | ((uint32_t)__half_as_ushort(__float2half_rn(0.f)) << 16);
+      *reinterpret_cast<uint2*>(out_row(ry + pad0) + (rx + pad0) * 4) = o;
+    }
+  }
+  if (p.full) {  // the black surround: float32(0) / 255 - 0.4
+    uint2 o;
+    o.x = lut2(0, 0);
+    o.y = (uint32_t)__half_as_ushort(s_lut[0]) | ((uint32_t)__half_as_ushort(__float2half_rn(0.f)) << 16);
+    const int npx = (y1 - y0) * S;
+    for (int i = tid; i < npx; i += kPyrThreads) {
+      const int ly = i / S, x = i - ly * S, y = y0 + ly;
+      const bool inside = y >= pad0 && y < pad0 + R && x >= pad0 && x < pad0 + R;
+      if (!inside) *reinterpret_cast<uint2*>(out_row(y) + x * 4) = o;
+    }
   }
 }
 

@@ -64,6 +64,9 @@ struct vnect_handle {
   unsigned long long* d_post_trace = nullptr;  // VNECT_B200_POST_TRACE=1: phase timestamps of the last post-process launch
   std::vector<ScaleTable> h_tables;  // host copy: the post-process block's shared-memory plan is derived from it
   PyramidTable* d_pyr_tables = nullptr;
+  __half* d_norm_lut = nullptr;
+  int pyr_src_rows = 1;         // most source rows a pyramid block stages
+  bool x1_surround_ok = false;  // the constant surround of the shrunken scales is in place in every slot of x1
   FilterState *d_st2d = nullptr, *d_st3d = nullptr;
   double* d_j2_box = nullptr;
   float* d_j3_raw = nullptr;
@@ -624,14 +627,27 @@ static int alloc_prepost(vnect_t* h) {
       ptab[i].xt[d].y = (short)(3 * std::min(ix + 1, S - 1));
       ptab[i].xt[d].z = (short)std::nearbyint((1.f - fx) * 2048.f);
       ptab[i].xt[d].w = (short)std::nearbyint(fx * 2048.f);
-      ptab[i].yj0[d] = (short)std::min(std::max(iy, 0), S - 1);
-      ptab[i].yj1[d] = (short)std::min(std::max(iy + 1, 0), S - 1);
-      ptab[i].yb0[d] = (short)std::nearbyint((1.f - fy) * 2048.f);
-      ptab[i].yb1[d] = (short)std::nearbyint(fy * 2048.f);
+      ptab[i].yt[d].x = (short)std::min(std::max(iy, 0), S - 1);
+      ptab[i].yt[d].y = (short)std::min(std::max(iy + 1, 0), S - 1);
+      ptab[i].yt[d].z = (short)std::nearbyint((1.f - fy) * 2048.f);
+      ptab[i].yt[d].w = (short)std::nearbyint(fy * 2048.f);
+    }
+    py.r_magic[i] = (unsigned int)((1ull << 32) / (unsigned long long)py.R[i]) + 1u;
+    // source rows one block of kPyrRows output rows samples
+    for (int y0 = 0; y0 < py.R[i] && py.R[i] != S; y0 += 1) {
+      const int y1 = std::min(y0 + kPyrRows, py.R[i]) - 1;
+      h->pyr_src_rows = std::max(h->pyr_src_rows, ptab[i].yt[y1].y - ptab[i].yt[y0].x + 1);
     }
   }
   if ((rc = upload(h, ptab, &h->d_pyr_tables))) return rc;
   py.tables = h->d_pyr_tables;
+  // float32(v) / 255 - 0.4 -> fp16 (estimator.py:81 in float32, then the operand precision of the stem)
+  std::vector<__half> lut(256);
+  for (int v = 0; v < 256; ++v) lut[v] = __float2half_rn((float)v / 255.f - 0.4f);
+  if ((rc = upload(h, lut, &h->d_norm_lut))) return rc;
+  py.lut = h->d_norm_lut;
+  py.src_row_bytes = (S * 3 + 15) & ~15;
+  py.full = 0;
   return VNECT_OK;
 }
 
@@ -859,9 +875,37 @@ static Geometry squarify_geometry(int S, int H, int W) {
 }
 
 // device frames -> x1 (stem layout) for n_frames * n_scales forwards
+static int launch_pyramid(vnect_t* h, const uint8_t* sq, int64_t sq_pitch, int64_t sq_stride, int n_frames, bool full_surround) {
+  const int S = h->S;
+  PyramidParams py = h->pyr;
+  py.n_frames = n_frames; py.sq_pitch = sq_pitch; py.sq_frame_stride = sq_stride;
+  py.full = full_surround ? 1 : 0;
+  const size_t smem = (size_t)h->pyr_src_rows * py.src_row_bytes;
+  static unsigned long long done = 0;
+  CU(h, ensure_dyn_smem(pyramid_kernel, 160 * 1024, &done));
+  if (smem > 160 * 1024) return fail(h, VNECT_E_INVALID, "pyramid scale too small for the staged rows (%zu bytes)", smem);
+  CU(h, launch_pdl(pyramid_kernel, dim3((S + kPyrRows - 1) / kPyrRows, n_frames * h->n_scales), dim3(kPyrThreads), smem,
+                   h->stream, sq, h->x1, py));
+  ++h->launches;
+  return VNECT_OK;
+}
+
+// The surround of every shrunken scale is a per-slot constant of x1: written here for all slots, once, and again only
+// after vnect_forward has put caller-supplied images into the buffer.  Never part of a captured graph.
+static int ensure_surround(vnect_t* h) {
+  if (h->x1_surround_ok) return VNECT_OK;
+  const int S = h->S;
+  int rc = launch_pyramid(h, h->d_sq, (int64_t)S * 3, (int64_t)S * S * 3, h->cfg.max_frames, true);
+  if (rc) return rc;
+  h->x1_surround_ok = true;
+  return VNECT_OK;
+}
+
 static int run_preprocess(vnect_t* h, const uint8_t* dev_bgr, int n_frames, int H, int W, int64_t pitch,
                           int64_t frame_stride, const Geometry& g, bool tracked = false) {
   const int S = h->S;
+  int rc0 = ensure_surround(h);
+  if (rc0) return rc0;
   const uint8_t* sq = dev_bgr;
   int64_t sq_pitch = pitch, sq_stride = frame_stride;
   if (tracked) {
@@ -881,10 +925,7 @@ static int run_preprocess(vnect_t* h, const uint8_t* dev_bgr, int n_frames, int 
     ++h->launches;
     sq = h->d_sq; sq_pitch = (int64_t)S * 3; sq_stride = (int64_t)S * S * 3;
   }
-  PyramidParams py = h->pyr;
-  py.n_frames = n_frames; py.sq_pitch = sq_pitch; py.sq_frame_stride = sq_stride;
-  CU(h, launch_pdl(pyramid_kernel, dim3(S, n_frames * h->n_scales), dim3(128), 0, h->stream, sq, h->x1, py));
-  ++h->launches;
+  if (int rc = launch_pyramid(h, sq, sq_pitch, sq_stride, n_frames, false)) return rc;
   return VNECT_OK;
 }
 
@@ -1017,6 +1058,7 @@ int vnect_forward(vnect_t* h, const float* nhwc, int32_t n, float* hm, float* xm
   const int S = h->S, hs = h->hs;
   const size_t in_elems = (size_t)n * S * S * 3;
   CU(h, cudaMemcpyAsync(h->d_f32_in, nhwc, in_elems * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  h->x1_surround_ok = false;  // caller-supplied images replace whole slots of x1
   f32_to_stem_kernel<<<grid_for((int64_t)n * S * S, 256, h->num_sms), 256, 0, h->stream>>>(h->d_f32_in, h->x1, n, S, h->stem_rpp, h->stem_pitch);
   CU(h, cudaGetLastError());
   ++h->launches;
@@ -1041,6 +1083,7 @@ int vnect_forward(vnect_t* h, const float* nhwc, int32_t n, float* hm, float* xm
 static int run_pipeline(vnect_t* h, int lane, const uint8_t* dev_bgr, int n_frames, int H, int W, int64_t pitch,
                         int64_t frame_stride, double* out2d, float* out3d, bool tracked = false) {
   const Geometry g = squarify_geometry(h->S, H, W);
+  if (int rc = ensure_surround(h)) return rc;
   auto direct = [&]() -> int {
     int rc;
     if ((rc = run_preprocess(h, dev_bgr, n_frames, H, W, pitch, frame_stride, g, tracked))) return rc;
