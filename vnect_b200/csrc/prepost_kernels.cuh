@@ -168,7 +168,8 @@ constexpr int kMaxBox = 512;
 // Per pyramid scale: the OpenCV coordinate / fixed-point coefficient of every destination column and row, computed
 // once on the host with the same arithmetic as cv_linear_coord / cv_coef (the scales are fixed at vnect_create).
 struct PyramidTable {
-  short4 xt[kMaxBox];  // x axis (index clamp + f reset): .x/.y = byte offsets of the two source pixels, .z/.w = weights
+  uint2 xt[kMaxBox];   // x axis (index clamp + f reset): .x = 4*ix | 4*ix1 << 16 (byte offsets into a staged row of 4-byte
+                       // pixels), .y = a0 | a1 << 16 (11-bit fixed-point weights)
   short4 yt[kMaxBox];  // y axis (rows clamped, f kept): .x/.y = the two source rows, .z/.w = weights
 };
 
@@ -181,14 +182,36 @@ struct PyramidParams {
   int R[kMaxScales];                  // resized side cvRound(S*s); == S for s >= 1 (identity)
   int pad0[kMaxScales];               // (S - R) / 2
   unsigned int r_magic[kMaxScales];   // floor(2^32 / R) + 1: i / R == umulhi(i, r_magic) for the indices used here
+  unsigned int q_magic;               // the same for S / 4
   double inv_scale[kMaxScales];       // 1 / s
   const PyramidTable* tables;         // [n_scales], device
-  const __half* lut;                  // [256]: fp16(float32(v) / 255 - 0.4) for every 8-bit value
+  const uint32_t* lut;                // [256]: fp16(float32(v) / 255 - 0.4) in the low half of a word, for every 8-bit value
   // stem layout: [forward][parity][rows_per_parity][row_pitch] halves, pixel (y, x) lives at padded (y+2, x+2)
   int rows_per_parity, row_pitch;
   int full;                           // also write the black surround of the shrunken scales (see below)
-  int src_row_bytes;                  // S * 3 rounded up to 16: pitch of the staged source rows
 };
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {  // plain shared-memory load from a 32-bit shared address
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// 12 source bytes = 4 BGR pixels as three words -> four words with one pixel in the low three bytes of each
+__device__ __forceinline__ uint4 expand_bgr4(uint32_t w0, uint32_t w1, uint32_t w2) {
+  return make_uint4(w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8);
+}
+__device__ __forceinline__ void load_bgr4(const uint8_t* s, bool aligned, uint32_t* w0, uint32_t* w1, uint32_t* w2) {
+  if (aligned) {
+    *w0 = __ldg(reinterpret_cast<const uint32_t*>(s));
+    *w1 = __ldg(reinterpret_cast<const uint32_t*>(s) + 1);
+    *w2 = __ldg(reinterpret_cast<const uint32_t*>(s) + 2);
+  } else {
+    *w0 = s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24);
+    *w1 = s[4] | (s[5] << 8) | (s[6] << 16) | ((uint32_t)s[7] << 24);
+    *w2 = s[8] | (s[9] << 8) | (s[10] << 16) | ((uint32_t)s[11] << 24);
+  }
+}
 
 // estimator.gen_input_batch (estimator.py:70-81): per scale shrink + zero pad (utils.py:123-150), then
 // float32(u8)/255 - 0.4, stored as fp16 in the parity-split padded NHWC4 layout the stem conv's TMA reads.
@@ -198,17 +221,21 @@ struct PyramidParams {
 //  * shrunken scale: only the R x R picture is computed.  Its black surround is the same constant for every frame
 //    (fp16(0/255 - 0.4)), lives in a slot of x1 that always holds this scale, and is therefore written ONCE
 //    (`full`, at start-up and after vnect_forward has overwritten the buffer): 51 % of a 0.7-scale forward's bytes.
-//    The source rows the block's 8 output rows sample (~8/s + 2) are staged in shared memory with 16-byte loads, so
-//    the 12 taps of a pixel are shared-memory byte loads and every source byte leaves L2 once per block.
+//    The source rows the block's 8 output rows sample (~8/s + 2) are staged in shared memory as 4-byte pixels, so a
+//    tap is one aligned word, the horizontal pass of a row is two byte permutes + three dp2a (weights as a 16-bit
+//    pair), and every source byte leaves L2 once per block;
 //  * the normalisation is a 256-entry table built on the host (an IEEE division per channel was a third of the first
 //    version's instructions; rebuilding the table in every block was most of the second's).
 __global__ void __launch_bounds__(kPyrThreads) pyramid_kernel(const uint8_t* __restrict__ sq, __half* __restrict__ x1,
                                                               const __grid_constant__ PyramidParams p) {
-  extern __shared__ __align__(16) uint8_t s_rows[];
-  __shared__ __align__(4) __half s_lut[256];
+  extern __shared__ __align__(16) uint8_t s_px[];  // staged source rows, 4 bytes per pixel
+  __shared__ __align__(16) uint32_t s_lut[256];
+  __shared__ uint2 s_xt[kMaxBox];  // this scale's column entries
+  struct RowInfo { int r0, r1; unsigned int b0, b1; int out; int pad[3]; };
+  __shared__ __align__(16) RowInfo s_row[kPyrRows];
   pdl_launch_dependents();
   const int tid = threadIdx.x;
-  if (tid < 128) reinterpret_cast<uint32_t*>(s_lut)[tid] = reinterpret_cast<const uint32_t*>(p.lut)[tid];
+  s_lut[tid] = p.lut[tid];  // kPyrThreads == 256
   pdl_wait();  // x1 may still be read by the previous batch's stem kernel; sq comes from the copy / squarify before us
   const int S = p.S;
   const int fwd = blockIdx.y;
@@ -216,43 +243,36 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_kernel(const uint8_t* __r
   const int R = p.R[si], pad0 = p.pad0[si];
   const uint8_t* src = sq + (int64_t)frame * p.sq_frame_stride;
   const int y0 = blockIdx.x * kPyrRows, y1 = min(y0 + kPyrRows, S);
-  // output row y starts at padded row y + 2, padded column 2 (8 halves)
-  auto out_row = [&](int y) -> __half* {
+  __half* x1f = x1 + (int64_t)fwd * 2 * p.rows_per_parity * p.row_pitch;
+  // output row y starts at padded row y + 2, padded column 2 (8 halves); offset in halves from x1f
+  auto out_row = [&](int y) -> int {
     const int pr = y + 2;
-    return x1 + (((int64_t)fwd * 2 + (pr & 1)) * p.rows_per_parity + (pr >> 1)) * p.row_pitch + 8;
+    return ((pr & 1) * p.rows_per_parity + (pr >> 1)) * p.row_pitch + 8;
   };
-  auto lut2 = [&](uint32_t a, uint32_t b) -> uint32_t {  // two table entries packed
-    return (uint32_t)__half_as_ushort(s_lut[a]) | ((uint32_t)__half_as_ushort(s_lut[b]) << 16);
-  };
-  __syncthreads();
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)p.sq_pitch) & 3) == 0;
+  const int qpr = S >> 2;  // 4-pixel groups per row (S is a multiple of 16)
+  const int pitch = (int)p.sq_pitch;  // a frame's rows are less than 2 GB apart
+  // flat index i = tid + k * 256 over rows of `w` items as (row, column), advanced without a division per step
+  const int step_rows_q = kPyrThreads / qpr, step_cols_q = kPyrThreads - step_rows_q * qpr;
   if (R == S) {
-    const int qpr = S >> 2;  // 4-pixel groups per row (S is a multiple of 16)
-    const int nq = (y1 - y0) * qpr;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)p.sq_pitch) & 3) == 0;
-    for (int q = tid; q < nq; q += kPyrThreads) {
-      const int ly = q / qpr, qx = q - ly * qpr;
-      const uint8_t* s = src + (int64_t)(y0 + ly) * p.sq_pitch + qx * 12;
+    __syncthreads();
+    const uint8_t* src0 = src + (int64_t)y0 * p.sq_pitch;
+    const int rows = y1 - y0;
+    int ly = (int)__umulhi((unsigned int)tid, p.q_magic), qx = tid - ly * qpr;
+    for (; ly < rows; ly += step_rows_q, qx += step_cols_q) {
+      if (qx >= qpr) { qx -= qpr; if (++ly >= rows) break; }
       uint32_t w0, w1, w2;
-      if (aligned) {
-        w0 = __ldg(reinterpret_cast<const uint32_t*>(s));
-        w1 = __ldg(reinterpret_cast<const uint32_t*>(s) + 1);
-        w2 = __ldg(reinterpret_cast<const uint32_t*>(s) + 2);
-      } else {
-        w0 = s[0] | (s[1] << 8) | (s[2] << 16) | ((uint32_t)s[3] << 24);
-        w1 = s[4] | (s[5] << 8) | (s[6] << 16) | ((uint32_t)s[7] << 24);
-        w2 = s[8] | (s[9] << 8) | (s[10] << 16) | ((uint32_t)s[11] << 24);
-      }
-      const uint32_t zero = (uint32_t)__half_as_ushort(__float2half_rn(0.f)) << 16;
-      uint4 o0, o1;
-      o0.x = lut2(w0 & 0xff, (w0 >> 8) & 0xff);
-      o0.y = (uint32_t)__half_as_ushort(s_lut[(w0 >> 16) & 0xff]) | zero;
-      o0.z = lut2(w0 >> 24, w1 & 0xff);
-      o0.w = (uint32_t)__half_as_ushort(s_lut[(w1 >> 8) & 0xff]) | zero;
-      o1.x = lut2((w1 >> 16) & 0xff, w1 >> 24);
-      o1.y = (uint32_t)__half_as_ushort(s_lut[w2 & 0xff]) | zero;
-      o1.z = lut2((w2 >> 8) & 0xff, (w2 >> 16) & 0xff);
-      o1.w = (uint32_t)__half_as_ushort(s_lut[w2 >> 24]) | zero;
-      uint4* o = reinterpret_cast<uint4*>(out_row(y0 + ly) + qx * 16);
+      load_bgr4(src0 + (ly * pitch + qx * 12), aligned, &w0, &w1, &w2);
+      uint4 o0, o1;  // the fourth half of a pixel is fp16 zero = the empty high half of a table word
+      o0.x = s_lut[w0 & 0xff] | (s_lut[(w0 >> 8) & 0xff] << 16);
+      o0.y = s_lut[(w0 >> 16) & 0xff];
+      o0.z = s_lut[w0 >> 24] | (s_lut[w1 & 0xff] << 16);
+      o0.w = s_lut[(w1 >> 8) & 0xff];
+      o1.x = s_lut[(w1 >> 16) & 0xff] | (s_lut[w1 >> 24] << 16);
+      o1.y = s_lut[w2 & 0xff];
+      o1.z = s_lut[(w2 >> 8) & 0xff] | (s_lut[(w2 >> 16) & 0xff] << 16);
+      o1.w = s_lut[w2 >> 24];
+      uint4* o = reinterpret_cast<uint4*>(x1f + (out_row(y0 + ly) + qx * 16));
       o[0] = o0;
       o[1] = o1;
     }
@@ -261,59 +281,71 @@ __global__ void __launch_bounds__(kPyrThreads) pyramid_kernel(const uint8_t* __r
   const PyramidTable* __restrict__ T = p.tables + si;
   const int ry0 = max(y0, pad0) - pad0, ry1 = min(y1, pad0 + R) - pad0;  // picture rows of this block
   if (ry0 < ry1) {
-    // stage the source rows [s_lo, s_hi] (the row entries are non-decreasing)
+    // stage the source rows [s_lo, s_hi] (the row entries are non-decreasing), expanded to one word per pixel
     const int s_lo = T->yt[ry0].x, s_hi = T->yt[ry1 - 1].y;
-    const int rb = p.src_row_bytes;
-    const uint8_t* g0 = src + (int64_t)s_lo * p.sq_pitch;
-    if (((reinterpret_cast<uintptr_t>(src) | (uintptr_t)p.sq_pitch) & 15) == 0) {
-      const int vpr = rb >> 4;
-      const int nv = (s_hi - s_lo + 1) * vpr;
-      for (int i = tid; i < nv; i += kPyrThreads) {
-        const int r = i / vpr, c = i - r * vpr;
-        *reinterpret_cast<uint4*>(s_rows + r * rb + c * 16) = __ldg(reinterpret_cast<const uint4*>(g0 + (int64_t)r * p.sq_pitch) + c);
+    const int rb = S * 4;
+    {
+      const uint8_t* src0 = src + (int64_t)s_lo * p.sq_pitch;
+      const int rows = s_hi - s_lo + 1;
+      int r = (int)__umulhi((unsigned int)tid, p.q_magic), qx = tid - r * qpr;
+      for (; r < rows; r += step_rows_q, qx += step_cols_q) {
+        if (qx >= qpr) { qx -= qpr; if (++r >= rows) break; }
+        uint32_t w0, w1, w2;
+        load_bgr4(src0 + (r * pitch + qx * 12), aligned, &w0, &w1, &w2);
+        *reinterpret_cast<uint4*>(s_px + r * rb + qx * 16) = expand_bgr4(w0, w1, w2);
       }
-    } else {
-      const int nb = (s_hi - s_lo + 1) * S * 3;
-      for (int i = tid; i < nb; i += kPyrThreads) {
-        const int r = i / (S * 3), c = i - r * (S * 3);
-        s_rows[r * rb + c] = g0[(int64_t)r * p.sq_pitch + c];
-      }
+    }
+    for (int i = tid; i < R; i += kPyrThreads) s_xt[i] = T->xt[i];
+    if (tid < ry1 - ry0) {
+      const short4 yt = T->yt[ry0 + tid];
+      RowInfo ri;
+      ri.r0 = (yt.x - s_lo) * rb;
+      ri.r1 = (yt.y - s_lo) * rb;
+      // (b * (t >> 4)) >> 16 as the high word of (b << 16) * (t >> 4): all operands are non-negative
+      ri.b0 = (unsigned int)yt.z << 16;
+      ri.b1 = (unsigned int)yt.w << 16;
+      ri.out = out_row(ry0 + tid + pad0) + pad0 * 4;
+      ri.pad[0] = ri.pad[1] = ri.pad[2] = 0;
+      s_row[tid] = ri;
     }
     __syncthreads();
-    const int npx = (ry1 - ry0) * R;
-    const unsigned int magic = p.r_magic[si];
-    for (int i = tid; i < npx; i += kPyrThreads) {
-      const int ly = (int)__umulhi((unsigned int)i, magic);
-      const int rx = i - ly * R, ry = ry0 + ly;
-      const short4 yt = T->yt[ry];
-      const short4 xt = T->xt[rx];
-      const uint8_t* r0 = s_rows + (yt.x - s_lo) * rb;
-      const uint8_t* r1 = s_rows + (yt.y - s_lo) * rb;
-      const int o0 = xt.x, o1 = xt.y, a0 = xt.z, a1 = xt.w;
-      // (b * (t >> 4)) >> 16 as the high word of (b << 16) * (t >> 4): all operands are non-negative
-      const unsigned int b0 = (unsigned int)yt.z << 16, b1 = (unsigned int)yt.w << 16;
-      uint32_t v[3];
+    const int rows = ry1 - ry0;
+    const int step_rows = kPyrThreads / R, step_cols = kPyrThreads - step_rows * R;
+    const uint32_t px_base = smem_u32(s_px), lut_base = smem_u32(s_lut);
+    int ly = (int)__umulhi((unsigned int)tid, p.r_magic[si]), rx = tid - ly * R;
+    for (; ly < rows; ly += step_rows, rx += step_cols) {
+      if (rx >= R) { rx -= R; if (++ly >= rows) break; }
+      const RowInfo ri = s_row[ly];
+      const uint2 xt = s_xt[rx];
+      const uint32_t c0 = px_base + (xt.x & 0xffff), c1 = px_base + (xt.x >> 16);
+      const uint32_t p00 = lds_u32(c0 + ri.r0), p01 = lds_u32(c1 + ri.r0);
+      const uint32_t p10 = lds_u32(c0 + ri.r1), p11 = lds_u32(c1 + ri.r1);
+      // horizontal pass: t = v(x0) * a0 + v(x1) * a1 per channel, the two bytes of a channel side by side
+      const uint32_t q0 = __byte_perm(p00, p01, 0x5140), q0r = __byte_perm(p00, p01, 0x0062);
+      const uint32_t q1 = __byte_perm(p10, p11, 0x5140), q1r = __byte_perm(p10, p11, 0x0062);
+      const uint32_t t0[3] = {__dp2a_lo(xt.y, q0, 0u), __dp2a_hi(xt.y, q0, 0u), __dp2a_lo(xt.y, q0r, 0u)};
+      const uint32_t t1[3] = {__dp2a_lo(xt.y, q1, 0u), __dp2a_hi(xt.y, q1, 0u), __dp2a_lo(xt.y, q1r, 0u)};
+      uint32_t e[3];  // table word of channel c: its address is base + 4 * ((sum + 2) >> 2) = (base + 2 + sum) & ~3
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int t0 = r0[o0 + c] * a0 + r0[o1 + c] * a1;
-        const int t1 = r1[o0 + c] * a0 + r1[o1 + c] * a1;
-        v[c] = (__umulhi(b0, (unsigned int)(t0 >> 4)) + __umulhi(b1, (unsigned int)(t1 >> 4)) + 2u) >> 2;
-      }
+      for (int c = 0; c < 3; ++c)
+        e[c] = lds_u32((lut_base + 2u + __umulhi(ri.b0, t0[c] >> 4) + __umulhi(ri.b1, t1[c] >> 4)) & ~3u);
       uint2 o;
-      o.x = lut2(v[0], v[1]);
-      o.y = (uint32_t)__half_as_ushort(s_lut[v[2]]) | ((uint32_t)__half_as_ushort(__float2half_rn(0.f)) << 16);
-      *reinterpret_cast<uint2*>(out_row(ry + pad0) + (rx + pad0) * 4) = o;
+      o.x = e[0] | (e[1] << 16);
+      o.y = e[2];
+      *reinterpret_cast<uint2*>(x1f + (ri.out + rx * 4)) = o;
     }
+  } else {
+    __syncthreads();  // s_lut
   }
   if (p.full) {  // the black surround: float32(0) / 255 - 0.4
     uint2 o;
-    o.x = lut2(0, 0);
-    o.y = (uint32_t)__half_as_ushort(s_lut[0]) | ((uint32_t)__half_as_ushort(__float2half_rn(0.f)) << 16);
+    o.x = s_lut[0] | (s_lut[0] << 16);
+    o.y = s_lut[0];
     const int npx = (y1 - y0) * S;
     for (int i = tid; i < npx; i += kPyrThreads) {
       const int ly = i / S, x = i - ly * S, y = y0 + ly;
       const bool inside = y >= pad0 && y < pad0 + R && x >= pad0 && x < pad0 + R;
-      if (!inside) *reinterpret_cast<uint2*>(out_row(y) + x * 4) = o;
+      if (!inside) *reinterpret_cast<uint2*>(x1f + out_row(y) + x * 4) = o;
     }
   }
 }

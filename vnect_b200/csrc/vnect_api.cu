@@ -64,7 +64,7 @@ struct vnect_handle {
   unsigned long long* d_post_trace = nullptr;  // VNECT_B200_POST_TRACE=1: phase timestamps of the last post-process launch
   std::vector<ScaleTable> h_tables;  // host copy: the post-process block's shared-memory plan is derived from it
   PyramidTable* d_pyr_tables = nullptr;
-  __half* d_norm_lut = nullptr;
+  uint32_t* d_norm_lut = nullptr;
   int pyr_src_rows = 1;         // most source rows a pyramid block stages
   bool x1_surround_ok = false;  // the constant surround of the shrunken scales is in place in every slot of x1
   FilterState *d_st2d = nullptr, *d_st3d = nullptr;
@@ -623,10 +623,9 @@ static int alloc_prepost(vnect_t* h) {
       float fx, fy;
       host_linear_coord(d, py.inv_scale[i], S, true, &ix, &fx);
       host_linear_coord(d, py.inv_scale[i], S, false, &iy, &fy);
-      ptab[i].xt[d].x = (short)(3 * ix);
-      ptab[i].xt[d].y = (short)(3 * std::min(ix + 1, S - 1));
-      ptab[i].xt[d].z = (short)std::nearbyint((1.f - fx) * 2048.f);
-      ptab[i].xt[d].w = (short)std::nearbyint(fx * 2048.f);
+      const unsigned int a0 = (unsigned int)std::nearbyint((1.f - fx) * 2048.f), a1 = (unsigned int)std::nearbyint(fx * 2048.f);
+      ptab[i].xt[d].x = (unsigned int)(4 * ix) | ((unsigned int)(4 * std::min(ix + 1, S - 1)) << 16);
+      ptab[i].xt[d].y = a0 | (a1 << 16);
       ptab[i].yt[d].x = (short)std::min(std::max(iy, 0), S - 1);
       ptab[i].yt[d].y = (short)std::min(std::max(iy + 1, 0), S - 1);
       ptab[i].yt[d].z = (short)std::nearbyint((1.f - fy) * 2048.f);
@@ -642,11 +641,16 @@ static int alloc_prepost(vnect_t* h) {
   if ((rc = upload(h, ptab, &h->d_pyr_tables))) return rc;
   py.tables = h->d_pyr_tables;
   // float32(v) / 255 - 0.4 -> fp16 (estimator.py:81 in float32, then the operand precision of the stem)
-  std::vector<__half> lut(256);
-  for (int v = 0; v < 256; ++v) lut[v] = __float2half_rn((float)v / 255.f - 0.4f);
+  std::vector<uint32_t> lut(256);
+  for (int v = 0; v < 256; ++v) {
+    const __half hv = __float2half_rn((float)v / 255.f - 0.4f);
+    unsigned short bits;
+    memcpy(&bits, &hv, 2);
+    lut[v] = bits;
+  }
   if ((rc = upload(h, lut, &h->d_norm_lut))) return rc;
   py.lut = h->d_norm_lut;
-  py.src_row_bytes = (S * 3 + 15) & ~15;
+  py.q_magic = (unsigned int)((1ull << 32) / (unsigned long long)(S / 4)) + 1u;
   py.full = 0;
   return VNECT_OK;
 }
@@ -880,7 +884,7 @@ static int launch_pyramid(vnect_t* h, const uint8_t* sq, int64_t sq_pitch, int64
   PyramidParams py = h->pyr;
   py.n_frames = n_frames; py.sq_pitch = sq_pitch; py.sq_frame_stride = sq_stride;
   py.full = full_surround ? 1 : 0;
-  const size_t smem = (size_t)h->pyr_src_rows * py.src_row_bytes;
+  const size_t smem = (size_t)h->pyr_src_rows * S * 4;  // staged source rows, one word per pixel
   static unsigned long long done = 0;
   CU(h, ensure_dyn_smem(pyramid_kernel, 160 * 1024, &done));
   if (smem > 160 * 1024) return fail(h, VNECT_E_INVALID, "pyramid scale too small for the staged rows (%zu bytes)", smem);
