@@ -459,6 +459,7 @@ struct PostParams {
   float* out3d;                   // [n_frames][21][3]
   double* packed;                 // optional [n_frames][21][5] = (row, col, x, y, z): the layout the multi-GPU gather moves
   unsigned int* nonfinite;        // counts (frame, joint) blocks that met a NaN / Inf in the CNN's maps (fp16 overflow guard)
+  unsigned int* nonfinite_flag;   // host-visible (mapped pinned) word of the submitting lane: set to 1 in that case
   // shared-memory plan of one block (post_smem_plan, host): which raw cells of every scale's heat-map plane are staged
   // and where.  An identity scale needs its whole plane, a resized one only the rows its centre crop samples.
   int identity_mask;              // bit sc: scale sc is a plain copy
@@ -761,7 +762,10 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
   // fp16 activations overflow at 65504: an Inf / NaN anywhere in the CNN almost surely reaches the maps.  Count it (the
   // host turns a non-zero count into an error) instead of returning joints computed from garbage.
   const int any_bad = __syncthreads_or(bad);
-  if (any_bad && tid == 0 && p.nonfinite != nullptr) atomicAdd(p.nonfinite, 1u);
+  if (any_bad && tid == 0 && p.nonfinite != nullptr) {
+    atomicAdd(p.nonfinite, 1u);
+    if (p.nonfinite_flag != nullptr) *reinterpret_cast<volatile unsigned int*>(p.nonfinite_flag) = 1u;
+  }
   bmax = s_wmax[0]; bidx = s_widx[0]; bmin = s_wmin[0]; bvmax = s_wamax[0];
   for (int w = 1; w < nwarps; ++w) {
     if (s_wmax[w] > bmax) { bmax = s_wmax[w]; bidx = s_widx[w]; }
@@ -967,7 +971,10 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
       const float* m = p.maps + ((size_t)(frame * ns + sc) * 84 + kJoints * (1 + map) + joint) * cells;
       const float gv = scaled_cell(m, hs, p.tables[sc], (cell & 2) ? y1 : y0, (cell & 1) ? x1 : x0);
       s_gather[tid] = gv;
-      if (!(fabsf(gv) <= 3.4028234e38f) && p.nonfinite != nullptr) atomicAdd(p.nonfinite, 1u);
+      if (!(fabsf(gv) <= 3.4028234e38f) && p.nonfinite != nullptr) {
+        atomicAdd(p.nonfinite, 1u);
+        if (p.nonfinite_flag != nullptr) *reinterpret_cast<volatile unsigned int*>(p.nonfinite_flag) = 1u;
+      }
     }
     __syncthreads();
     if (tid < 3) {

@@ -83,12 +83,16 @@ struct vnect_handle {
     float* d_out3d = nullptr;
     int* h_stream_ids = nullptr;
     double *h_t2d = nullptr, *h_t3d = nullptr;
-    unsigned int* h_nonfinite = nullptr;  // pinned: the non-finite counter as of the end of this lane's last batch
+    void* h_meta = nullptr;               // pinned block behind h_stream_ids / h_t2d / h_t3d (one H2D copy per call)
+    size_t meta_bytes = 0;
+    unsigned int* h_nonfinite = nullptr;  // pinned + device-visible: set by the post-process when a batch of this lane met NaN / Inf maps
     cudaEvent_t copy_done = nullptr, done = nullptr;
     bool pending = false;
   } lanes[2];
   Lane* cur = &lanes[0];
   cudaStream_t copy_stream = nullptr;
+  std::vector<unsigned int> seen_stamp;  // duplicate stream ids within a call (stage_frame_meta)
+  unsigned int seen_epoch = 0;
   unsigned device_calls = 0;
   // tracked streams (run_estimator.py:100-119): per-stream crop box on the device, per-call frame geometry
   int4* d_boxes = nullptr;         // [max_streams] (x, y, w, h)
@@ -571,15 +575,23 @@ static int alloc_prepost(vnect_t* h) {
   CU(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   for (auto& L : h->lanes) {
     if ((rc = dev_alloc(h, &L.d_frames, h->d_frames_bytes))) return rc;
-    if ((rc = dev_alloc(h, &L.d_stream_ids, mf))) return rc;
-    if ((rc = dev_alloc(h, &L.d_t2d, mf))) return rc;
-    if ((rc = dev_alloc(h, &L.d_t3d, mf))) return rc;
+    {  // ids | t2d | t3d in one block on both sides: one H2D copy per call
+      const size_t off_t2 = ((size_t)mf * sizeof(int) + 15) & ~size_t(15), off_t3 = off_t2 + (size_t)mf * sizeof(double);
+      L.meta_bytes = off_t3 + (size_t)mf * sizeof(double);
+      uint8_t* d_meta = nullptr;
+      if ((rc = dev_alloc(h, &d_meta, L.meta_bytes))) return rc;
+      L.d_stream_ids = reinterpret_cast<int*>(d_meta);
+      L.d_t2d = reinterpret_cast<double*>(d_meta + off_t2);
+      L.d_t3d = reinterpret_cast<double*>(d_meta + off_t3);
+      CU(h, cudaMallocHost(&L.h_meta, L.meta_bytes));
+      memset(L.h_meta, 0, L.meta_bytes);
+      L.h_stream_ids = reinterpret_cast<int*>(L.h_meta);
+      L.h_t2d = reinterpret_cast<double*>(static_cast<uint8_t*>(L.h_meta) + off_t2);
+      L.h_t3d = reinterpret_cast<double*>(static_cast<uint8_t*>(L.h_meta) + off_t3);
+    }
     if ((rc = dev_alloc(h, &L.d_out2d, (size_t)mf * kJoints * 2))) return rc;
     if ((rc = dev_alloc(h, &L.d_out3d, (size_t)mf * kJoints * 3))) return rc;
-    CU(h, cudaMallocHost(&L.h_stream_ids, mf * sizeof(int)));
-    CU(h, cudaMallocHost(&L.h_t2d, mf * sizeof(double)));
-    CU(h, cudaMallocHost(&L.h_t3d, mf * sizeof(double)));
-    CU(h, cudaMallocHost(&L.h_nonfinite, sizeof(unsigned int)));
+    CU(h, cudaHostAlloc(&L.h_nonfinite, sizeof(unsigned int), cudaHostAllocMapped));
     *L.h_nonfinite = 0;
     CU(h, cudaEventCreateWithFlags(&L.copy_done, cudaEventDisableTiming));
     CU(h, cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
@@ -940,10 +952,12 @@ static int lane_acquire(vnect_t* h, int lane) {
   if (h->cur->pending) {
     CU(h, cudaEventSynchronize(h->cur->done));
     h->cur->pending = false;
-    if (*h->cur->h_nonfinite != 0) {  // the batch that just completed produced NaN / Inf maps: fail loudly, once
-      const unsigned int n = *h->cur->h_nonfinite;
+    if (*reinterpret_cast<volatile unsigned int*>(h->cur->h_nonfinite) != 0) {  // the batch that just completed produced NaN / Inf maps: fail loudly, once
+      unsigned int n = 0;  // error path only: the count lives on the device
+      cudaStreamSynchronize(h->stream);
+      cudaMemcpy(&n, h->d_nonfinite, sizeof n, cudaMemcpyDeviceToHost);
       *h->cur->h_nonfinite = 0;
-      cudaMemsetAsync(h->d_nonfinite, 0, sizeof(unsigned int), h->stream);
+      cudaMemset(h->d_nonfinite, 0, sizeof(unsigned int));
       return fail(h, VNECT_E_NUMERIC, "non-finite values in the CNN output maps (%u joint blocks): fp16 activations "
                   "overflow at 65504 -- are the weights normalised? (vnect_check_finite names the first layer)", n);
     }
@@ -951,20 +965,21 @@ static int lane_acquire(vnect_t* h, int lane) {
   return VNECT_OK;
 }
 
-// queued after a batch's post-process: snapshot of the non-finite counter into the lane's pinned word
-static int snapshot_nonfinite(vnect_t* h) {
-  CU(h, cudaMemcpyAsync(h->cur->h_nonfinite, h->d_nonfinite, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
-  return VNECT_OK;
-}
+// The post-process itself raises the lane's host-visible flag (PostParams::nonfinite_flag, a mapped pinned word) when
+// it meets NaN / Inf maps, so no device -> host copy of a counter sits in the stream after every batch.
+static int snapshot_nonfinite(vnect_t*) { return VNECT_OK; }
 
 static int stage_frame_meta(vnect_t* h, int n_frames, const int32_t* stream_ids, const double* t2d, const double* t3d,
                             cudaStream_t copy_on) {
   if (n_frames < 1 || n_frames > h->cfg.max_frames) return fail(h, VNECT_E_INVALID, "n_frames %d not in [1, %d]", n_frames, h->cfg.max_frames);
-  std::set<int> seen;
+  h->seen_stamp.resize(h->cfg.max_streams, 0);
+  const unsigned int stamp = ++h->seen_epoch;
   for (int i = 0; i < n_frames; ++i) {
     const int sid = stream_ids ? stream_ids[i] : i;
     if (sid < 0 || sid >= h->cfg.max_streams) return fail(h, VNECT_E_INVALID, "stream id %d not in [0, %d)", sid, h->cfg.max_streams);
-    if (!seen.insert(sid).second) return fail(h, VNECT_E_INVALID, "stream id %d appears twice in one call (frames of a stream are sequential)", sid);
+    const bool dup = h->seen_stamp[sid] == stamp;
+    h->seen_stamp[sid] = stamp;
+    if (dup) return fail(h, VNECT_E_INVALID, "stream id %d appears twice in one call (frames of a stream are sequential)", sid);
     if (h->cfg.filters) {
       if (!t2d || !t3d) return fail(h, VNECT_E_INVALID, "timestamps required when filters are on");
       // OneEuroFilter.py:65-66: freq = 1.0 / (timestamp - lasttime) when both are truthy
@@ -990,9 +1005,7 @@ static int stage_frame_meta(vnect_t* h, int n_frames, const int32_t* stream_ids,
       h->last_t3d[sid] = t3d[i];
     }
   }
-  CU(h, cudaMemcpyAsync(h->cur->d_stream_ids, h->cur->h_stream_ids, n_frames * sizeof(int), cudaMemcpyHostToDevice, copy_on));
-  CU(h, cudaMemcpyAsync(h->cur->d_t2d, h->cur->h_t2d, n_frames * sizeof(double), cudaMemcpyHostToDevice, copy_on));
-  CU(h, cudaMemcpyAsync(h->cur->d_t3d, h->cur->h_t3d, n_frames * sizeof(double), cudaMemcpyHostToDevice, copy_on));
+  CU(h, cudaMemcpyAsync(h->cur->d_stream_ids, h->cur->h_meta, h->cur->meta_bytes, cudaMemcpyHostToDevice, copy_on));
   return VNECT_OK;
 }
 
@@ -1013,6 +1026,8 @@ static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, i
   p.out2d = dev_out2d; p.out3d = dev_out3d;
   p.packed = h->d_packed;
   p.nonfinite = guard ? h->d_nonfinite : nullptr;  // caller-supplied maps (vnect_postprocess) are taken as they are
+  p.nonfinite_flag = nullptr;
+  if (guard) CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&p.nonfinite_flag), h->cur->h_nonfinite, 0));
   // Threads per (frame, joint) block = the cells of `rows` heat-map rows.  A full batch is bound by instruction issue
   // summed over all blocks (two rows: every lane busy at hs = 46); a few frames leave most SMs empty, so wider blocks
   // shorten each block's own chain instead.  VNECT_B200_POST_ROWS overrides for A/B runs.
@@ -1159,7 +1174,10 @@ int vnect_estimate_device(vnect_t* h, const uint8_t* dev_bgr, int32_t n_frames, 
   // alternate lanes for the per-call meta so the host can run one call ahead of the GPU
   int rc = lane_acquire(h, (int)(h->device_calls++ & 1));
   if (rc) return rc;
-  if ((rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d, h->stream))) return rc;
+  // the per-call meta travels on the copy stream, under the previous call's kernels
+  if ((rc = stage_frame_meta(h, n_frames, stream_ids, t2d, t3d, h->copy_stream))) return rc;
+  CU(h, cudaEventRecord(h->cur->copy_done, h->copy_stream));
+  CU(h, cudaStreamWaitEvent(h->stream, h->cur->copy_done, 0));
   const int lane = (int)(h->cur - h->lanes);
   if ((rc = run_pipeline(h, lane, dev_bgr, n_frames, H, W, pitch, frame_stride, dev_joints2d, dev_joints3d))) return rc;
   if ((rc = snapshot_nonfinite(h))) return rc;
@@ -1762,9 +1780,7 @@ void vnect_destroy(vnect_t* h) {
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& L : h->lanes) {
-    if (L.h_stream_ids) cudaFreeHost(L.h_stream_ids);
-    if (L.h_t2d) cudaFreeHost(L.h_t2d);
-    if (L.h_t3d) cudaFreeHost(L.h_t3d);
+    if (L.h_meta) cudaFreeHost(L.h_meta);
     if (L.h_nonfinite) cudaFreeHost(L.h_nonfinite);
     if (L.copy_done) cudaEventDestroy(L.copy_done);
     if (L.done) cudaEventDestroy(L.done);
