@@ -44,6 +44,7 @@ inline bool encode_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_
     for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUtensorMapSwizzle sw = swz_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swz_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swz_bytes == 0  ? CU_TENSOR_MAP_SWIZZLE_NONE
                                             : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -540,6 +541,8 @@ inline cudaError_t launch_conv(const ConvLaunch& L, cudaStream_t st) {
 struct StemPoolLaunch {
   StemRollParams r;
   int grid = 0;
+  int cg = 1;          // 2: CTA pairs (stem_roll_kernel<., 2>), the two x tiles of a segment on the two CTAs
+  CUtensorMap tmap_x;  // pairs: the stem input as [16-byte units][8 halves], strips are boxes of 132 units
 };
 
 // [64][224] K-major (k = ky*32 + kx*4 + c) -> the rolling kernel's stacked weights: rows (ky = 6, 4, 2, 0) x 64 couts for
@@ -562,6 +565,29 @@ inline void pack_stem_stacked(const __half* kmajor, __half* out) {
     }
 }
 
+// Per-rank weight tables of the CTA-pair kernel (stem_roll.cuh): out = [rank][kPairWBytes]; entry (g, cnt) of a parity
+// holds rows [64 g + 32 cnt rank, + 32 cnt) of that parity's stack, 64B-swizzled like pack_stem_stacked
+inline void pack_stem_pair(const __half* kmajor, __half* out) {
+  for (int rank = 0; rank < 2; ++rank)
+    for (int parity = 0; parity < 2; ++parity) {
+      const int ng = parity ? 3 : 4;
+      __half* pbase = out + (size_t)rank * (kPairWBytes / 2) + (parity ? kPairWEvenBytes / 2 : 0);
+      for (int g = 0; g < ng; ++g)
+        for (int cnt = 1; cnt <= ng - g; ++cnt) {
+          __half* entry = pbase + (size_t)pair_w_units(ng, g, cnt) * (kPairUnitBytes / 2);
+          for (int r = 0; r < 32 * cnt; ++r) {
+            const int srow = 64 * g + 32 * cnt * rank + r;
+            const int gg = srow / 64, n = srow % 64;
+            const int ky = (parity ? 5 : 6) - 2 * gg;
+            for (int k = 0; k < 32; ++k) {
+              const int c = k >> 3, e = k & 7;
+              entry[r * 32 + ((c ^ ((r >> 1) & 3)) << 3) + e] = kmajor[n * 224 + ky * 32 + k];
+            }
+          }
+        }
+    }
+}
+
 // segment length (pooled rows) of the rolling kernel: fewest (waves x input rows per item); a segment re-reads 6
 // input rows of its upper neighbour, so longer is cheaper until the last wave goes idle
 inline void stem_roll_set_batch(StemRollParams& r, int nb, int num_sms, int* grid) {
@@ -581,12 +607,16 @@ inline void stem_roll_set_batch(StemRollParams& r, int nb, int num_sms, int* gri
   r.segs_per_image = (r.PH + best_rows - 1) / best_rows;
   r.num_items = nb * r.segs_per_image * r.n_xt;
   *grid = r.num_items < num_sms ? r.num_items : num_sms;
+  *grid &= ~1;  // CTA pairs need an even grid (n_xt == 2 makes the item count even); harmless otherwise unless 1
+  if (*grid == 0) *grid = 1;
 }
 
+// w_pair: pack_stem_pair's tables (or nullptr: single CTAs only); x1_halves: allocated size of the stem input
 inline bool build_stem_pool(const __half* x1, int S, int rows_per_parity, int row_pitch, const __half* w_stacked,
                             const float* bias, __half* pooled_out, int nb, int num_sms, StemPoolLaunch* L,
-                            std::string* err) {
+                            std::string* err, const __half* w_pair = nullptr, size_t x1_halves = 0) {
   memset(L, 0, sizeof(*L));
+  L->cg = 1;
   StemRollParams& r = L->r;
   r.vw = S / 2 + 3;
   if (row_pitch * 2 != r.vw * 16 || S % 16 != 0) {
@@ -615,6 +645,16 @@ inline bool build_stem_pool(const __half* x1, int S, int rows_per_parity, int ro
     ++r.n_xt;
     pb = pe;
   }
+  static const bool pairs_on = [] { const char* e = getenv("VNECT_B200_STEM_PAIRS"); return !(e && atoi(e) == 0); }();
+  if (pairs_on && w_pair != nullptr && r.n_xt == 2 && x1_halves >= 8 && num_sms >= 2) {
+    const uint64_t dims[2] = {8, (uint64_t)(x1_halves / 8)};
+    const uint64_t strides[1] = {16};
+    const uint32_t box[2] = {8, (uint32_t)(kRollStripLoad / 16)};
+    if (!encode_tmap(&L->tmap_x, x1, 2, dims, strides, box, 0, err)) return false;
+    L->cg = 2;
+    r.w = reinterpret_cast<const uint8_t*>(w_pair);
+    r.x1_units = (int64_t)(x1_halves / 8);
+  }
   stem_roll_set_batch(r, nb, num_sms, &L->grid);
   return true;
 }
@@ -622,15 +662,13 @@ inline bool build_stem_pool(const __half* x1, int S, int rows_per_parity, int ro
 inline void stem_pool_set_batch(StemPoolLaunch& L, int nb, int num_sms) { stem_roll_set_batch(L.r, nb, num_sms, &L.grid); }
 
 inline cudaError_t launch_stem_pool(const StemPoolLaunch& L, cudaStream_t st) {
-  static unsigned long long done = 0;
-  cudaError_t e = ensure_dyn_smem(stem_roll_kernel<false>, StemRollSmem::BYTES, &done);
-  if (e != cudaSuccess) return e;
-  if (L.r.dbg != nullptr) {
-    static unsigned long long done_dbg = 0;
-    if ((e = ensure_dyn_smem(stem_roll_kernel<true>, StemRollSmem::BYTES, &done_dbg)) != cudaSuccess) return e;
-    return launch_pdl(stem_roll_kernel<true>, dim3(L.grid), dim3(kRollThreads), StemRollSmem::BYTES, st, L.r);
-  }
-  return launch_pdl(stem_roll_kernel<false>, dim3(L.grid), dim3(kRollThreads), StemRollSmem::BYTES, st, L.r);
+  static unsigned long long done[4] = {0, 0, 0, 0};
+  auto go = [&](auto kern, unsigned long long* mask) -> cudaError_t {
+    if (cudaError_t e = ensure_dyn_smem(kern, StemRollSmem::BYTES, mask); e != cudaSuccess) return e;
+    return launch_pdl_cluster(kern, dim3(L.grid), dim3(kRollThreads), StemRollSmem::BYTES, st, L.cg, L.r, L.tmap_x);
+  };
+  if (L.cg == 2) return L.r.dbg != nullptr ? go(stem_roll_kernel<true, 2>, &done[3]) : go(stem_roll_kernel<false, 2>, &done[2]);
+  return L.r.dbg != nullptr ? go(stem_roll_kernel<true, 1>, &done[1]) : go(stem_roll_kernel<false, 1>, &done[0]);
 }
 
 }  // namespace vnect

@@ -328,11 +328,15 @@ static int run_stem_pool(int NB, int S, int num_sms) {
   for (auto& v : h_in) v = __float2half(frand());
   for (auto& v : h_w) v = __float2half(frand() * 0.15f);
   pack_stem_stacked(h_w.data(), h_ws.data());
+  std::vector<__half> h_wp((size_t)kPairWBytes);
+  pack_stem_pair(h_w.data(), h_wp.data());
   std::vector<float> h_bias(64);
   for (auto& v : h_bias) v = frand() * 0.5f;
-  __half *d_in, *d_w, *d_ws, *d_out;
+  __half *d_in, *d_w, *d_ws, *d_wp, *d_out;
   CK(cudaMalloc(&d_ws, h_ws.size() * 2));
   CK(cudaMemcpy(d_ws, h_ws.data(), h_ws.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&d_wp, h_wp.size() * 2));
+  CK(cudaMemcpy(d_wp, h_wp.data(), h_wp.size() * 2, cudaMemcpyHostToDevice));
   float *d_bias, *d_acc;
   CK(cudaMalloc(&d_in, in_elems * 2));
   CK(cudaMalloc(&d_w, h_w.size() * 2));
@@ -345,7 +349,7 @@ static int run_stem_pool(int NB, int S, int num_sms) {
   CK(cudaMemset(d_out, 0xff, out_elems * 2));
   StemPoolLaunch L;
   std::string err;
-  if (!build_stem_pool(d_in, S, rpp, pitch, d_ws, d_bias, d_out, NB, num_sms, &L, &err)) {
+  if (!build_stem_pool(d_in, S, rpp, pitch, d_ws, d_bias, d_out, NB, num_sms, &L, &err, d_wp, in_elems)) {
     printf("[stem_pool] build FAILED: %s\n", err.c_str());
     return 1;
   }
@@ -404,8 +408,8 @@ static int run_stem_pool(int NB, int S, int num_sms) {
     if (roll) printf("   CTA0 MMA warp cycles: wait-strips %llu, wait-slot %llu, total %llu\n", h_dbg[4], h_dbg[5], h_dbg[6]);
     L.r.dbg = nullptr;
   }
-  printf("[stem_roll rolling conv1+pool1 S=%d nb=%d] items=%d grid=%d x-tiles=%d seg_rows=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n",
-         S, NB, L.r.num_items, L.grid, L.r.n_xt, L.r.seg_rows, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
+  printf("[stem_roll rolling conv1+pool1 S=%d nb=%d cg=%d] items=%d grid=%d x-tiles=%d seg_rows=%d checked=%lld bad=%lld max_abs_err=%.3e  %s\n",
+         S, NB, L.cg, L.r.num_items, L.grid, L.r.n_xt, L.r.seg_rows, checked, bad, max_err, bad == 0 ? "PASS" : "FAIL");
   if (bad == 0) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
@@ -545,6 +549,17 @@ int main(int argc, char** argv) {
   if (argc > 1 && strcmp(argv[1], "probe") == 0) {
     run_desc_probe();
     return 0;
+  }
+  if (argc > 1 && strcmp(argv[1], "stem") == 0) {  // the fused conv1 + pool1 kernel only (VNECT_B200_STEM_PAIRS=0: single CTAs)
+    int f = 0;
+    f += run_stem_pool(2, 368, sms);
+    f += run_stem_pool(3, 448, sms);
+    f += run_stem_pool(1, 64, sms);
+    f += run_stem_pool(1, 512, sms);
+    f += run_stem_pool(32, 368, sms);
+    f += run_stem_pool(128, 368, sms);
+    printf(f ? "SELFTEST FAILED (%d failing cases)\n" : "SELFTEST PASSED (%d failing cases)\n", f);
+    return f ? 1 : 0;
   }
   if (argc > 1 && strcmp(argv[1], "epi") == 0) {  // the epilogue-bound 1x1 layers only (experiment builds)
     Case a = {"EPI TMARES 1x1 256->1024 +res 23x23 nb128", CONV_1x1, 128, 23, 23, 256, 1024, 1024, 256, EPI_TMA_RES, true, true, 1024, 0};

@@ -49,6 +49,21 @@ constexpr int kRollWEvenBytes = 256 * 64;  // [4 taps x 64 couts][32 K] fp16, 64
 constexpr int kRollWOddBytes = 192 * 64;   // [3 taps x 64 couts][32 K]
 static_assert(kRollWEvenBytes + kRollWOddBytes == kStemWBytes, "the two stacks hold all 7 row taps");
 
+// CTA pairs (cta_group::2): the two CTAs of a cluster take the two x tiles of one (forward, segment), the leader issues
+// M = 256 MMAs and each CTA supplies only HALF of the stacked-weight operand -- the MMA is bound by reading its
+// operands from shared memory (12 KB per 128 x 256 x 16 step with a single CTA, 8 KB per CTA in a pair).  An MMA over
+// `cnt` stacked taps starting at group g reads rows [64 g + 32 cnt rank, + 32 cnt) of the stack in CTA `rank`, from the
+// SAME shared-memory offset in both CTAs, so every (g, cnt) gets its own 2 KB * cnt entry in a per-rank table:
+//   even rows: g = 0..3, cnt = 1..4-g (20 units of 2 KB), odd rows: g = 0..2, cnt = 1..3-g (10 units).
+constexpr int kPairUnitBytes = 32 * 64;                 // 32 weight rows of 32 K values
+constexpr int kPairWEvenBytes = 20 * kPairUnitBytes;
+constexpr int kPairWBytes = 30 * kPairUnitBytes;        // per rank
+__host__ __device__ constexpr int pair_w_units(int n_groups, int g, int cnt) {  // entry offset in units, stack of n_groups
+  int u = 0;
+  for (int gg = 0; gg < g; ++gg) u += (n_groups - gg) * (n_groups - gg + 1) / 2;
+  return u + cnt * (cnt - 1) / 2;
+}
+
 struct StemRollParams {
   const uint8_t* x1;
   int64_t plane_bytes;
@@ -63,12 +78,13 @@ struct StemRollParams {
   int segs_per_image;
   int num_items;        // forwards * segs_per_image * n_xt
   int reverse;          // 1: walk the items from last to first (see ConvGemmParams::reverse)
+  int64_t x1_units;     // CTA pairs: 16-byte units the strip tensor map covers
   unsigned long long* dbg;  // optional [4] cycle counters of CTA 0 (selftest only): wait-for-MMA, drain, pool, total
 };
 
 struct StemRollSmem {
   static constexpr int W_OFF = 0;
-  static constexpr int STRIP_OFF = kStemWBytes;
+  static constexpr int STRIP_OFF = kPairWBytes;  // the single-CTA kernel uses the first kStemWBytes of it
   static constexpr int ROW_OFF = ((STRIP_OFF + kRollStages * kRollStripBytes + 1023) / 1024) * 1024;
   static constexpr int BAR_OFF = ROW_OFF + kRollRowBufs * kRollRowBytes;
   static constexpr int CMD_OFF = BAR_OFF + 1024;                 // issue program of one item: 32 B per input row
@@ -115,9 +131,13 @@ __device__ __forceinline__ long long roll_clock() {
   else return 0;
 }
 
-template <bool DBG = false>
-__global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid_constant__ StemRollParams p) {
+template <bool DBG = false, int CG = 1>
+__global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid_constant__ StemRollParams p,
+                                                                    const __grid_constant__ CUtensorMap tmap_x) {
   constexpr uint32_t TMEM_COLS = 512;
+  constexpr int kWBytes = CG == 2 ? kPairWBytes : kStemWBytes;
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int worker = blockIdx.x / CG, n_workers = gridDim.x / CG, n_units = p.num_items / CG;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_smem = smem + StemRollSmem::W_OFF;
@@ -141,39 +161,60 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
     }
     for (int s = 0; s < kRollSlots; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 8);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], 8 * CG);  // one arrive per epilogue warp (of both CTAs of a pair, on the leader's barrier)
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();
+    if constexpr (CG == 2) {
+      tma_prefetch_desc(&tmap_x);
+      // the weights are constants: fetched before the predecessor has finished, and resident in BOTH CTAs before the
+      // cluster barrier below lets the leader issue anything that reads the peer's half
+      mbar_arrive_expect_tx(w_bar, kWBytes);
+      bulk_load_1d(w_smem, p.w + static_cast<size_t>(cta_rank) * kPairWBytes, kWBytes, w_bar);
+    }
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_pair<TMEM_COLS>(tmem_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   if (threadIdx.x >= 128 && threadIdx.x < 192) bias_s[threadIdx.x - 128] = p.bias[threadIdx.x - 128];
   pdl_launch_dependents();
   pdl_wait();  // bias (read above) is a constant; the input strips come from the previous kernel
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) {
+    if (warp == 0) mbar_wait(w_bar, 0);
+    cluster_sync_all();  // the peer's barriers are initialised and its weights resident before anything signals / reads them
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ================================================================ strip loader: one bulk copy per padded input row
     const bool issuer = elect_one();
-    if (issuer) {
-      mbar_arrive_expect_tx(w_bar, kStemWBytes);
-      bulk_load_1d(w_smem, p.w, kStemWBytes, w_bar);
+    if constexpr (CG == 1) {
+      if (issuer) {
+        mbar_arrive_expect_tx(w_bar, kStemWBytes);
+        bulk_load_1d(w_smem, p.w, kStemWBytes, w_bar);
+      }
     }
     int stage = 0;
     uint32_t phase = 0;
-    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-      const RollItem R = roll_decode(p, it);
-      const uint8_t* base = p.x1 + static_cast<int64_t>(R.img) * 2 * p.plane_bytes + 16ll * p.xt_x0[R.xt];
+    for (int u = worker; u < n_units; u += n_workers) {
+      const RollItem R = roll_decode(p, u * CG + cta_rank);
+      const int64_t base_off = static_cast<int64_t>(R.img) * 2 * p.plane_bytes + 16ll * p.xt_x0[R.xt];
       for (int ri = 0; ri < R.n_in; ++ri) {
         const int r = 2 * R.ya + ri;
+        const int64_t off = base_off + (r & 1) * p.plane_bytes + 16ll * (r >> 1) * p.vw;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (issuer) {
-          mbar_arrive_expect_tx(&full_bar[stage], kRollStripLoad);
-          bulk_load_1d(strips + stage * kRollStripBytes, base + (r & 1) * p.plane_bytes + 16ll * (r >> 1) * p.vw,
-                       kRollStripLoad, &full_bar[stage]);
+          if constexpr (CG == 2) {  // both CTAs' strips are counted on the leader's barrier
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kRollStripLoad);
+            tma_load_2d_pair(strips + stage * kRollStripBytes, &tmap_x, &full_bar[stage], 0, static_cast<int>(off >> 4));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], kRollStripLoad);
+            bulk_load_1d(strips + stage * kRollStripBytes, p.x1 + off, kRollStripLoad, &full_bar[stage]);
+          }
         }
         __syncwarp();
         if (++stage == kRollStages) {
@@ -182,15 +223,26 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
         }
       }
     }
-  } else if (warp == 1) {
+    if constexpr (CG == 2) {
+      // drain: the leader's multicast commits still arrive on this CTA's empty barriers after its last load; the CTA
+      // may not retire before every slot has been released
+      for (int s2 = 0; s2 < kRollStages; ++s2) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (++stage == kRollStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && cta_rank == 0) {
     // ================================================================ MMA issuer (warp-converged, one lane issues)
     // Which accumulators an input row feeds, where a run wraps around the TMEM ring, which slot has to be waited for
     // and which row completes is ~100 dependent scalar instructions per input row; done inline, that arithmetic (not
     // the tensor pipe) set the pace.  So the 32 lanes first write the whole item's issue program into a smem table,
     // one input row per lane, and the issue loop only loads a 32-byte command and fires.
     const bool issuer = elect_one();
-    mbar_wait(w_bar, 0);
-    const uint32_t w_even = (smem_u32(w_smem) & 0x3FFFF) >> 4, w_odd = w_even + (kRollWEvenBytes >> 4);
+    if constexpr (CG == 1) mbar_wait(w_bar, 0);
+    const uint32_t w_even = (smem_u32(w_smem) & 0x3FFFF) >> 4, w_odd = w_even + ((CG == 2 ? kPairWEvenBytes : kRollWEvenBytes) >> 4);
     const uint32_t a_lo0 = ((smem_u32(strips) & 0x3FFFF) >> 4) | (1u << 16);  // no-swizzle K-major: LBO = 16 B
     constexpr uint32_t kADescHi = (128u >> 4) | (1u << 14);                    // SBO = 128 B, descriptor version 1
     constexpr uint32_t kBDescHi = (512u >> 4) | (1u << 14) | (4u << 29);       // SBO = 512 B, version 1, 64B swizzle
@@ -201,8 +253,8 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
     int G0 = 0;  // conv rows this CTA has started before the current item: row G lives in TMEM slot G & 7
     long long m_full = 0, m_empty = 0;
     const long long m_begin = roll_clock<DBG>();
-    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-      const RollItem R = roll_decode(p, it);
+    for (int u = worker; u < n_units; u += n_workers) {
+      const RollItem R = roll_decode(p, u * CG + cta_rank);
       for (int ri = lane; ri < R.n_in; ri += 32) {
         const bool even = !(ri & 1);
         const int ly_hi = min(R.n_rows - 1, ri >> 1);
@@ -213,13 +265,20 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
         const int ky = ri - 2 * ly_lo;                    // tap of the first row; later rows: ky - 2, ...
         const int g = even ? (6 - ky) >> 1 : (5 - ky) >> 1;  // its 64-row group in the stacked weights
         const uint32_t wb = (even ? w_even : w_odd) | (1u << 16);
+        const int cnt2 = total - cnt1 > 0 ? total - cnt1 : 1;
         uint4 c0, c1;
         c0.x = static_cast<uint32_t>(slot * 64);                    // run 1: TMEM column offset
-        c0.y = make_idesc_f16(kBlockM, 64 * cnt1, false);
-        c0.z = wb + static_cast<uint32_t>(g * (4096 >> 4));          // low word of the B descriptor
+        c0.y = make_idesc_f16(kBlockM * CG, 64 * cnt1, false);
         c0.w = cnt1 < total ? 0u : kNone;                            // run 2 starts at slot 0
-        c1.x = make_idesc_f16(kBlockM, 64 * (total - cnt1 > 0 ? total - cnt1 : 1), false);
-        c1.y = wb + static_cast<uint32_t>((g + cnt1) * (4096 >> 4));
+        c1.x = make_idesc_f16(kBlockM * CG, 64 * cnt2, false);
+        if constexpr (CG == 2) {  // per-(group, count) entries of the pair table
+          const int ng = even ? 4 : 3;
+          c0.z = wb + static_cast<uint32_t>(pair_w_units(ng, g, cnt1) * (kPairUnitBytes >> 4));
+          c1.y = wb + static_cast<uint32_t>(pair_w_units(ng, min(g + cnt1, ng - 1), cnt2) * (kPairUnitBytes >> 4));
+        } else {
+          c0.z = wb + static_cast<uint32_t>(g * (4096 >> 4));        // low word of the B descriptor
+          c1.y = wb + static_cast<uint32_t>((g + cnt1) * (4096 >> 4));
+        }
         // first tap (ky = 0) of conv row ri/2: its slot must have been drained and zeroed
         const int Gt = G0 + (ri >> 1);
         c1.z = (even && (ri >> 1) < R.n_rows) ? static_cast<uint32_t>((Gt & 7) | (((Gt >> 3) & 1) << 8)) : kNone;
@@ -243,15 +302,30 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
         if (issuer) {
           const uint64_t a_desc = (static_cast<uint64_t>(kADescHi) << 32) | (a_lo0 + static_cast<uint32_t>(stage * (kRollStripBytes >> 4)));
           const uint64_t b1 = (static_cast<uint64_t>(kBDescHi) << 32) | c0.z;
-          umma_f16(tmem_base + c0.x, a_desc, b1, c0.y, 1u);
-          umma_f16(tmem_base + c0.x, a_desc + 2, b1 + 2, c0.y, 1u);  // +32 B of A, +32 B along K of B
+          if constexpr (CG == 2) {
+            umma_f16_pair(tmem_base + c0.x, a_desc, b1, c0.y, 1u);
+            umma_f16_pair(tmem_base + c0.x, a_desc + 2, b1 + 2, c0.y, 1u);
+          } else {
+            umma_f16(tmem_base + c0.x, a_desc, b1, c0.y, 1u);
+            umma_f16(tmem_base + c0.x, a_desc + 2, b1 + 2, c0.y, 1u);  // +32 B of A, +32 B along K of B
+          }
           if (c0.w != kNone) {
             const uint64_t b2 = (static_cast<uint64_t>(kBDescHi) << 32) | c1.y;
-            umma_f16(tmem_base, a_desc, b2, c1.x, 1u);
-            umma_f16(tmem_base, a_desc + 2, b2 + 2, c1.x, 1u);
+            if constexpr (CG == 2) {
+              umma_f16_pair(tmem_base, a_desc, b2, c1.x, 1u);
+              umma_f16_pair(tmem_base, a_desc + 2, b2 + 2, c1.x, 1u);
+            } else {
+              umma_f16(tmem_base, a_desc, b2, c1.x, 1u);
+              umma_f16(tmem_base, a_desc + 2, b2 + 2, c1.x, 1u);
+            }
           }
-          if (c1.w != kNone) umma_commit(&tmem_full[c1.w]);
-          umma_commit(&empty_bar[stage]);
+          if constexpr (CG == 2) {  // both CTAs' epilogues / loaders
+            if (c1.w != kNone) umma_commit_pair(&tmem_full[c1.w]);
+            umma_commit_pair(&empty_bar[stage]);
+          } else {
+            if (c1.w != kNone) umma_commit(&tmem_full[c1.w]);
+            umma_commit(&empty_bar[stage]);
+          }
         }
         __syncwarp();
         if (++stage == kRollStages) {
@@ -285,13 +359,16 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
     tc_fence_before();
     __syncwarp();
     if (lane == 0)
-      for (int s = 0; s < kRollSlots; ++s) mbar_arrive(&tmem_empty[s]);
+      for (int s = 0; s < kRollSlots; ++s) {
+        if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[s]);
+        else mbar_arrive(&tmem_empty[s]);
+      }
     int G0 = 0;
     uint32_t win = 0;  // pooling windows done by this CTA: column maxima alternate between two smem buffers
     long long t_wait = 0, t_drain = 0, t_pool = 0;
     const long long t_begin = roll_clock<DBG>();
-    for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
-      const RollItem R = roll_decode(p, it);
+    for (int u = worker; u < n_units; u += n_workers) {
+      const RollItem R = roll_decode(p, u * CG + cta_rank);
       const int x0 = p.xt_x0[R.xt], pb = p.xt_pb[R.xt], pe = p.xt_pe[R.xt];
       __half2 row_a[16], row_b[16];  // the open window's first (even) and second (odd) conv row, this thread's column
       for (int ly = 0; ly < R.n_rows; ++ly) {
@@ -309,7 +386,10 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[G & 7]);
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_leader(&tmem_empty[G & 7]);
+          else mbar_arrive(&tmem_empty[G & 7]);
+        }
         __half2 cur[16];  // bias + ReLU + fp16 pack (cvt.rn.relu does the max(.,0) while packing)
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -380,9 +460,11 @@ __global__ void __launch_bounds__(kRollThreads, 1) stem_roll_kernel(const __grid
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // neither CTA may retire while its partner can still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 

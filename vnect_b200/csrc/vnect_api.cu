@@ -745,15 +745,19 @@ int vnect_finalize(vnect_t* h) {
   {  // conv1 + pool1 (vnect_model.py:27-29) fused: rolling raw-strip implicit GEMM + max-pool (stem_roll.cuh)
     std::vector<__half> wk = to_half(pack_stem(h->vars.at("conv1/weights"))), ws(wk.size());
     pack_stem_stacked(wk.data(), ws.data());
-    __half* dws = nullptr;
+    std::vector<__half> wp((size_t)kPairWBytes);  // two ranks x kPairWBytes / 2 halves
+    pack_stem_pair(wk.data(), wp.data());
+    __half *dws = nullptr, *dwp = nullptr;
     float* db = nullptr;
     if ((rc = upload(h, ws, &dws))) return rc;
+    if ((rc = upload(h, wp, &dwp))) return rc;
     if ((rc = upload(h, h->vars.at("conv1/biases").data, &db))) return rc;
     if ((rc = new_act(h, "pool1", S / 4, S / 4, 64))) return rc;
     Step st;
     st.kind = 3; st.name = "conv1+pool1";
     std::string err;
-    if (!build_stem_pool(h->x1, S, h->stem_rpp, h->stem_pitch, dws, db, h->acts.at("pool1").p, nb, h->num_sms, &st.stem_pool, &err))
+    if (!build_stem_pool(h->x1, S, h->stem_rpp, h->stem_pitch, dws, db, h->acts.at("pool1").p, nb, h->num_sms, &st.stem_pool, &err,
+                         dwp, (size_t)nb * 2 * h->stem_rpp * h->stem_pitch + 16384))
       return fail(h, VNECT_E_CUDA, "conv1+pool1: %s", err.c_str());
     h->steps.push_back(st);
   }
