@@ -430,10 +430,16 @@ def main():
     fwd_ms, per = eng.time_forward(nf * len(SCALES), reps=3, per_layer=True)
     conv_ms = sum(per.values())  # every launch of one forward batch is an implicit-GEMM kernel (pool1 is fused)
     peaks, peak_src = measured_peaks()
-    achieved = EXECUTED_FLOPS_PER_FORWARD * nf * len(SCALES) / (conv_ms * 1e-3) / 1e12
+    # the family's launch time inside a step = the forward as it runs there (back to back, programmatic dependent
+    # launch); the sum of the layers timed one by one (conv_ms) adds a launch ramp per layer and is kept as a second view.
+    # Flops: the ones EXECUTED (res2b / res2c / res3d are evaluated at even pixels only); the reference graph's count
+    # (SURVEY.md section 8d, 23.83 GFLOP per forward) gives frac_algorithmic.
+    achieved = EXECUTED_FLOPS_PER_FORWARD * nf * len(SCALES) / (fwd_ms * 1e-3) / 1e12
+    achieved_alg = FLOPS_PER_FORWARD * nf * len(SCALES) / (fwd_ms * 1e-3) / 1e12
+    achieved_ser = EXECUTED_FLOPS_PER_FORWARD * nf * len(SCALES) / (conv_ms * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     traffic, traffic_note = None, None
-    try:  # DRAM traffic of the same launches from the committed ncu capture (profiles/r01_step_traffic.txt)
+    try:  # DRAM traffic of the same launches from the committed ncu capture (profiles/conv_traffic.json names its source)
         with open(os.path.join(ROOT, "profiles", "conv_traffic.json")) as f:
             tj = json.load(f)
         if tj.get("frames_per_step") == nf:
@@ -451,10 +457,13 @@ def main():
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained (burst %.1f)" % (peak_src, peaks["bf16_tflops"]),
                 "traffic": traffic, "traffic_note": traffic_note,
                 "hbm_view": None if traffic is None else {
-                    "achieved_gbs": traffic / (conv_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
-                    "frac": traffic / (conv_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                    "note": "the family mixes tensor-bound 3x3 convs with HBM-bound 1x1 expand convs; per-launch numbers in profiles/r01_step_traffic.txt"},
+                    "achieved_gbs": traffic / (fwd_ms * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                    "frac": traffic / (fwd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "note": "the family mixes tensor-bound 3x3 convs with HBM-bound 1x1 expand convs; per-launch numbers in profiles/r02_step_traffic.txt"},
                 "frac_of_burst": achieved / peaks["bf16_tflops"],
+                "frac_algorithmic": achieved_alg / peak, "frac_algorithmic_of_burst": achieved_alg / peaks["bf16_tflops"],
+                "frac_layers_timed_one_by_one": achieved_ser / peak,
+                "time_basis": "forward_ms_per_batch: CUDA events around the %d launches of one forward batch, run back to back as in a step" % len(per),
                 "conv_ms_per_batch": conv_ms, "forward_ms_per_batch": fwd_ms,
                 "flops_per_forward_executed": EXECUTED_FLOPS_PER_FORWARD, "flops_per_forward_reference": FLOPS_PER_FORWARD}
 

@@ -871,3 +871,26 @@ def test_joints2angles_vs_reference_golden(golden):
         assert np.all(np.abs(np.array(Joints2Angles.joints2angles(g["poses"][3], engine=eng)) - g["static"][3]) <= tol)
     finally:
         eng.close()
+
+
+def test_surround_rewritten_after_operator_level_forward(engine_w0):
+    """The black surround of a shrunken scale is a per-slot constant of the stem input, written once (pyramid_kernel,
+    `full`).  vnect_forward puts caller-supplied images into the same buffer: the next estimate must rewrite it --
+    same joints as before, bit for bit, also when the call replays a captured graph."""
+    frames = np.stack([synth.frame_c2(40 + i) for i in range(3)])
+    ids = np.arange(3)
+    runs = []
+    for k in range(4):
+        if k in (1, 3):  # clobber every slot with images that are NOT -0.4 outside the shrunken picture
+            x = np.random.default_rng(5 + k).standard_normal((6, 368, 368, 3)).astype(np.float32)
+            engine_w0.forward(x)
+        engine_w0.reset()
+        j2, j3 = engine_w0.estimate(frames, ids, np.full(3, 2.0), np.full(3, 2.004))
+        runs.append((j2.copy(), j3.copy(), engine_w0.raw_argmax(3).copy()))
+    for j2, j3, raw in runs[1:]:
+        assert np.array_equal(raw, runs[0][2])
+        assert np.array_equal(j2, runs[0][0]) and np.array_equal(j3, runs[0][1])
+    # and the pre-processing tap still shows the surround
+    got, _, _ = engine_w0.preprocess(frames[0])
+    ref, _, _ = prepost.gen_input_batch(frames[0], 368, SCALES2)
+    assert np.array_equal(got, ref.astype(np.float16).astype(np.float32))
