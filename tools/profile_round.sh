@@ -8,7 +8,7 @@
 set -u
 TAG=${1:-rXX}
 PER_STEP=${2:-46}
-SKIP=$((2 * PER_STEP))
+SKIP=$((2 * PER_STEP + 1))  # + the one-off surround initialisation of the first call
 export VNECT_B200_NO_GRAPH=1
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c $PER_STEP --csv \
@@ -20,8 +20,8 @@ ncu --set full --clock-control none -s $SKIP -c $PER_STEP -f -o /tmp/${TAG}_full
     python tools/profile_step.py 2 1 > gpurun_out/${TAG}_ncu_full.log 2>&1
 ncu -i /tmp/${TAG}_full_all.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_all.csv 2>> gpurun_out/${TAG}_ncu_full.log
 # source-correlated single launches: the fused block tail (first of the step), the halo 3x3 (res2a_branch2b), the stem
-ncu --set full --clock-control none --import-source on -k regex:block_tail_kernel -s 8 -c 1 -f -o gpurun_out/prof_conv_tail \
+ncu --set full --clock-control none --import-source on -k regex:stem_roll_kernel -s 2 -c 1 -f -o gpurun_out/prof_stem \
     python tools/profile_step.py 2 1 >> gpurun_out/${TAG}_ncu_full.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:postprocess_kernel -s 2 -c 1 -f -o gpurun_out/prof_prepost \
+ncu --set full --clock-control none --import-source on -k regex:"postprocess_kernel|pyramid_kernel" -s 5 -c 2 -f -o gpurun_out/prof_prepost \
     python tools/profile_step.py 2 1 >> gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out/*.csv gpurun_out/*.ncu-rep

@@ -140,5 +140,5 @@ def full_csv():
 launches()
 traffic()
 full_csv()
-full("prof_conv*.ncu-rep", "conv")
+full("prof_stem.ncu-rep", "stem")
 full("prof_prepost.ncu-rep", "prepost")
