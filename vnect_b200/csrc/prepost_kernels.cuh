@@ -870,6 +870,7 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
   };
   const int nq = s_nq;
   const bool one_warp = nq <= kQuadPar;  // the usual case: a handful of quads
+  if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 16 + 13] = (unsigned long long)nq;
   if (one_warp) {
     // every cell of every surviving quad on its own thread, then every candidate on its own lane of warp 0; meanwhile
     // two lanes of warp 1 advance the clock-only part of this joint's 2D filters

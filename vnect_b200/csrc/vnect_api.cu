@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <tuple>
 #include <map>
+#include <algorithm>
 #include <set>
 #include <string>
 #include <vector>
@@ -1728,6 +1729,18 @@ int vnect_time_prepost(vnect_t* h, int32_t n_frames, int32_t reps, float* pre_ms
                 1e3 * (double)(tr[(size_t)b * 16 + 12] - tr[(size_t)b * 16 + 11]) / (double)(tr[(size_t)b * 16 + 10] - tr[(size_t)b * 16]));
         break;
       }
+    {  // survivors per block and the spread of the blocks' own durations (start -> fence + counter)
+      std::vector<double> dur;
+      std::vector<unsigned long long> nqs;
+      for (int b = 0; b < nb; ++b) {
+        dur.push_back((tr[(size_t)b * 16 + 9] - tr[(size_t)b * 16]) * 1e-3);
+        nqs.push_back(tr[(size_t)b * 16 + 13]);
+      }
+      std::sort(dur.begin(), dur.end());
+      std::sort(nqs.begin(), nqs.end());
+      fprintf(stderr, "  block duration p50 %.2f p90 %.2f p99 %.2f max %.2f us; surviving quads per block p50 %llu p90 %llu p99 %llu max %llu\n",
+              dur[nb / 2], dur[nb * 9 / 10], dur[nb * 99 / 100], dur[nb - 1], nqs[nb / 2], nqs[nb * 9 / 10], nqs[nb * 99 / 100], nqs[nb - 1]);
+    }
     for (int k = 1; k <= 10; ++k) {
       double sum = 0, mx = 0; int cnt = 0;
       for (int b = 0; b < nb; ++b) {
@@ -1757,6 +1770,18 @@ int vnect_time_prepost(vnect_t* h, int32_t n_frames, int32_t reps, float* pre_ms
                 1e3 * (double)(tr[(size_t)b * 16 + 12] - tr[(size_t)b * 16 + 11]) / (double)(tr[(size_t)b * 16 + 10] - tr[(size_t)b * 16]));
         break;
       }
+    {  // survivors per block and the spread of the blocks' own durations (start -> fence + counter)
+      std::vector<double> dur;
+      std::vector<unsigned long long> nqs;
+      for (int b = 0; b < nb; ++b) {
+        dur.push_back((tr[(size_t)b * 16 + 9] - tr[(size_t)b * 16]) * 1e-3);
+        nqs.push_back(tr[(size_t)b * 16 + 13]);
+      }
+      std::sort(dur.begin(), dur.end());
+      std::sort(nqs.begin(), nqs.end());
+      fprintf(stderr, "  block duration p50 %.2f p90 %.2f p99 %.2f max %.2f us; surviving quads per block p50 %llu p90 %llu p99 %llu max %llu\n",
+              dur[nb / 2], dur[nb * 9 / 10], dur[nb * 99 / 100], dur[nb - 1], nqs[nb / 2], nqs[nb * 9 / 10], nqs[nb * 99 / 100], nqs[nb - 1]);
+    }
     for (int k = 1; k <= 10; ++k) {
       double sum = 0, mx = 0; int cnt = 0;
       for (int b = 0; b < nb; ++b) {
