@@ -460,6 +460,8 @@ struct PostParams {
   double* packed;                 // optional [n_frames][21][5] = (row, col, x, y, z): the layout the multi-GPU gather moves
   unsigned int* nonfinite;        // counts (frame, joint) blocks that met a NaN / Inf in the CNN's maps (fp16 overflow guard)
   unsigned int* nonfinite_flag;   // host-visible (mapped pinned) word of the submitting lane: set to 1 in that case
+  double* prep3;                  // [n_frames][21][3][3] scratch: clock-only part (freq, te, alpha_d) of every 3D filter step,
+                                  // computed by the joint's own block while it is otherwise idle, used by the frame's tail
   // shared-memory plan of one block (post_smem_plan, host): which raw cells of every scale's heat-map plane are staged
   // and where.  An identity scale needs its whole plane, a resized one only the rows its centre crop samples.
   int identity_mask;              // bit sc: scale sc is a plain copy
@@ -624,6 +626,7 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
   extern __shared__ float4 s_dyn4[];
   float* s_dyn = reinterpret_cast<float*>(s_dyn4);
   __shared__ int4 s_rowpk[NS][kMaxHm];  // y-axis resize entries as byte offsets: (j0*hs*4, j1*hs*4, b0, b1)
+  __shared__ int4 s_colpk[NS][kMaxHm];  // x-axis entries: (i0*4, i1*4, a0, a1) -- the exact path looks them up per quad
   __shared__ float s_wmax[kPostMaxWarps], s_wmin[kPostMaxWarps], s_wamax[kPostMaxWarps];
   __shared__ int s_widx[kPostMaxWarps];
   __shared__ double s_bval[kPostMaxWarps];
@@ -637,6 +640,8 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
   __shared__ double s_t2;
   __shared__ double s_exact[kQuadPar * 4];
   __shared__ double s_prep[2][3];
+  __shared__ __align__(16) FilterState s_st3[3];
+  __shared__ double s_t3;
   __shared__ int s_sid;
 
   const int frame = blockIdx.x / kJoints;
@@ -669,6 +674,7 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
         int4 rp = T.rowpk[i];
         rp.x *= 4; rp.y *= 4;
         s_rowpk[sc][i] = rp;
+        s_colpk[sc][i] = make_int4(T.i0[i] * 4, T.i1[i] * 4, __float_as_int(T.a0[i]), __float_as_int(T.a1[i]));
       }
     }
   }
@@ -700,7 +706,11 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
         const int sid = p.stream_ids[frame];
         cp_async_16(reinterpret_cast<char*>(s_st2) + tid * 16,
                     reinterpret_cast<const char*>(p.st2d + ((size_t)sid * kJoints + joint) * 2) + tid * 16);
-        if (tid == 0) { s_sid = sid; s_t2 = p.t2d[frame]; }
+        if (tid == 0) { s_sid = sid; s_t2 = p.t2d[frame]; s_t3 = p.t3d[frame]; }
+      } else if (tid < 15 && p.filters_on) {  // this joint's three 3D filter states (144 contiguous bytes)
+        const int sid = p.stream_ids[frame];
+        cp_async_16(reinterpret_cast<char*>(s_st3) + (tid - 6) * 16,
+                    reinterpret_cast<const char*>(p.st3d + ((size_t)sid * kJoints + joint) * 3) + (tid - 6) * 16);
       }
     }
     cp_async_commit();
@@ -794,7 +804,11 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
     // n >= 3 (on both sides of the comparison: 1.5e-6 * max|v| at n = 4), the upsample's own rounding by 1e-16
     thr = any_bad ? -INFINITY : __double2float_rd(v - (double)bamax * (1e-6 * ns));
   }
-  // cells that may belong to the argmax's quad -> the (up to four) quads around each
+  // Cells that may belong to the argmax's quad -> the (up to four) quads around each, filtered once more: every
+  // candidate of a quad has fractions in [0, 15/16] on both axes and the upsample is affine in each, so its largest
+  // candidate is at most the largest of the four corner values of that box -- a far tighter cap than the quad's largest
+  // cell (with random-init maps the plain cell test left 20 quads per joint in the median, 170 at worst).  A quad is
+  // listed by the first of its cells (row-major) that passed the cell test.
   if (act && tmax >= thr) {
     unsigned long long rows = 0;  // bit k: this thread's k-th cell passes (hs <= 64 rows)
     int k = 0;
@@ -805,6 +819,18 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
       rows &= rows - 1;
       for (int qy = max(y - 1, 0); qy <= y; ++qy)
         for (int qx = max(x - 1, 0); qx <= x; ++qx) {
+          const int qy1 = min(qy + 1, hs - 1), qx1 = min(qx + 1, hs - 1);
+          const float s00 = s_sum[qy * hs + qx], s01 = s_sum[qy * hs + qx1], s10 = s_sum[qy1 * hs + qx], s11 = s_sum[qy1 * hs + qx1];
+          // an earlier cell of the quad passed the cell test too: that one lists it
+          const bool first = (qy == y && qx == x) || (qy == y && !(s00 >= thr)) ||
+                             (qy != y && qx == x && !(s00 >= thr) && !(s01 >= thr && qx1 != qx)) ||
+                             (qy != y && qx != x && !(s00 >= thr) && !(s01 >= thr) && !(s10 >= thr));
+          if (!first) continue;
+          const float f = 0.9375f;
+          const float h0 = fmaf(s01 - s00, f, s00), h1 = fmaf(s11 - s10, f, s10);
+          const float cap = fmaxf(fmaxf(s00, h0), fmaxf(fmaf(s10 - s00, f, s00), fmaf(h1 - h0, f, h0)));
+          // float32 evaluation of the cap: a few 2^-24 relative, far inside the margin already taken off thr
+          if (!(cap >= thr)) continue;
           const int slot = atomicAdd(&s_nq, 1);
           if (slot < kQuadCap) s_quads[slot] = (unsigned short)(qy * hs + qx);
         }
@@ -826,14 +852,12 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
           v = sc == p.alias_scale ? __ldg(p.maps + ((size_t)(frame * ns + sc) * 84 + joint) * cells + c)
                                   : *reinterpret_cast<const float*>(pl[sc] + c * 4);
         } else {
-          const ScaleTable& T = p.tables[sc];
-          const int4 rp = s_rowpk[sc][y];
-          const float* r0 = reinterpret_cast<const float*>(pl[sc] + rp.x);
-          const float* r1 = reinterpret_cast<const float*>(pl[sc] + rp.y);
-          const int x0 = T.i0[xx], x1 = T.i1[xx];
-          const float a0 = T.a0[xx], a1 = T.a1[xx];
-          const float t0 = __fadd_rn(__fmul_rn(r0[x0], a0), __fmul_rn(r0[x1], a1));
-          const float t1 = __fadd_rn(__fmul_rn(r1[x0], a0), __fmul_rn(r1[x1], a1));
+          const int4 rp = s_rowpk[sc][y], cp = s_colpk[sc][xx];
+          const char* r0 = pl[sc] + rp.x;
+          const char* r1 = pl[sc] + rp.y;
+          const float a0 = __int_as_float(cp.z), a1 = __int_as_float(cp.w);
+          const float t0 = __fadd_rn(__fmul_rn(*reinterpret_cast<const float*>(r0 + cp.x), a0), __fmul_rn(*reinterpret_cast<const float*>(r0 + cp.y), a1));
+          const float t1 = __fadd_rn(__fmul_rn(*reinterpret_cast<const float*>(r1 + cp.x), a0), __fmul_rn(*reinterpret_cast<const float*>(r1 + cp.y), a1));
           v = __fadd_rn(__fmul_rn(t0, __int_as_float(rp.z)), __fmul_rn(t1, __int_as_float(rp.w)));
         }
         acc = __dadd_rn(acc, (double)v);
@@ -871,19 +895,28 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
   const int nq = s_nq;
   const bool one_warp = nq <= kQuadPar;  // the usual case: a handful of quads
   if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 16 + 13] = (unsigned long long)nq;
+  // Five lanes of warp 1 advance the clock-only part (four dependent divisions, ~0.5 us each here) of this joint's two 2D
+  // and three 3D filter steps while warp 0 evaluates the quads; the 3D ones go to global scratch for the frame's tail.
+  if (p.filters_on && tid >= 32 && tid < 37) {
+    const int k = tid - 32;
+    if (k < 2) {
+      const FilterPrep f = oef_prepare(s_st2[k], p.cfg2d, s_t2);
+      s_prep[k][0] = f.freq; s_prep[k][1] = f.te; s_prep[k][2] = f.a_d;
+    } else {
+      const FilterPrep f = oef_prepare(s_st3[k - 2], p.cfg3d, s_t3);
+      double* o = p.prep3 + ((size_t)(frame * kJoints + joint) * 3 + (k - 2)) * 3;
+      o[0] = f.freq; o[1] = f.te; o[2] = f.a_d;
+    }
+  }
   if (one_warp) {
-    // every cell of every surviving quad on its own thread, then every candidate on its own lane of warp 0; meanwhile
-    // two lanes of warp 1 advance the clock-only part of this joint's 2D filters
+    // every cell of every surviving quad on its own thread, then every candidate on its own lane of warp 0
     for (int i = tid; i < nq * 4; i += nthreads) {
       const int q = s_quads[i >> 2];
       const int qy = q / hs, qx = q - qy * hs;
       s_exact[i] = exact_cell(min(qy + ((i >> 1) & 1), hs - 1), min(qx + (i & 1), hs - 1));
     }
-    if (p.filters_on && tid >= 32 && tid < 34) {
-      const FilterPrep f = oef_prepare(s_st2[tid - 32], p.cfg2d, s_t2);
-      s_prep[tid - 32][0] = f.freq; s_prep[tid - 32][1] = f.te; s_prep[tid - 32][2] = f.a_d;
-    }
     __syncthreads();
+    if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 16 + 14] = globaltimer_ns();
     if (warp_id == 0) {
       for (int i = lane_id; i < nq * 9; i += 32) {
         const int qi = i / 9, slot = i - qi * 9;
@@ -938,12 +971,8 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
       p.raw_argmax[(frame * kJoints + joint) * 2 + tid] = (tid == 0) ? row : col;
       if (p.filters_on) {
         FilterState st2 = s_st2[tid];
-        if (one_warp) {
-          const FilterPrep f = {s_prep[tid][0], s_prep[tid][1], s_prep[tid][2]};
-          coord = oef_finish(st2, p.cfg2d, f, coord, s_t2, false);
-        } else {
-          coord = oef_step(st2, p.cfg2d, coord, s_t2, false);
-        }
+        const FilterPrep f = {s_prep[tid][0], s_prep[tid][1], s_prep[tid][2]};
+        coord = oef_finish(st2, p.cfg2d, f, coord, s_t2, false);
         p.st2d[((size_t)s_sid * kJoints + joint) * 2 + tid] = st2;
       }
       p.j2_box[(frame * kJoints + joint) * 2 + tid] = coord;
@@ -964,6 +993,25 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
     x0 = min(max(x0, 0), hs - 1);    // memory safety only: filtered joints stay inside the box
     y0 = min(max(y0, 0), hs - 1);
     const int x1 = min(x0 + 1, hs - 1), y1 = min(y0 + 1, hs - 1);
+    // rescale to input pixels (estimator.py:138-139; + the crop origin for tracked streams, run_estimator.py:104-105):
+    // two lanes of warp 1, beside the gather of warp 0
+    if (tid >= 32 && tid < 34) {
+      const int c = tid - 32;
+      const double jb = c == 0 ? py : px;
+      double off = (c == 0) ? (double)p.off_y : (double)p.off_x, scaler = p.scaler;
+      double v2;
+      if (p.geoms != nullptr) {
+        const FrameGeom g = p.geoms[frame];
+        off = (c == 0) ? (double)g.off_y : (double)g.off_x;
+        scaler = g.scaler;
+        v2 = __ddiv_rn(__dsub_rn(jb, off), scaler);
+        v2 = __dadd_rn(v2, (c == 0) ? (double)g.y : (double)g.x);
+      } else {
+        v2 = __ddiv_rn(__dsub_rn(jb, off), scaler);
+      }
+      p.out2d[(frame * kJoints + joint) * 2 + c] = v2;
+      if (p.packed != nullptr) p.packed[(frame * kJoints + joint) * 5 + c] = v2;
+    }
     const int items = 12 * ns;
     if (tid < items) {
       const int sc = tid % ns;
@@ -1011,29 +1059,15 @@ __global__ void __launch_bounds__(kPostMaxThreads, 2) postprocess_kernel(const _
     const volatile float* raw = p.j3_raw + frame * kJoints * 3;
     float v = __fsub_rn(raw[j * 3 + c], raw[kRootJoint * 3 + c]);  // joints_3d -= joints_3d[14] (utils.py:218)
     if (p.filters_on) {
-      FilterState st = p.st3d[((size_t)p.stream_ids[frame] * kJoints + j) * 3 + c];
-      v = __double2float_rn(oef_step(st, p.cfg3d, (double)v, p.t3d[frame], true));
-      p.st3d[((size_t)p.stream_ids[frame] * kJoints + j) * 3 + c] = st;
+      const size_t si = ((size_t)p.stream_ids[frame] * kJoints + j) * 3 + c;
+      FilterState st = p.st3d[si];
+      const volatile double* pr = p.prep3 + ((size_t)(frame * kJoints + j) * 3 + c) * 3;  // written by joint j's block
+      const FilterPrep f = {pr[0], pr[1], pr[2]};
+      v = __double2float_rn(oef_finish(st, p.cfg3d, f, (double)v, p.t3d[frame], true));
+      p.st3d[si] = st;
     }
     p.out3d[(frame * kJoints + j) * 3 + c] = v;
     if (p.packed != nullptr) p.packed[(frame * kJoints + j) * 5 + 2 + c] = (double)v;
-  }
-  for (int i = tid; i < kJoints * 2; i += nthreads) {
-    const int j = i >> 1, c = i & 1;
-    const volatile double* jb = p.j2_box + frame * kJoints * 2;
-    double off = (c == 0) ? (double)p.off_y : (double)p.off_x, scaler = p.scaler;  // estimator.py:138-139
-    double v2 = 0.0;
-    if (p.geoms != nullptr) {
-      const FrameGeom g = p.geoms[frame];
-      off = (c == 0) ? (double)g.off_y : (double)g.off_x;
-      scaler = g.scaler;
-      v2 = __ddiv_rn(__dsub_rn(jb[j * 2 + c], off), scaler);
-      v2 = __dadd_rn(v2, (c == 0) ? (double)g.y : (double)g.x);  // joints_2d[:, 0] += y; [:, 1] += x (run_estimator.py:104-105)
-    } else {
-      v2 = __ddiv_rn(__dsub_rn(jb[j * 2 + c], off), scaler);
-    }
-    p.out2d[(frame * kJoints + j) * 2 + c] = v2;
-    if (p.packed != nullptr) p.packed[(frame * kJoints + j) * 5 + c] = v2;
   }
   POST_TRACE(10);
   if (p.trace != nullptr && tid == 0) p.trace[(size_t)blockIdx.x * 16 + 12] = (unsigned long long)clock64();

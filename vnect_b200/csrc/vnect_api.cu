@@ -73,6 +73,7 @@ struct vnect_handle {
   float* d_j3_raw = nullptr;
   int* d_raw_argmax = nullptr;
   unsigned int* d_counter = nullptr;
+  double* d_prep3 = nullptr;   // [max_frames][21][3][3]: see PostParams::prep3
   double* d_filter_scratch = nullptr;
   // Two submission lanes: each owns its input staging, per-call meta (pinned host + device) and result buffers, so
   // the H2D copy of batch k+1 (copy stream) overlaps the kernels of batch k (compute stream).
@@ -606,6 +607,7 @@ static int alloc_prepost(vnect_t* h) {
   if ((rc = dev_alloc(h, &h->d_j3_raw, (size_t)mf * kJoints * 3))) return rc;
   if ((rc = dev_alloc(h, &h->d_raw_argmax, (size_t)mf * kJoints * 2))) return rc;
   if ((rc = dev_alloc(h, &h->d_counter, mf))) return rc;
+  if ((rc = dev_alloc(h, &h->d_prep3, (size_t)mf * kJoints * 9))) return rc;
   if (getenv("VNECT_B200_POST_TRACE") && (rc = dev_alloc(h, &h->d_post_trace, (size_t)mf * kJoints * 16))) return rc;
   if ((rc = dev_alloc(h, &h->d_filter_scratch, 64))) return rc;
   if ((rc = dev_alloc(h, &h->d_st_ang, (size_t)ms * 8))) return rc;
@@ -1028,6 +1030,7 @@ static int run_postprocess(vnect_t* h, int n_frames, double scaler, int off_x, i
   p.scaler = scaler; p.off_x = off_x; p.off_y = off_y;
   p.j2_box = h->d_j2_box; p.j3_raw = h->d_j3_raw; p.raw_argmax = h->d_raw_argmax;
   p.frame_counter = h->d_counter;
+  p.prep3 = h->d_prep3;
   p.out2d = dev_out2d; p.out3d = dev_out3d;
   p.packed = h->d_packed;
   p.nonfinite = guard ? h->d_nonfinite : nullptr;  // caller-supplied maps (vnect_postprocess) are taken as they are
@@ -1741,6 +1744,14 @@ int vnect_time_prepost(vnect_t* h, int32_t n_frames, int32_t reps, float* pre_ms
       fprintf(stderr, "  block duration p50 %.2f p90 %.2f p99 %.2f max %.2f us; surviving quads per block p50 %llu p90 %llu p99 %llu max %llu\n",
               dur[nb / 2], dur[nb * 9 / 10], dur[nb * 99 / 100], dur[nb - 1], nqs[nb / 2], nqs[nb * 9 / 10], nqs[nb * 99 / 100], nqs[nb - 1]);
     }
+    {  // inside "exact+reduce": the exact cells are in shared memory (blocks on the few-quads path only)
+      double sum = 0; int cnt = 0;
+      for (int b = 0; b < nb; ++b) {
+        const unsigned long long v = tr[(size_t)b * 16 + 14], s0 = tr[(size_t)b * 16 + 5];
+        if (v >= s0 && v <= t1) { sum += (v - s0) * 1e-3; ++cnt; }
+      }
+      fprintf(stderr, "  exact cells ready %.2f us after the marking barrier (%d blocks)\n", cnt ? sum / cnt : 0.0, cnt);
+    }
     for (int k = 1; k <= 10; ++k) {
       double sum = 0, mx = 0; int cnt = 0;
       for (int b = 0; b < nb; ++b) {
@@ -1781,6 +1792,14 @@ int vnect_time_prepost(vnect_t* h, int32_t n_frames, int32_t reps, float* pre_ms
       std::sort(nqs.begin(), nqs.end());
       fprintf(stderr, "  block duration p50 %.2f p90 %.2f p99 %.2f max %.2f us; surviving quads per block p50 %llu p90 %llu p99 %llu max %llu\n",
               dur[nb / 2], dur[nb * 9 / 10], dur[nb * 99 / 100], dur[nb - 1], nqs[nb / 2], nqs[nb * 9 / 10], nqs[nb * 99 / 100], nqs[nb - 1]);
+    }
+    {  // inside "exact+reduce": the exact cells are in shared memory (blocks on the few-quads path only)
+      double sum = 0; int cnt = 0;
+      for (int b = 0; b < nb; ++b) {
+        const unsigned long long v = tr[(size_t)b * 16 + 14], s0 = tr[(size_t)b * 16 + 5];
+        if (v >= s0 && v <= t1) { sum += (v - s0) * 1e-3; ++cnt; }
+      }
+      fprintf(stderr, "  exact cells ready %.2f us after the marking barrier (%d blocks)\n", cnt ? sum / cnt : 0.0, cnt);
     }
     for (int k = 1; k <= 10; ++k) {
       double sum = 0, mx = 0; int cnt = 0;
