@@ -76,6 +76,7 @@ struct ConvGemmParams {
   int OH, OW;    // output grid
   int oys, oxs;  // output pixel = (y*oys + py, x*oxs + px)
   int decimate;  // 1: only rows with even (y, x) are stored, at (y/2, x/2) -- feeds the stride-2 1x1 convs
+  int im2col;    // 1: flat-row 3x3 conv whose A operand comes through an im2col tensor map (tap_dx / tap_dy = filter offsets 0..2)
 };
 
 // CG = 2: CTA pair (cluster of two SMs) working on one 256-row x BLOCK_N tile with tcgen05.mma.cta_group::2.  Each CTA
@@ -280,6 +281,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           continue;
         }
         const int b_row = ph * p.b_rows_per_phase + n_tile * BLOCK_N + cta_rank * (BLOCK_N / CG);
+        // im2col: the tile is 128 consecutive output pixels of the batch; base pixel of the first one (SAME padding 1)
+        int iw = 0, ih = 0, in_ = 0;
+        if (p.im2col) {
+          const int px0 = m_tile * kBlockM;
+          in_ = px0 / (p.H * p.W);
+          const int rem = px0 - in_ * p.H * p.W;
+          ih = rem / p.W;
+          iw = rem - ih * p.W - 1;
+          ih -= 1;
+        }
         for (int t = 0; t < p.taps; ++t) {
           const int ti = ph * p.taps + t;
           const int ax = cx * p.in_stride + p.tap_dx[ti], ay = cy * p.in_stride + p.tap_dy[ti], ap = p.tap_dp[ti];
@@ -289,11 +300,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
               if constexpr (CG == 2) {  // both CTAs' bytes are counted on the leader's barrier
                 if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * p.stage_tx_bytes);
-                tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
+                if (p.im2col) tma_load_im2col_4d_pair(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, iw, ih, in_, p.tap_dx[ti], p.tap_dy[ti]);
+                else tma_load_5d_pair(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
                 tma_load_2d_pair(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
               } else {
                 mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx_bytes);
-                tma_load_5d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
+                if (p.im2col) tma_load_im2col_4d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, iw, ih, in_, p.tap_dx[ti], p.tap_dy[ti]);
+                else tma_load_5d(sa, &tmap_a, &full_bar[stage], cb * BLOCK_K, ax, ay, ap, cn);
                 if constexpr (!BRES)
                   tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, &full_bar[stage], (t * p.cblocks + cb) * BLOCK_K, b_row);
               }

@@ -32,6 +32,40 @@ inline PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                     CUtensorMapFloatOOBfill);
+
+// NHWC fp16 activation [NB, H, W, C] as an im2col tensor map of a 3x3 'SAME' stride-1 conv: a load delivers 128
+// consecutive output pixels (walking on across rows and images) x 64 channels at one filter offset, 128B-swizzled.
+// Base pixels run over [-1, W - 2] x [-1, H - 2] (lower corner -pad, upper corner pad - (filter - 1)).
+inline bool encode_tmap_im2col_3x3(CUtensorMap* m, const void* ptr, int NB, int H, int W, int C, std::string* err) {
+  static PFN_encodeIm2col fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+      if (err) *err = "cuTensorMapEncodeIm2col entry point unavailable";
+      return false;
+    }
+    fn = reinterpret_cast<PFN_encodeIm2col>(p);
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+  const int lower[2] = {-1, -1}, upper[2] = {-1, -1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper, 64, kBlockM,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeIm2col failed (" + std::to_string((int)r) + ")";
+    return false;
+  }
+  return true;
+}
+
 inline bool encode_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                         const uint32_t* box, int swz_bytes, std::string* err, const uint32_t* elem_strides = nullptr) {
   PFN_encodeTiled enc = get_encode_tiled();
@@ -104,6 +138,8 @@ struct ConvSpec {
   int b_resident = 0;
   // 1: 3x3 stride-1 conv through one halo patch per channel block (8 x 16 pixel tiles, conv_gemm.cuh HALO)
   int halo = 0;
+  // 1: 3x3 stride-1 conv on flat pixel rows through an im2col tensor map (no tile row wasted on small images)
+  int im2col = 0;
   // fused block tail (block_tail.cuh): this 1x1 conv (+ residual / folded shortcut) also feeds a second 1x1 conv
   // Y = relu(out * W2^T + bias2) of n2 output channels; w2 is [n2][n_pad] fp16 K-major, out2 NHWC [.., n2] on the
   // same pixel grid as `out`.  Needs block_n = 256 on CTA pairs and a TMA epilogue.
@@ -228,6 +264,31 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     box[0] = block_k; box[1] = kBlockM; box[2] = 1; box[3] = 1; box[4] = 1;
     k_total = s.cin_pad + s.cin2_pad;
     p.cblocks2 = s.cin2_pad / block_k;
+  } else if (s.kind == CONV_3x3 && s.im2col) {
+    if (s.halo || s.in_stride != 1 || s.cin_pad % 64 != 0 || swz != 128) {
+      if (err) *err = "the im2col path is the plain stride-1 3x3 conv with 128B-swizzled 64-channel K blocks";
+      return false;
+    }
+    p.mode = 0;
+    p.im2col = 1;
+    p.taps = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {  // filter offsets from the base pixel, not displacements from the output pixel
+        p.tap_dy[ky * 3 + kx] = (signed char)ky;
+        p.tap_dx[ky * 3 + kx] = (signed char)kx;
+        p.tap_dp[ky * 3 + kx] = 0;
+      }
+    p.cblocks = s.cin_pad / block_k;
+    p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
+    p.tw = kBlockM;
+    p.th = 1;
+    p.tiles_x = p.tiles_y = 1;
+    // dims / box describe the A tile for the byte count below; the map itself is built by encode_tmap_im2col_3x3
+    dims[0] = s.cin_pad; dims[1] = p.M; dims[2] = 1; dims[3] = 1; dims[4] = 1;
+    strides[0] = (uint64_t)s.cin_pad * 2;
+    strides[1] = strides[2] = strides[3] = (uint64_t)s.cin_pad * 2 * p.M;
+    box[0] = block_k; box[1] = kBlockM; box[2] = 1; box[3] = 1; box[4] = 1;
+    k_total = 9 * s.cin_pad;
   } else if (s.kind == CONV_3x3 || s.kind == CONV_DECONV4 || spatial1) {
     p.mode = 1;
     if (s.halo) {
@@ -315,7 +376,9 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     if (err) *err = "resident weights need a single-tile 64-column EPI_TMA layer of at most 9 K blocks";
     return false;
   }
-  if (!encode_tmap(&L->tmap_a, s.in, 5, dims, strides, box, swz, err, a_stride != 1 ? estr : nullptr)) return false;
+  if (p.im2col) {
+    if (!encode_tmap_im2col_3x3(&L->tmap_a, s.in, s.NB, s.H, s.W, s.cin_pad, err)) return false;
+  } else if (!encode_tmap(&L->tmap_a, s.in, 5, dims, strides, box, swz, err, a_stride != 1 ? estr : nullptr)) return false;
   uint64_t bd[2] = {(uint64_t)k_total, (uint64_t)p.phases * s.n_pad};
   uint64_t bs[1] = {(uint64_t)k_total * 2};
   uint32_t bb[2] = {(uint32_t)block_k, (uint32_t)(s.block_n / s.cg)};

@@ -151,6 +151,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// im2col-mode load of a 4-D NHWC tensor map (cuTensorMapEncodeIm2col): `pixelsPerColumn` consecutive OUTPUT pixels
+// starting at base pixel (w, h) of image n -- the walk continues into the next row and the next image -- each read at
+// filter offset (ow, oh) from its base pixel, out-of-image taps zero-filled: one K block of an implicit-GEMM 3x3 conv
+// whose GEMM rows are flat pixel indices, so no row of a 128-row tile is wasted on a 23 x 23 image.
+__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h,
+                                                   int n, int ow, int oh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2], {%7, %8};" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+      "h"(static_cast<uint16_t>(ow)), "h"(static_cast<uint16_t>(oh))
+      : "memory");
+}
 // ---------------------------------------------------------------- CTA pair (cta_group::2): two SMs, one 256-row MMA
 // The even CTA of the pair (cluster rank 0) is the leader: it issues the MMAs and owns the barriers the pair shares.
 // Shared-window addresses carry the CTA rank in bit 24, so clearing it names the same offset in the leader's smem.
@@ -182,6 +195,15 @@ __device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* m
       "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
       "%6, %7}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_pair(void* dst, const CUtensorMap* m, uint64_t* bar, int c, int w,
+                                                        int h, int n, int ow, int oh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c), "r"(w), "r"(h), "r"(n),
+      "h"(static_cast<uint16_t>(ow)), "h"(static_cast<uint16_t>(oh))
       : "memory");
 }
 // executed by the same warp of BOTH CTAs of the pair, with the same smem slot offset

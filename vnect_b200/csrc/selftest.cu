@@ -82,6 +82,7 @@ struct Case {
   int bres = 0;  // 1: weights resident in smem
   int halo = 0;  // 1: 3x3 conv through halo patches (8 x 16 pixel tiles, nine taps read one smem patch)
   int n2 = 0;    // > 0: fused block tail, second 1x1 conv of n2 channels on this conv's output (block_tail.cuh)
+  int im2col = 0;  // 1: 3x3 conv on flat pixel rows through an im2col tensor map
 };
 
 // reference of the chained conv, from the fp16 X the kernel under test wrote: y[m][col] = relu(sum_c X[m][c] * W2[col][c] + b2[col])
@@ -117,6 +118,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   s.cg = c.cg;
   s.b_resident = c.bres;
   s.halo = c.halo;
+  s.im2col = c.im2col;
   const int phases = c.kind == CONV_DECONV4 ? 4 : 1;
   const int taps = c.kind == CONV_1x1 ? 1 : c.kind == CONV_3x3 ? 9 : c.kind == CONV_DECONV4 ? 4 : 7;
   const int k_total = c.kind == CONV_STEM7 ? 7 * 32 : taps * c.cin_pad + c.cin2;
@@ -220,6 +222,8 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   g.in_stride = c.in_stride;
   g.taps = taps; g.phases = phases; g.k_total = k_total; g.stem_rpp = rpp; g.stem_pitch = pitch;
   memcpy(g.dx, L.p.tap_dx, 16); memcpy(g.dy, L.p.tap_dy, 16); memcpy(g.dp, L.p.tap_dp, 16);
+  if (L.p.im2col)  // the launch holds filter offsets from the base pixel (0..2); the reference wants displacements (-1..1)
+    for (int t = 0; t < 9; ++t) { g.dx[t] = (signed char)(g.dx[t] - 1); g.dy[t] = (signed char)(g.dy[t] - 1); }
   naive_acc_kernel<<<1184, 256>>>(d_in, d_w, d_acc, g, d_in2, c.cin2);
   CK(cudaDeviceSynchronize());
   std::vector<float> h_acc(acc_elems);
@@ -558,6 +562,22 @@ int main(int argc, char** argv) {
     f += run_stem_pool(1, 512, sms);
     f += run_stem_pool(32, 368, sms);
     f += run_stem_pool(128, 368, sms);
+    printf(f ? "SELFTEST FAILED (%d failing cases)\n" : "SELFTEST PASSED (%d failing cases)\n", f);
+    return f ? 1 : 0;
+  }
+  if (argc > 1 && strcmp(argv[1], "im2col") == 0) {  // 3x3 convs at 23 x 23 on flat pixel rows (im2col tensor map) against spatial tiles
+    Case a = {"IM2COL 3x3 256->256 relu 23x23 n64", CONV_3x3, 3, 23, 23, 256, 256, 256, 64, EPI_TMA, true, false, 256, 0};
+    Case b = {"IM2COL PAIR 3x3 256->256 relu 23x23", CONV_3x3, 3, 23, 23, 256, 256, 256, 256, EPI_TMA, true, false, 256, 0};
+    Case c = {"IM2COL PAIR 3x3 512->512 relu 23x23 (odd tile count)", CONV_3x3, 5, 23, 23, 512, 512, 512, 256, EPI_TMA, true, false, 512, 0};
+    Case d = {"IM2COL 3x3 64->64 relu 13x9 n64", CONV_3x3, 2, 13, 9, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0};
+    Case e0 = {"BIG PAIR 3x3 256->256 23x23 nb128 (spatial tiles)", CONV_3x3, 128, 23, 23, 256, 256, 256, 256, EPI_TMA, true, false, 256, 0};
+    Case e1 = {"BIG IM2COL PAIR 3x3 256->256 23x23 nb128", CONV_3x3, 128, 23, 23, 256, 256, 256, 256, EPI_TMA, true, false, 256, 0};
+    Case f0 = {"BIG PAIR 3x3 512->512 23x23 nb128 (spatial tiles)", CONV_3x3, 128, 23, 23, 512, 512, 512, 256, EPI_TMA, true, false, 512, 0};
+    Case f1 = {"BIG IM2COL PAIR 3x3 512->512 23x23 nb128", CONV_3x3, 128, 23, 23, 512, 512, 512, 256, EPI_TMA, true, false, 512, 0};
+    a.im2col = b.im2col = c.im2col = d.im2col = e1.im2col = f1.im2col = 1;
+    b.cg = c.cg = e0.cg = e1.cg = f0.cg = f1.cg = 2;
+    int f = 0;
+    for (Case* k : {&a, &b, &c, &d, &e0, &e1, &f0, &f1}) f += run_case(*k, sms, true);
     printf(f ? "SELFTEST FAILED (%d failing cases)\n" : "SELFTEST PASSED (%d failing cases)\n", f);
     return f ? 1 : 0;
   }

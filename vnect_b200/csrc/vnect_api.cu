@@ -406,6 +406,11 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
   if (halo_on && k == 3 && o.in_stride == 1 && s.epi == EPI_TMA && halo_tiling_ok(OH, OW) &&
       (s.block_n == 64 ? s.cg == 1 : (s.block_n == 128)))
     s.halo = 1;
+  // the other stride-1 3x3 convs (23 x 23 at box size 368: five 23 x 5 tiles fill 529 of 640 GEMM rows) run on flat pixel
+  // rows through an im2col tensor map: every row of a 128-row tile is a real pixel.  Same K order, so the same results.
+  // VNECT_B200_IM2COL=0 turns it off (A/B measurement)
+  static const bool im2col_on = [] { const char* e = getenv("VNECT_B200_IM2COL"); return !(e && atoi(e) == 0); }();
+  if (im2col_on && k == 3 && o.in_stride == 1 && !s.halo && !s.b_resident && cin_pad % 64 == 0) s.im2col = 1;
   Step st;
   st.kind = 0; st.name = scope;
   if (k == 1 && can_chain(s, o, cout)) {
