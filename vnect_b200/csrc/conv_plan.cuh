@@ -39,7 +39,8 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
 
 // NHWC fp16 activation [NB, H, W, C] as an im2col tensor map of a 3x3 'SAME' stride-1 conv: a load delivers 128
 // consecutive output pixels (walking on across rows and images) x 64 channels at one filter offset, 128B-swizzled.
-// Base pixels run over [-1, W - 2] x [-1, H - 2] (lower corner -pad, upper corner pad - (filter - 1)).
+// Base pixels run over [-1, W - 2] x [-1, H - 2] (lower corner -pad, upper corner pad - (filter - 1)).  (With element
+// strides 2 for the even-pixel convs a load delivers fewer bytes than the barrier expects: not used there.)
 inline bool encode_tmap_im2col_3x3(CUtensorMap* m, const void* ptr, int NB, int H, int W, int C, std::string* err) {
   static PFN_encodeIm2col fn = nullptr;
   if (!fn) {
@@ -264,20 +265,39 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     box[0] = block_k; box[1] = kBlockM; box[2] = 1; box[3] = 1; box[4] = 1;
     k_total = s.cin_pad + s.cin2_pad;
     p.cblocks2 = s.cin2_pad / block_k;
-  } else if (s.kind == CONV_3x3 && s.im2col) {
+  } else if ((s.kind == CONV_3x3 || s.kind == CONV_DECONV4) && s.im2col) {
     if (s.halo || s.in_stride != 1 || s.cin_pad % 64 != 0 || swz != 128) {
-      if (err) *err = "the im2col path is the plain stride-1 3x3 conv with 128B-swizzled 64-channel K blocks";
+      if (err) *err = "the im2col path is the plain stride-1 3x3 conv (or the 4x4/2 transposed conv) with 128B-swizzled 64-channel K blocks";
       return false;
     }
     p.mode = 0;
     p.im2col = 1;
-    p.taps = 9;
-    for (int ky = 0; ky < 3; ++ky)
-      for (int kx = 0; kx < 3; ++kx) {  // filter offsets from the base pixel, not displacements from the output pixel
-        p.tap_dy[ky * 3 + kx] = (signed char)ky;
-        p.tap_dx[ky * 3 + kx] = (signed char)kx;
-        p.tap_dp[ky * 3 + kx] = 0;
+    if (s.kind == CONV_3x3) {
+      p.taps = 9;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {  // filter offsets from the base pixel, not displacements from the output pixel
+          p.tap_dy[ky * 3 + kx] = (signed char)ky;
+          p.tap_dx[ky * 3 + kx] = (signed char)kx;
+          p.tap_dp[ky * 3 + kx] = 0;
+        }
+    } else {  // the four output phases of the transposed conv, each a 2x2-tap conv inside the same 3x3 neighbourhood
+      p.taps = 4;
+      p.phases = 4;
+      p.oys = p.oxs = 2;
+      p.OH = 2 * s.H;
+      p.OW = 2 * s.W;
+      for (int ph = 0; ph < 4; ++ph) {
+        const int py = ph >> 1, px = ph & 1;
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            const int dy = py == 0 ? (a == 0 ? 0 : -1) : (a == 0 ? 1 : 0);
+            const int dx = px == 0 ? (b == 0 ? 0 : -1) : (b == 0 ? 1 : 0);
+            p.tap_dy[ph * 4 + a * 2 + b] = (signed char)(dy + 1);
+            p.tap_dx[ph * 4 + a * 2 + b] = (signed char)(dx + 1);
+            p.tap_dp[ph * 4 + a * 2 + b] = 0;
+          }
       }
+    }
     p.cblocks = s.cin_pad / block_k;
     p.num_m_tiles = (p.M + kBlockM - 1) / kBlockM;
     p.tw = kBlockM;
@@ -288,7 +308,7 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     strides[0] = (uint64_t)s.cin_pad * 2;
     strides[1] = strides[2] = strides[3] = (uint64_t)s.cin_pad * 2 * p.M;
     box[0] = block_k; box[1] = kBlockM; box[2] = 1; box[3] = 1; box[4] = 1;
-    k_total = 9 * s.cin_pad;
+    k_total = p.taps * s.cin_pad;
   } else if (s.kind == CONV_3x3 || s.kind == CONV_DECONV4 || spatial1) {
     p.mode = 1;
     if (s.halo) {

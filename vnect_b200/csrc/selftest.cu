@@ -223,7 +223,7 @@ static int run_case(const Case& c, int num_sms, bool timing) {
   g.taps = taps; g.phases = phases; g.k_total = k_total; g.stem_rpp = rpp; g.stem_pitch = pitch;
   memcpy(g.dx, L.p.tap_dx, 16); memcpy(g.dy, L.p.tap_dy, 16); memcpy(g.dp, L.p.tap_dp, 16);
   if (L.p.im2col)  // the launch holds filter offsets from the base pixel (0..2); the reference wants displacements (-1..1)
-    for (int t = 0; t < 9; ++t) { g.dx[t] = (signed char)(g.dx[t] - 1); g.dy[t] = (signed char)(g.dy[t] - 1); }
+    for (int t = 0; t < 16; ++t) { g.dx[t] = (signed char)(g.dx[t] - 1); g.dy[t] = (signed char)(g.dy[t] - 1); }
   naive_acc_kernel<<<1184, 256>>>(d_in, d_w, d_acc, g, d_in2, c.cin2);
   CK(cudaDeviceSynchronize());
   std::vector<float> h_acc(acc_elems);
@@ -574,10 +574,14 @@ int main(int argc, char** argv) {
     Case e1 = {"BIG IM2COL PAIR 3x3 256->256 23x23 nb128", CONV_3x3, 128, 23, 23, 256, 256, 256, 256, EPI_TMA, true, false, 256, 0};
     Case f0 = {"BIG PAIR 3x3 512->512 23x23 nb128 (spatial tiles)", CONV_3x3, 128, 23, 23, 512, 512, 512, 256, EPI_TMA, true, false, 512, 0};
     Case f1 = {"BIG IM2COL PAIR 3x3 512->512 23x23 nb128", CONV_3x3, 128, 23, 23, 512, 512, 512, 256, EPI_TMA, true, false, 512, 0};
-    a.im2col = b.im2col = c.im2col = d.im2col = e1.im2col = f1.im2col = 1;
-    b.cg = c.cg = e0.cg = e1.cg = f0.cg = f1.cg = 2;
+    Case g0 = {"deconv4x4s2 256->192 head 23x23 (spatial tiles)", CONV_DECONV4, 3, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false, 128, 0};
+    Case g1 = {"IM2COL deconv4x4s2 256->192 head 23x23", CONV_DECONV4, 3, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false, 128, 0};
+    Case h0 = {"BIG PAIR deconv4x4s2 256->192 head 23x23 nb128 (spatial tiles)", CONV_DECONV4, 128, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false, 128, 0};
+    Case h1 = {"BIG IM2COL PAIR deconv4x4s2 256->192 head 23x23 nb128", CONV_DECONV4, 128, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false, 128, 0};
+    a.im2col = b.im2col = c.im2col = d.im2col = e1.im2col = f1.im2col = g1.im2col = h1.im2col = 1;
+    b.cg = c.cg = e0.cg = e1.cg = f0.cg = f1.cg = h0.cg = h1.cg = 2;
     int f = 0;
-    for (Case* k : {&a, &b, &c, &d, &e0, &e1, &f0, &f1}) f += run_case(*k, sms, true);
+    for (Case* k : {&a, &b, &c, &d, &e0, &e1, &f0, &f1, &g0, &g1, &h0, &h1}) f += run_case(*k, sms, true);
     printf(f ? "SELFTEST FAILED (%d failing cases)\n" : "SELFTEST PASSED (%d failing cases)\n", f);
     return f ? 1 : 0;
   }
@@ -672,6 +676,19 @@ int main(int argc, char** argv) {
     for (Case* c : {&t1, &t2, &t3, &t4, &t5, &t6, &t7, &t8}) {
       c->cg = 2;
       fails += run_case(*c, sms, true);
+    }
+  }
+  {  // 3x3 / transposed convs on flat pixel rows through the im2col tensor map (single CTAs, pairs, odd tile counts)
+    Case a = {"IM2COL 3x3 256->256 relu 23x23 n64", CONV_3x3, 3, 23, 23, 256, 256, 256, 64, EPI_TMA, true, false, 256, 0};
+    Case b = {"IM2COL PAIR 3x3 256->256 relu 23x23", CONV_3x3, 3, 23, 23, 256, 256, 256, 256, EPI_TMA, true, false, 256, 0};
+    Case c = {"IM2COL PAIR 3x3 512->512 relu 23x23 (odd tile count)", CONV_3x3, 5, 23, 23, 512, 512, 512, 256, EPI_TMA, true, false, 512, 0};
+    Case d = {"IM2COL 3x3 64->64 relu 13x9 n64", CONV_3x3, 2, 13, 9, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0};
+    Case e = {"IM2COL deconv4x4s2 256->192 head 23x23", CONV_DECONV4, 3, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false, 128, 0};
+    Case g = {"IM2COL PAIR deconv4x4s2 256->192 head 23x23", CONV_DECONV4, 3, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false, 128, 0};
+    b.cg = c.cg = g.cg = 2;
+    for (Case* k : {&a, &b, &c, &d, &e, &g}) {
+      k->im2col = 1;
+      fails += run_case(*k, sms, true);
     }
   }
   fails += run_stem_pool(2, 368, sms);
