@@ -288,8 +288,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           in_ = px0 / (p.H * p.W);
           const int rem = px0 - in_ * p.H * p.W;
           ih = rem / p.W;
-          iw = rem - ih * p.W - 1;
-          ih -= 1;
+          iw = (rem - ih * p.W) * p.in_stride - 1;  // in_stride 2: the conv is evaluated at every second pixel of its input
+          ih = ih * p.in_stride - 1;
         }
         for (int t = 0; t < p.taps; ++t) {
           const int ti = ph * p.taps + t;

@@ -39,9 +39,10 @@ typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32
 
 // NHWC fp16 activation [NB, H, W, C] as an im2col tensor map of a 3x3 'SAME' stride-1 conv: a load delivers 128
 // consecutive output pixels (walking on across rows and images) x 64 channels at one filter offset, 128B-swizzled.
-// Base pixels run over [-1, W - 2] x [-1, H - 2] (lower corner -pad, upper corner pad - (filter - 1)).  (With element
-// strides 2 for the even-pixel convs a load delivers fewer bytes than the barrier expects: not used there.)
-inline bool encode_tmap_im2col_3x3(CUtensorMap* m, const void* ptr, int NB, int H, int W, int C, std::string* err) {
+// Base pixels run over [-1, W - 2] x [-1, H - 2] (lower corner -pad, upper corner pad - (filter - 1)), in steps of
+// `stride` (element strides of the map) for a conv evaluated at every stride-th pixel of the [NB, H, W, C] tensor: a
+// load still delivers 128 pixels (measured with a probe: W = 14, stride 2 -> 7 pixels per row, then the next row).
+inline bool encode_tmap_im2col_3x3(CUtensorMap* m, const void* ptr, int NB, int H, int W, int C, std::string* err, int stride = 1) {
   static PFN_encodeIm2col fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -56,7 +57,7 @@ inline bool encode_tmap_im2col_3x3(CUtensorMap* m, const void* ptr, int NB, int 
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)NB};
   const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
   const int lower[2] = {-1, -1}, upper[2] = {-1, -1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper, 64, kBlockM,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -266,7 +267,7 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     k_total = s.cin_pad + s.cin2_pad;
     p.cblocks2 = s.cin2_pad / block_k;
   } else if ((s.kind == CONV_3x3 || s.kind == CONV_DECONV4) && s.im2col) {
-    if (s.halo || s.in_stride != 1 || s.cin_pad % 64 != 0 || swz != 128) {
+    if (s.halo || (s.in_stride != 1 && s.kind != CONV_3x3) || s.cin_pad % 64 != 0 || swz != 128) {
       if (err) *err = "the im2col path is the plain stride-1 3x3 conv (or the 4x4/2 transposed conv) with 128B-swizzled 64-channel K blocks";
       return false;
     }
@@ -386,7 +387,7 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     box[0] = 32; box[1] = p.tw; box[2] = p.th; box[3] = 1; box[4] = 1;
     k_total = 7 * 32;
   }
-  const int a_stride = (s.kind == CONV_STEM7) ? 1 : s.in_stride;
+  const int a_stride = (s.kind == CONV_STEM7 || p.im2col) ? 1 : s.in_stride;  // an im2col load is 128 pixels whatever the stride
   // per CTA: its A rows plus its share of the B tile (half of it in a CTA pair; nothing when the weights are resident)
   p.stage_tx_bytes = (uint32_t)(box[0] * (box[1] / a_stride) * (box[2] / a_stride) * 2 +
                                 (s.b_resident ? 0u : (uint32_t)(s.block_n / s.cg) * block_k * 2));
@@ -397,7 +398,7 @@ inline bool build_conv(const ConvSpec& s, int num_sms, ConvLaunch* L, std::strin
     return false;
   }
   if (p.im2col) {
-    if (!encode_tmap_im2col_3x3(&L->tmap_a, s.in, s.NB, s.H, s.W, s.cin_pad, err)) return false;
+    if (!encode_tmap_im2col_3x3(&L->tmap_a, s.in, s.NB, s.H * s.in_stride, s.W * s.in_stride, s.cin_pad, err, s.in_stride)) return false;
   } else if (!encode_tmap(&L->tmap_a, s.in, 5, dims, strides, box, swz, err, a_stride != 1 ? estr : nullptr)) return false;
   uint64_t bd[2] = {(uint64_t)k_total, (uint64_t)p.phases * s.n_pad};
   uint64_t bs[1] = {(uint64_t)k_total * 2};

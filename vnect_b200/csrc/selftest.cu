@@ -574,6 +574,18 @@ int main(int argc, char** argv) {
     Case e1 = {"BIG IM2COL PAIR 3x3 256->256 23x23 nb128", CONV_3x3, 128, 23, 23, 256, 256, 256, 256, EPI_TMA, true, false, 256, 0};
     Case f0 = {"BIG PAIR 3x3 512->512 23x23 nb128 (spatial tiles)", CONV_3x3, 128, 23, 23, 512, 512, 512, 256, EPI_TMA, true, false, 512, 0};
     Case f1 = {"BIG IM2COL PAIR 3x3 512->512 23x23 nb128", CONV_3x3, 128, 23, 23, 512, 512, 512, 256, EPI_TMA, true, false, 512, 0};
+    Case i0 = {"S2 3x3 64->64 relu 92->46 (spatial tiles)", CONV_3x3, 2, 46, 46, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0, 2, 1};
+    Case i1 = {"IM2COL S2 3x3 64->64 relu 92->46", CONV_3x3, 2, 46, 46, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0, 2, 1};
+    Case i2 = {"IM2COL S2 3x3 128->128 relu 46->23", CONV_3x3, 3, 23, 23, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0, 2, 1};
+    Case j0 = {"BIG S2 3x3 64->64 92->46 nb128 (spatial tiles)", CONV_3x3, 128, 46, 46, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0, 2, 1};
+    Case j1 = {"BIG IM2COL S2 3x3 64->64 92->46 nb128", CONV_3x3, 128, 46, 46, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0, 2, 1};
+    Case j2 = {"BIG S2 PAIR 3x3 128->128 46->23 nb128 (spatial tiles)", CONV_3x3, 128, 23, 23, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0, 2, 1};
+    Case j3 = {"BIG IM2COL S2 PAIR 3x3 128->128 46->23 nb128", CONV_3x3, 128, 23, 23, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0, 2, 1};
+    Case j4 = {"BIG BRES S2 3x3 64->64 92->46 nb128 (spatial tiles, resident weights)", CONV_3x3, 128, 46, 46, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0, 2, 1};
+    Case j5 = {"BIG IM2COL BRES S2 3x3 64->64 92->46 nb128", CONV_3x3, 128, 46, 46, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0, 2, 1};
+    i1.im2col = i2.im2col = j1.im2col = j3.im2col = j5.im2col = 1;
+    j2.cg = j3.cg = 2;
+    j4.bres = j5.bres = 1;
     Case g0 = {"deconv4x4s2 256->192 head 23x23 (spatial tiles)", CONV_DECONV4, 3, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false, 128, 0};
     Case g1 = {"IM2COL deconv4x4s2 256->192 head 23x23", CONV_DECONV4, 3, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false, 128, 0};
     Case h0 = {"BIG PAIR deconv4x4s2 256->192 head 23x23 nb128 (spatial tiles)", CONV_DECONV4, 128, 23, 23, 256, 192, 191, 192, EPI_DECONV_HEAD, true, false, 128, 0};
@@ -581,7 +593,7 @@ int main(int argc, char** argv) {
     a.im2col = b.im2col = c.im2col = d.im2col = e1.im2col = f1.im2col = g1.im2col = h1.im2col = 1;
     b.cg = c.cg = e0.cg = e1.cg = f0.cg = f1.cg = h0.cg = h1.cg = 2;
     int f = 0;
-    for (Case* k : {&a, &b, &c, &d, &e0, &e1, &f0, &f1, &g0, &g1, &h0, &h1}) f += run_case(*k, sms, true);
+    for (Case* k : {&a, &b, &c, &d, &e0, &e1, &f0, &f1, &g0, &g1, &h0, &h1, &i0, &i1, &i2, &j0, &j1, &j2, &j3, &j4, &j5}) f += run_case(*k, sms, true);
     printf(f ? "SELFTEST FAILED (%d failing cases)\n" : "SELFTEST PASSED (%d failing cases)\n", f);
     return f ? 1 : 0;
   }

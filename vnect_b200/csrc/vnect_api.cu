@@ -410,7 +410,8 @@ static int add_conv(vnect_t* h, const std::string& scope, int k, const std::stri
   // rows through an im2col tensor map: every row of a 128-row tile is a real pixel.  Same K order, so the same results.
   // VNECT_B200_IM2COL=0 turns it off (A/B measurement)
   static const bool im2col_on = [] { const char* e = getenv("VNECT_B200_IM2COL"); return !(e && atoi(e) == 0); }();
-  if (im2col_on && k == 3 && o.in_stride == 1 && !s.halo && !s.b_resident && cin_pad % 64 == 0) s.im2col = 1;
+  // (stride-2 convs included: res3d's 3x3 at 46 -> 23, 31 -> 27 us; the resident-weight 64-channel ones gain nothing)
+  if (im2col_on && k == 3 && !s.halo && !s.b_resident && cin_pad % 64 == 0) s.im2col = 1;
   Step st;
   st.kind = 0; st.name = scope;
   if (k == 1 && can_chain(s, o, cout)) {
