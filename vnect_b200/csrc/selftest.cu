@@ -583,6 +583,12 @@ int main(int argc, char** argv) {
     Case j3 = {"BIG IM2COL S2 PAIR 3x3 128->128 46->23 nb128", CONV_3x3, 128, 23, 23, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0, 2, 1};
     Case j4 = {"BIG BRES S2 3x3 64->64 92->46 nb128 (spatial tiles, resident weights)", CONV_3x3, 128, 46, 46, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0, 2, 1};
     Case j5 = {"BIG IM2COL BRES S2 3x3 64->64 92->46 nb128", CONV_3x3, 128, 46, 46, 64, 64, 64, 64, EPI_TMA, true, false, 64, 0, 2, 1};
+    Case k0 = {"BIG HALO PAIR 3x3 256->128 46x46 nb128 (head)", CONV_3x3, 128, 46, 46, 256, 128, 128, 128, EPI_TMA, true, false, 128, 0};
+    Case k1 = {"BIG IM2COL PAIR 3x3 256->128 46x46 nb128 (head)", CONV_3x3, 128, 46, 46, 256, 128, 128, 128, EPI_TMA, true, false, 128, 0};
+    Case k2 = {"BIG HALO PAIR 3x3 128->128 46x46 nb128", CONV_3x3, 128, 46, 46, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0};
+    Case k3 = {"BIG IM2COL PAIR 3x3 128->128 46x46 nb128", CONV_3x3, 128, 46, 46, 128, 128, 128, 128, EPI_TMA, true, false, 128, 0};
+    k0.halo = k2.halo = 1; k1.im2col = k3.im2col = 1;
+    k0.cg = k1.cg = k2.cg = k3.cg = 2;
     i1.im2col = i2.im2col = j1.im2col = j3.im2col = j5.im2col = 1;
     j2.cg = j3.cg = 2;
     j4.bres = j5.bres = 1;
@@ -593,7 +599,7 @@ int main(int argc, char** argv) {
     a.im2col = b.im2col = c.im2col = d.im2col = e1.im2col = f1.im2col = g1.im2col = h1.im2col = 1;
     b.cg = c.cg = e0.cg = e1.cg = f0.cg = f1.cg = h0.cg = h1.cg = 2;
     int f = 0;
-    for (Case* k : {&a, &b, &c, &d, &e0, &e1, &f0, &f1, &g0, &g1, &h0, &h1, &i0, &i1, &i2, &j0, &j1, &j2, &j3, &j4, &j5}) f += run_case(*k, sms, true);
+    for (Case* k : {&a, &b, &c, &d, &e0, &e1, &f0, &f1, &g0, &g1, &h0, &h1, &i0, &i1, &i2, &j0, &j1, &j2, &j3, &j4, &j5, &k0, &k1, &k2, &k3}) f += run_case(*k, sms, true);
     printf(f ? "SELFTEST FAILED (%d failing cases)\n" : "SELFTEST PASSED (%d failing cases)\n", f);
     return f ? 1 : 0;
   }
