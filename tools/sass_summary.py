@@ -19,6 +19,7 @@ blocks = sass.split("Function : ")[1:]
 for name, blk in zip(names, blocks):
     body = blk.split("\n")
     cnt = collections.Counter()
+    tma_forms = collections.Counter()
     first_mma = None
     n_inst = 0
     for i, line in enumerate(body):
@@ -32,11 +33,15 @@ for name, blk in zip(names, blocks):
                 cnt[k] += 1
         if ".2CTA" in op and op.startswith("UTCHMMA"):
             cnt["UTCHMMA.2CTA"] += 1
+        if op.startswith("UTMALDG") or op.startswith("UTMASTG"):
+            tma_forms[op] += 1
         if first_mma is None and op.startswith("UTCHMMA"):
             first_mma = i
     short = name.replace("vnect::", "").replace("CUtensorMap_st, ", "")
     out.append(f"## {short[:150]}")
     out.append(f"   {n_inst} instructions; " + ", ".join(f"{k} {cnt[k]}" for k in KEYS if cnt[k]))
+    if tma_forms:
+        out.append("   TMA forms: " + ", ".join(f"{k} x{v}" for k, v in sorted(tma_forms.items())))
     if first_mma is not None:
         out.append("   around the first tcgen05.mma:")
         for line in body[max(0, first_mma - 6):first_mma + 10]:
